@@ -1,0 +1,250 @@
+// pack.cu -- per-view Gaussian record packing, its VJP (the backward "epilogue"), and the
+// float4-padded texture / texel-gradient staging buffers.
+//
+// pack_kernel    : (mean, scale, quat, opacity, colour, uv map, texture dims; camera) -> 128-byte record
+// epilogue_kernel: per-Gaussian gradient moments (written by the backward rasteriser) -> gradients of
+//                  means / scales / quats / opacity / colour / uv0 / umap / vmap.  No atomics, no zero-fill.
+// Both mirror tests/formulation.py::pack_record / ::epilogue line by line (same names).
+#include "common.cuh"
+
+namespace gstex {
+
+struct PackCamera {
+    Vec3 o;          // camera origin (c2w[:3,3])
+    float Rc[12];    // c2w rows 0..2 (rotation in [0,1,2],[4,5,6],[8,9,10])
+    float vm[12];    // viewmat rows 0..2
+};
+
+__device__ __forceinline__ void load_camera(const float *__restrict__ c2w, const float *__restrict__ viewmat,
+                                            PackCamera &cam) {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        cam.Rc[i] = c2w[i];
+        cam.vm[i] = viewmat[i];
+    }
+    cam.o = mk3(c2w[3], c2w[7], c2w[11]);
+}
+
+struct SurfelFrame {
+    Vec3 a1, a2, a3, d, um, vm_;
+    float c0, b1, b2, bu, bv, k1, k2;
+    Vec3 rc;       // expansion direction (uc, vc, 1)
+    bool exact;    // expansion centre is the exact projection of the mean (constants c1,c2,cu,cv vanish)
+};
+
+__device__ __forceinline__ void make_frame(Vec3 mean, float s1, float s2, float4 quat, Vec3 umap, Vec3 vmap,
+                                           float glob_scale, const PackCamera &cam, SurfelFrame &f) {
+    surfel_axes(quat, f.a1, f.a2, f.a3);
+    f.d = sub3(mean, cam.o);
+    f.um = umap;
+    f.vm_ = vmap;
+    f.c0 = dot3(f.a3, f.d);
+    f.b1 = dot3(f.a1, f.d);
+    f.b2 = dot3(f.a2, f.d);
+    f.bu = dot3(umap, f.d);
+    f.bv = dot3(vmap, f.d);
+    f.k1 = K_SIGMA / (s1 * glob_scale);
+    f.k2 = K_SIGMA / (s2 * glob_scale);
+    const Vec3 mc = rot_apply_t(cam.Rc, f.d);
+    f.exact = false;
+    f.rc = mk3(0.f, 0.f, 1.f);
+    if (mc.z > 1e-4f) {
+        const float uc = mc.x / mc.z, vc = mc.y / mc.z;
+        if (fabsf(uc) < 1e3f && fabsf(vc) < 1e3f) {
+            f.exact = true;
+            f.rc = mk3(uc, vc, 1.f);
+        }
+    }
+}
+
+// w = c0 * a - (a.d) * a3 ; h = Rc^T w   (numerator of a.(delta) as a linear form in the ray)
+__device__ __forceinline__ Vec3 form_vector(const SurfelFrame &f, Vec3 a, float b, const PackCamera &cam) {
+    const Vec3 w = mk3(fmaf(f.c0, a.x, -b * f.a3.x), fmaf(f.c0, a.y, -b * f.a3.y), fmaf(f.c0, a.z, -b * f.a3.z));
+    return rot_apply_t(cam.Rc, w);
+}
+
+__global__ void __launch_bounds__(256) pack_kernel(int n, const float *__restrict__ means,
+                                                   const float *__restrict__ scales, float glob_scale,
+                                                   const float4 *__restrict__ quats,
+                                                   const float *__restrict__ opacities,
+                                                   const float *__restrict__ colors, const float2 *__restrict__ uv0,
+                                                   const float *__restrict__ umap, const float *__restrict__ vmap,
+                                                   const int32_t *__restrict__ texture_dims,
+                                                   const float *__restrict__ viewmat, const float *__restrict__ c2w,
+                                                   float fx, float fy, float cx, float cy,
+                                                   float4 *__restrict__ recs, float2 *__restrict__ mean2d) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    PackCamera cam;
+    load_camera(c2w, viewmat, cam);
+    const Vec3 mean = ld3(means + 3 * g);
+    SurfelFrame f;
+    make_frame(mean, scales[3 * g], scales[3 * g + 1], quats[g], ld3(umap + 3 * g), ld3(vmap + 3 * g), glob_scale,
+               cam, f);
+    const Vec3 h1 = form_vector(f, f.a1, f.b1, cam), h2 = form_vector(f, f.a2, f.b2, cam);
+    const Vec3 hu = form_vector(f, f.um, f.bu, cam), hv = form_vector(f, f.vm_, f.bv, cam);
+    const Vec3 h3 = rot_apply_t(cam.Rc, f.a3);
+    const float ifx = 1.f / fx, ify = 1.f / fy;
+    const float c1 = f.exact ? 0.f : f.k1 * dot3(h1, f.rc), c2 = f.exact ? 0.f : f.k2 * dot3(h2, f.rc);
+    const float cu = f.exact ? 0.f : dot3(hu, f.rc), cv = f.exact ? 0.f : dot3(hv, f.rc);
+    const float c3 = dot3(h3, f.rc);
+    const float2 t0 = uv0[g];
+    float4 *r = recs + (size_t)g * 8;
+    r[0] = make_float4(fmaf(fx, f.rc.x, cx), fmaf(fy, f.rc.y, cy), f.c0, opacities[g]);
+    r[1] = make_float4(f.k1 * h1.x * ifx, f.k1 * h1.y * ify, c1, c3);
+    r[2] = make_float4(f.k2 * h2.x * ifx, f.k2 * h2.y * ify, c2, __int_as_float(g));
+    r[3] = make_float4(h3.x * ifx, h3.y * ify, __int_as_float(texture_dims[3 * g]),
+                       __int_as_float(texture_dims[3 * g + 1]));
+    r[4] = make_float4(hu.x * ifx, hu.y * ify, cu, t0.x);
+    r[5] = make_float4(hv.x * ifx, hv.y * ify, cv, t0.y);
+    r[6] = make_float4(colors[3 * g], colors[3 * g + 1], colors[3 * g + 2], __int_as_float(texture_dims[3 * g + 2]));
+    r[7] = make_float4(f.a3.x, f.a3.y, f.a3.z, 0.f);
+    mean2d[g] = pinhole(fx, fy, cx, cy, xform_point(cam.vm, mean));
+}
+
+__device__ __forceinline__ float put(float old, float v, int accumulate) { return accumulate ? old + v : v; }
+
+__global__ void __launch_bounds__(256) epilogue_kernel(
+    int n, const float *__restrict__ means, const float *__restrict__ scales, float glob_scale,
+    const float4 *__restrict__ quats, const float *__restrict__ umap, const float *__restrict__ vmap,
+    const float *__restrict__ viewmat, const float *__restrict__ c2w, float fx, float fy, float cx, float cy,
+    const float4 *__restrict__ acc, float *__restrict__ v_colors, float *__restrict__ v_opacity,
+    float *__restrict__ v_means, float *__restrict__ v_scales, float4 *__restrict__ v_quats,
+    float2 *__restrict__ v_uv0, float *__restrict__ v_umap, float *__restrict__ v_vmap, int accumulate) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    PackCamera cam;
+    load_camera(c2w, viewmat, cam);
+    const Vec3 mean = ld3(means + 3 * g);
+    const float s1 = scales[3 * g], s2 = scales[3 * g + 1];
+    const float4 quat = quats[g];
+    SurfelFrame f;
+    make_frame(mean, s1, s2, quat, ld3(umap + 3 * g), ld3(vmap + 3 * g), glob_scale, cam, f);
+    const float4 *A = acc + (size_t)g * 8;
+    const float4 q0 = A[0], q1 = A[1], q2 = A[2], q3 = A[3], q4 = A[4], q5 = A[5], q6 = A[6], q7 = A[7];
+    const float ifx = 1.f / fx, ify = 1.f / fy;
+    // dL/dh from the moments of dL/dN:  kappa * (Gx/fx + Gc*uc, Gy/fy + Gc*vc, Gc)
+    auto v_h = [&](float gx, float gy, float gc, float kappa) {
+        return mk3(kappa * fmaf(gc, f.rc.x, gx * ifx), kappa * fmaf(gc, f.rc.y, gy * ify), kappa * gc);
+    };
+    const Vec3 v_w1 = rot_apply(cam.Rc, v_h(q0.x, q0.y, q0.z, f.k1));
+    const Vec3 v_w2 = rot_apply(cam.Rc, v_h(q1.x, q1.y, q1.z, f.k2));
+    const Vec3 v_wu = rot_apply(cam.Rc, v_h(q3.x, q3.y, q3.z, 1.f));
+    const Vec3 v_wv = rot_apply(cam.Rc, v_h(q4.x, q4.y, q4.z, 1.f));
+    Vec3 v_a3 = add3(rot_apply(cam.Rc, v_h(q2.x, q2.y, q2.z, 1.f)), mk3(q6.x, q6.y, q6.z));
+    const float v_c0 = q0.w + dot3(v_w1, f.a1) + dot3(v_w2, f.a2) + dot3(v_wu, f.um) + dot3(v_wv, f.vm_);
+    const float v_b1 = -dot3(v_w1, f.a3), v_b2 = -dot3(v_w2, f.a3);
+    const float v_bu = -dot3(v_wu, f.a3), v_bv = -dot3(v_wv, f.a3);
+    const Vec3 v_a1 = axpy3(f.c0, v_w1, scale3(v_b1, f.d));
+    const Vec3 v_a2 = axpy3(f.c0, v_w2, scale3(v_b2, f.d));
+    const Vec3 v_um = axpy3(f.c0, v_wu, scale3(v_bu, f.d));
+    const Vec3 v_vm = axpy3(f.c0, v_wv, scale3(v_bv, f.d));
+    v_a3 = axpy3(-f.b1, v_w1, v_a3);
+    v_a3 = axpy3(-f.b2, v_w2, v_a3);
+    v_a3 = axpy3(-f.bu, v_wu, v_a3);
+    v_a3 = axpy3(-f.bv, v_wv, v_a3);
+    v_a3 = axpy3(v_c0, f.d, v_a3);
+    Vec3 v_d = scale3(v_b1, f.a1);
+    v_d = axpy3(v_b2, f.a2, v_d);
+    v_d = axpy3(v_bu, f.um, v_d);
+    v_d = axpy3(v_bv, f.vm_, v_d);
+    v_d = axpy3(v_c0, f.a3, v_d);
+    // blur branch: gradient of the projected mean (reference helpers.cuh:155-164, texture.cu:685-692)
+    {
+        const Vec3 pv = xform_point(cam.vm, mean);
+        const float rw = 1.f / (pv.z + 1e-6f);
+        const float gx = fx * q7.x, gy = fy * q7.y;
+        const Vec3 v_pv = mk3(gx * rw, gy * rw, -(gx * pv.x + gy * pv.y) * rw * rw);
+        v_d = add3(v_d, rot_apply_t(cam.vm, v_pv));
+    }
+    // scales: kappa_i = K/(s_i*glob)  =>  dL/ds_i = -(F_i . G_i)/s_i with F_i the record's form coefficients
+    const Vec3 h1 = form_vector(f, f.a1, f.b1, cam), h2 = form_vector(f, f.a2, f.b2, cam);
+    const float c1 = f.exact ? 0.f : f.k1 * dot3(h1, f.rc), c2 = f.exact ? 0.f : f.k2 * dot3(h2, f.rc);
+    const float fg1 = fmaf(f.k1 * h1.x * ifx, q0.x, fmaf(f.k1 * h1.y * ify, q0.y, c1 * q0.z));
+    const float fg2 = fmaf(f.k2 * h2.x * ifx, q1.x, fmaf(f.k2 * h2.y * ify, q1.y, c2 * q1.z));
+    const float4 vq = surfel_axes_vjp(quat, v_a1, v_a2, v_a3);
+
+    v_means[3 * g + 0] = put(v_means[3 * g + 0], v_d.x, accumulate);
+    v_means[3 * g + 1] = put(v_means[3 * g + 1], v_d.y, accumulate);
+    v_means[3 * g + 2] = put(v_means[3 * g + 2], v_d.z, accumulate);
+    v_scales[3 * g + 0] = put(v_scales[3 * g + 0], -fg1 / s1, accumulate);
+    v_scales[3 * g + 1] = put(v_scales[3 * g + 1], -fg2 / s2, accumulate);
+    v_scales[3 * g + 2] = put(v_scales[3 * g + 2], 0.f, accumulate);
+    float4 oq = accumulate ? v_quats[g] : make_float4(0.f, 0.f, 0.f, 0.f);
+    v_quats[g] = make_float4(oq.x + vq.x, oq.y + vq.y, oq.z + vq.z, oq.w + vq.w);
+    float2 ou = accumulate ? v_uv0[g] : make_float2(0.f, 0.f);
+    v_uv0[g] = make_float2(ou.x + q3.w, ou.y + q4.w);
+    v_umap[3 * g + 0] = put(v_umap[3 * g + 0], v_um.x, accumulate);
+    v_umap[3 * g + 1] = put(v_umap[3 * g + 1], v_um.y, accumulate);
+    v_umap[3 * g + 2] = put(v_umap[3 * g + 2], v_um.z, accumulate);
+    v_vmap[3 * g + 0] = put(v_vmap[3 * g + 0], v_vm.x, accumulate);
+    v_vmap[3 * g + 1] = put(v_vmap[3 * g + 1], v_vm.y, accumulate);
+    v_vmap[3 * g + 2] = put(v_vmap[3 * g + 2], v_vm.z, accumulate);
+    v_colors[3 * g + 0] = put(v_colors[3 * g + 0], q5.x, accumulate);
+    v_colors[3 * g + 1] = put(v_colors[3 * g + 1], q5.y, accumulate);
+    v_colors[3 * g + 2] = put(v_colors[3 * g + 2], q5.z, accumulate);
+    v_opacity[g] = put(v_opacity[g], q1.w, accumulate);
+}
+
+// (X,3) -> (X,float4) so that a texel is one aligned 16-byte load / one vector atomic
+__global__ void __launch_bounds__(256) pad_texture_kernel(int64_t num_texels, const float *__restrict__ tex,
+                                                          float4 *__restrict__ tex4) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= num_texels) return;
+    tex4[i] = make_float4(tex[3 * i], tex[3 * i + 1], tex[3 * i + 2], 0.f);
+}
+
+__global__ void __launch_bounds__(256) unpad_texture_grad_kernel(int64_t num_texels, const float4 *__restrict__ g4,
+                                                                 float *__restrict__ v_texture, int accumulate) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= num_texels) return;
+    const float4 g = g4[i];
+    v_texture[3 * i + 0] = put(v_texture[3 * i + 0], g.x, accumulate);
+    v_texture[3 * i + 1] = put(v_texture[3 * i + 1], g.y, accumulate);
+    v_texture[3 * i + 2] = put(v_texture[3 * i + 2], g.z, accumulate);
+}
+
+// ---- host launchers used by raster_forward.cu / raster_backward.cu ----------------------------------
+int launch_pack(int n, const float *means, const float *scales, float glob_scale, const float *quats,
+                const float *opacities, const float *colors, const float *uv0, const float *umap, const float *vmap,
+                const int32_t *texture_dims, const float *viewmat, const float *c2w, float fx, float fy, float cx,
+                float cy, float4 *recs, float2 *mean2d, cudaStream_t s) {
+    if (n == 0) return GSTEX_OK;
+    pack_kernel<<<ceil_div(n, 256), 256, 0, s>>>(n, means, scales, glob_scale, (const float4 *)quats, opacities,
+                                                 colors, (const float2 *)uv0, umap, vmap, texture_dims, viewmat, c2w,
+                                                 fx, fy, cx, cy, recs, mean2d);
+    GSTEX_LAUNCH_OK("pack_kernel");
+    return GSTEX_OK;
+}
+
+int launch_epilogue(int n, const float *means, const float *scales, float glob_scale, const float *quats,
+                    const float *umap, const float *vmap, const float *viewmat, const float *c2w, float fx, float fy,
+                    float cx, float cy, const float4 *acc, float *v_colors, float *v_opacity, float *v_means,
+                    float *v_scales, float *v_quats, float *v_uv0, float *v_umap, float *v_vmap, int accumulate,
+                    cudaStream_t s) {
+    if (n == 0) return GSTEX_OK;
+    epilogue_kernel<<<ceil_div(n, 256), 256, 0, s>>>(n, means, scales, glob_scale, (const float4 *)quats, umap, vmap,
+                                                     viewmat, c2w, fx, fy, cx, cy, acc, v_colors, v_opacity, v_means,
+                                                     v_scales, (float4 *)v_quats, (float2 *)v_uv0, v_umap, v_vmap,
+                                                     accumulate);
+    GSTEX_LAUNCH_OK("epilogue_kernel");
+    return GSTEX_OK;
+}
+
+int launch_pad_texture(int64_t num_texels, const float *tex, float4 *tex4, cudaStream_t s) {
+    if (num_texels == 0) return GSTEX_OK;
+    pad_texture_kernel<<<(unsigned)ceil_div64(num_texels, 256), 256, 0, s>>>(num_texels, tex, tex4);
+    GSTEX_LAUNCH_OK("pad_texture_kernel");
+    return GSTEX_OK;
+}
+
+int launch_unpad_texture_grad(int64_t num_texels, const float4 *g4, float *v_texture, int accumulate,
+                              cudaStream_t s) {
+    if (num_texels == 0) return GSTEX_OK;
+    unpad_texture_grad_kernel<<<(unsigned)ceil_div64(num_texels, 256), 256, 0, s>>>(num_texels, g4, v_texture,
+                                                                                   accumulate);
+    GSTEX_LAUNCH_OK("unpad_texture_grad_kernel");
+    return GSTEX_OK;
+}
+
+}  // namespace gstex

@@ -1,0 +1,173 @@
+// raster.cuh -- device code shared by the forward and backward rasterisers.
+//
+// Per (pixel, Gaussian) pair the kernels evaluate three affine forms in the pixel offset e = p - p_c
+// from the packed record (common.cuh: RecSlot), instead of the reference's per-pixel quat->R,
+// ray-plane intersection and delta chain (texture.cu:161-200):
+//     N1 = c1 + P1.e   N2 = c2 + P2.e   D = c3 + A3.e
+//     l1' = N1/D, l2' = N2/D           (in-plane coordinates, pre-scaled by sqrt(log2(e)/2)/(s*glob))
+//     alpha = min(0.99, opac * 2^-(l1'^2 + l2'^2))        == min(0.99, opac * exp(-sigma))
+//     t = (c0/D) * |R_w(p)|                                (Euclidean ray distance, texture.cu:170-171)
+// That is ~20 flops + 2 MUFU per pair instead of ~100.  tests/formulation.py is the float64 model,
+// tests/test_formulation.py proves it equal to the reference algebra (oracle) incl. all gradients.
+//
+// Forward and backward call the SAME eval_pair() with explicit fmaf / __f*_rn so that both make
+// bit-identical skip decisions.
+#pragma once
+#include <cuda_pipeline.h>
+
+#include "common.cuh"
+
+namespace gstex {
+
+constexpr int RASTER_BATCH = 128;      // Gaussians per shared-memory stage
+constexpr int RASTER_MAX_THREADS = 256;
+constexpr int RASTER_MAX_C = 64;       // generic-channel path (reference texture.cu:102-103)
+
+struct PixelConsts {
+    float px, py;   // pixel centre
+    float rn;       // |R_w|, norm of the un-normalised world ray c2w_rot * ((px-cx)/fx, (py-cy)/fy, 1)
+    float vdep;     // viewmat[2,:3] . normalised ray   (reference texture.cu:74)
+    float eps;      // 1e-6 * rn  (plane-denominator clamp, texture_helpers.cuh:304-311)
+};
+
+__device__ __forceinline__ PixelConsts make_pixel(int col, int row, const float *__restrict__ c2w,
+                                                  const float *__restrict__ viewmat, float fx, float fy,
+                                                  float cx, float cy) {
+    PixelConsts pc;
+    pc.px = (float)col + 0.5f;
+    pc.py = (float)row + 0.5f;
+    const float u = __fdiv_rn(pc.px - cx, fx), v = __fdiv_rn(pc.py - cy, fy);
+    const Vec3 rw = rot_apply(c2w, mk3(u, v, 1.f));
+    pc.rn = sqrtf(dot3(rw, rw));
+    const float inv = __fdiv_rn(1.f, pc.rn);
+    pc.vdep = (viewmat[8] * rw.x + viewmat[9] * rw.y + viewmat[10] * rw.z) * inv;
+    pc.eps = 1e-6f * pc.rn;
+    return pc;
+}
+
+struct PairEval {
+    float ex, ey;   // pixel offset from the record's expansion centre
+    float rD;       // 1 / D (clamped)
+    float l1, l2;   // scaled in-plane coordinates
+    float e;        // 2^-(l1^2+l2^2)
+    float f;        // d(alpha_raw)/d(opac): e, or exp(-sigma_blur) when the blur branch is taken
+    float alpha;    // min(0.99, opac * f)
+    float s;        // c0 / D  (depth along the un-normalised ray)
+    float t;        // s * rn
+    bool blur;      // blur branch selected (BLUR builds only)
+    float bx, by;   // projected mean - pixel (BLUR builds only)
+};
+
+template <bool BLUR>
+__device__ __forceinline__ void eval_pair(const float4 q0, const float4 q1, const float4 q2, const float4 q3,
+                                          const PixelConsts &pc, const float2 *__restrict__ mean2d,
+                                          PairEval &o) {
+    o.ex = __fsub_rn(pc.px, q0.x);
+    o.ey = __fsub_rn(pc.py, q0.y);
+    const float n1 = fmaf(q1.x, o.ex, fmaf(q1.y, o.ey, q1.z));
+    const float n2 = fmaf(q2.x, o.ex, fmaf(q2.y, o.ey, q2.z));
+    float d = fmaf(q3.x, o.ex, fmaf(q3.y, o.ey, q1.w));
+    if (fabsf(d) < pc.eps) d = copysignf(pc.eps, d);
+    o.rD = fast_rcp(d);
+    o.l1 = __fmul_rn(n1, o.rD);
+    o.l2 = __fmul_rn(n2, o.rD);
+    const float qq = fmaf(o.l1, o.l1, __fmul_rn(o.l2, o.l2));
+    o.e = fast_exp2(-qq);
+    o.f = o.e;
+    o.blur = false;
+    o.bx = o.by = 0.f;
+    if (BLUR) {
+        // reference texture.cu:184-197: sigma_blur = 0.5 * 2 * |xy_mean - p|^2, taken when it is the smaller
+        const float2 m2 = mean2d[__float_as_int(q2.w)];
+        o.bx = __fsub_rn(m2.x, pc.px);
+        o.by = __fsub_rn(m2.y, pc.py);
+        const float sb = fmaf(o.bx, o.bx, __fmul_rn(o.by, o.by));
+        if (sb < __fmul_rn(qq, LN2_F)) {
+            o.blur = true;
+            o.f = __expf(-sb);
+        }
+    }
+    o.alpha = fminf(ALPHA_CAP, __fmul_rn(q0.w, o.f));
+    o.s = __fmul_rn(q0.z, o.rD);
+    o.t = __fmul_rn(o.s, pc.rn);
+}
+
+__device__ __forceinline__ bool pair_skipped(const PairEval &pe) {
+    return pe.t < T_NEAR || pe.t > T_FAR || pe.alpha < ALPHA_MIN;  // reference texture.cu:213
+}
+
+// Bilinear / nearest texel addressing with replicate padding (texture_helpers.cuh:155-215).
+// idx[k] are TEXEL indices (not multiplied by the channel count).
+struct TexFetch {
+    int idx[4];
+    float w[4];
+    float fu, fv;
+    int h, wd;
+};
+
+__device__ __forceinline__ float clamp01(float x) { return fminf(fmaxf(x, 0.f), 1.f); }
+
+__device__ __forceinline__ void texel_setup(int h, int w, int si, float u, float v, bool bilinear, TexFetch &f) {
+    const float tu = (float)h * u, tv = (float)w * v;
+    int i0 = (int)tu, j0 = (int)tv;
+    const int i1 = min(i0 + 1, h - 1), j1 = min(j0 + 1, w - 1);
+    const float fu = tu - (float)i0, fv = tv - (float)j0;
+    i0 = min(i0, h - 1);
+    j0 = min(j0, w - 1);
+    const float w00 = (1.f - fu) * (1.f - fv), w01 = (1.f - fu) * fv, w10 = fu * (1.f - fv), w11 = fu * fv;
+    f.idx[0] = si + i0 * w + j0;
+    f.idx[1] = si + i0 * w + j1;
+    f.idx[2] = si + i1 * w + j0;
+    f.idx[3] = si + i1 * w + j1;
+    if (bilinear) {
+        f.w[0] = w00; f.w[1] = w01; f.w[2] = w10; f.w[3] = w11;
+    } else {  // largest weight, first wins on ties (texture_helpers.cuh:199-212)
+        int pick = 3;
+        if (w00 >= w01 && w00 >= w10 && w00 >= w11) pick = 0;
+        else if (w01 >= w00 && w01 >= w10 && w01 >= w11) pick = 1;
+        else if (w10 >= w00 && w10 >= w01 && w10 >= w11) pick = 2;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) f.w[k] = (k == pick) ? 1.f : 0.f;
+    }
+    f.fu = fu; f.fv = fv; f.h = h; f.wd = w;
+}
+
+// Thread -> pixel mapping inside a tile.  For 16x16 tiles every warp owns an 8x4 pixel patch
+// (compact footprint => fewer (warp, Gaussian) pairs survive the any-valid test in the backward pass).
+__device__ __forceinline__ void tile_pixel(int bw, int tr, int &lx, int &ly) {
+    if (bw == 16) {
+        const int w = tr >> 5, l = tr & 31;
+        lx = ((w & 1) << 3) + (l & 7);
+        ly = ((w >> 1) << 2) + (l >> 3);
+    } else {
+        lx = tr % bw;
+        ly = tr / bw;
+    }
+}
+
+// Stage `cnt` records (ids[first..first+cnt)) into shared memory with 16-byte cp.async copies: eight
+// consecutive threads fetch one 128-byte record (one cache line), so both the global reads and the
+// shared-memory writes are fully coalesced / conflict-free.
+__device__ __forceinline__ void stage_records(float4 *__restrict__ dst, const float4 *__restrict__ recs,
+                                              const int32_t *__restrict__ ids, int first, int cnt, int tr,
+                                              int nthreads) {
+    for (int c = tr; c < cnt * 8; c += nthreads) {
+        const int g = ids[first + (c >> 3)];
+        __pipeline_memcpy_async(dst + c, recs + (size_t)g * 8 + (c & 7), 16);
+    }
+    __pipeline_commit();
+}
+
+struct RasterCommon {
+    int img_w, img_h, tiles_x, bw, nthreads, settings, channels;
+    const int32_t *ids;        // gaussian_ids_sorted
+    const int2 *bins;          // tile_bins
+    const float4 *recs;        // packed records (n x 8 float4)
+    const float2 *mean2d;      // projected means (blur only)
+    const float4 *tex4;        // padded texture (X x float4), channels == 3
+    const float *tex;          // caller's texture (X x C), generic channel count
+    const float *viewmat, *c2w, *background;
+    float fx, fy, cx, cy;
+};
+
+}  // namespace gstex

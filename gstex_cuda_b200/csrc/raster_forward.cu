@@ -1,0 +1,286 @@
+// raster_forward.cu -- rasterise forward (reference texture.cu:11-329).
+//
+// One CTA per screen tile, one thread per pixel; for 16x16 tiles each warp owns an 8x4 pixel patch.
+// The tile's depth-sorted Gaussian list is streamed through shared memory in 128-record stages with
+// cp.async (LDGSTS) double buffering: while the CTA composites stage b, the 16 KB of stage b+1 are in
+// flight.  Each record is one 128-byte line gathered through gaussian_ids_sorted; all lanes read the
+// same record at the same time, so the shared-memory reads are broadcasts (LDS.128, no conflicts).
+// The texture is read as one aligned float4 per corner from the padded copy (4 LDG.128 per blended
+// pair instead of 12 scalar loads).
+//
+// Behavioural quirks reproduced (SURVEY 8a "quirks" 1-12): alpha cap 0.99, skip test t<0.01 | t>1000 |
+// alpha<1/255, termination T(1-alpha) <= 1e-4 tested before the skip is honoured, median depth while
+// T>0.5, distortion prefix sums, out_texture without background, final_idx = absolute list index.
+#include "raster.cuh"
+
+namespace gstex {
+
+struct ForwardOut {
+    float *out_img, *out_depth, *out_reg, *out_texture, *out_normal, *final_Ts, *out_reg_s;
+    int32_t *final_idx, *depth_idx;
+};
+
+// C3 = true : 3-channel texture read through the padded float4 copy, accumulators in registers.
+// C3 = false: runtime channel count (<= 64) read from the caller's (X,C) array (slow generic path).
+template <bool C3, bool BLUR>
+__global__ void __launch_bounds__(RASTER_MAX_THREADS) raster_forward_kernel(const RasterCommon p, const ForwardOut o) {
+    __shared__ float4 stage[2][RASTER_BATCH * 8];
+
+    const int tr = threadIdx.x;
+    const int tile = blockIdx.y * p.tiles_x + blockIdx.x;
+    int lx, ly;
+    tile_pixel(p.bw, tr, lx, ly);
+    const int col = blockIdx.x * p.bw + lx, row = blockIdx.y * p.bw + ly;
+    const bool inside = (tr < p.bw * p.bw) && col < p.img_w && row < p.img_h;
+    const PixelConsts pc = make_pixel(col, row, p.c2w, p.viewmat, p.fx, p.fy, p.cx, p.cy);
+    const bool use_ndc = (p.settings & GSTEX_SET_NDC) != 0;
+    const bool bilinear = !(p.settings & GSTEX_SET_NEAREST);
+    const int C = C3 ? 3 : p.channels;
+
+    const int2 range = p.bins[tile];
+    const int total = range.y - range.x;
+    const int nbatch = (total + RASTER_BATCH - 1) / RASTER_BATCH;
+
+    float T = 1.f;
+    float acc_c0 = 0.f, acc_c1 = 0.f, acc_c2 = 0.f;
+    float acc_n0 = 0.f, acc_n1 = 0.f, acc_n2 = 0.f;
+    float acc_t[C3 ? 3 : RASTER_MAX_C];
+#pragma unroll
+    for (int c = 0; c < (C3 ? 3 : RASTER_MAX_C); ++c) acc_t[c] = 0.f;
+    float depth = 0.f, reg = 0.f, S0 = 0.f, S1 = 0.f, S2 = 0.f;
+    int last = 0, dlast = -1;
+    bool done = !inside;
+
+    if (nbatch > 0) stage_records(stage[0], p.recs, p.ids, range.x, min(RASTER_BATCH, total), tr, p.nthreads);
+
+    for (int b = 0; b < nbatch; ++b) {
+        const int first = range.x + b * RASTER_BATCH;
+        const int cnt = min(RASTER_BATCH, range.y - first);
+        if (b + 1 < nbatch) {
+            stage_records(stage[(b + 1) & 1], p.recs, p.ids, first + RASTER_BATCH,
+                          min(RASTER_BATCH, range.y - first - RASTER_BATCH), tr, p.nthreads);
+            __pipeline_wait_prior(1);
+        } else {
+            __pipeline_wait_prior(0);
+        }
+        // stage b is visible to the whole CTA after this barrier; leave if every pixel is finished
+        if (__syncthreads_count(done) >= p.nthreads) break;
+        const float4 *__restrict__ S = stage[b & 1];
+        if (!done) {
+            for (int i = 0; i < cnt; ++i) {
+                const float4 q0 = S[i * 8 + 0], q1 = S[i * 8 + 1], q2 = S[i * 8 + 2], q3 = S[i * 8 + 3];
+                PairEval pe;
+                eval_pair<BLUR>(q0, q1, q2, q3, pc, p.mean2d, pe);
+                const float next_T = __fmul_rn(T, __fsub_rn(1.f, pe.alpha));
+                if (next_T <= T_STOP) {  // tested even for skipped Gaussians (reference texture.cu:216-221)
+                    done = true;
+                    break;
+                }
+                if (pair_skipped(pe)) continue;
+
+                const float4 q4 = S[i * 8 + 4], q5 = S[i * 8 + 5], q6 = S[i * 8 + 6], q7 = S[i * 8 + 7];
+                const float vis = pe.alpha * T;
+                acc_c0 = fmaf(q6.x, vis, acc_c0);
+                acc_c1 = fmaf(q6.y, vis, acc_c1);
+                acc_c2 = fmaf(q6.z, vis, acc_c2);
+                acc_n0 = fmaf(q7.x, vis, acc_n0);
+                acc_n1 = fmaf(q7.y, vis, acc_n1);
+                acc_n2 = fmaf(q7.z, vis, acc_n2);
+                const float nu = fmaf(q4.x, pe.ex, fmaf(q4.y, pe.ey, q4.z));
+                const float nv = fmaf(q5.x, pe.ex, fmaf(q5.y, pe.ey, q5.z));
+                const float u = clamp01(fmaf(nu, pe.rD, q4.w)), v = clamp01(fmaf(nv, pe.rD, q5.w));
+                TexFetch tf;
+                texel_setup(__float_as_int(q3.z), __float_as_int(q3.w), __float_as_int(q6.w), u, v, bilinear, tf);
+                if (C3) {
+                    const float4 t0 = __ldg(p.tex4 + tf.idx[0]), t1 = __ldg(p.tex4 + tf.idx[1]);
+                    const float4 t2 = __ldg(p.tex4 + tf.idx[2]), t3 = __ldg(p.tex4 + tf.idx[3]);
+                    const float w0 = tf.w[0] * vis, w1 = tf.w[1] * vis, w2 = tf.w[2] * vis, w3 = tf.w[3] * vis;
+                    acc_t[0] += w0 * t0.x + w1 * t1.x + w2 * t2.x + w3 * t3.x;
+                    acc_t[1] += w0 * t0.y + w1 * t1.y + w2 * t2.y + w3 * t3.y;
+                    acc_t[2] += w0 * t0.z + w1 * t1.z + w2 * t2.z + w3 * t3.z;
+                } else {
+                    const float *__restrict__ tx = p.tex;
+                    for (int c = 0; c < C; ++c) {
+                        const float val = tf.w[0] * __ldg(tx + (size_t)tf.idx[0] * C + c) +
+                                          tf.w[1] * __ldg(tx + (size_t)tf.idx[1] * C + c) +
+                                          tf.w[2] * __ldg(tx + (size_t)tf.idx[2] * C + c) +
+                                          tf.w[3] * __ldg(tx + (size_t)tf.idx[3] * C + c);
+                        acc_t[c] = fmaf(vis, val, acc_t[c]);
+                    }
+                }
+                const float t_view = pe.t * pc.vdep;
+                if (T > 0.5f) {  // median depth (reference texture.cu:286-291)
+                    depth = t_view;
+                    dlast = first + i;
+                }
+                float tv = pe.t;
+                if (use_ndc) tv = (T_FAR * t_view - T_FAR * T_NEAR) / ((T_FAR - T_NEAR) * t_view);
+                reg += vis * (tv * tv * S0 + S2 - 2.f * tv * S1);  // helpers.cuh:259-264
+                S0 += vis;
+                S1 += vis * tv;
+                S2 += vis * tv * tv;
+                T = next_T;
+                last = first + i;
+            }
+        }
+        __syncthreads();  // everyone is done with stage b before it is refilled (two iterations ahead)
+    }
+    __pipeline_wait_prior(0);
+
+    if (inside) {
+        const int pix = row * p.img_w + col;
+        const float bg0 = p.background[0], bg1 = p.background[1], bg2 = p.background[2];
+        o.final_Ts[pix] = T;
+        o.final_idx[pix] = last;
+        o.depth_idx[pix] = dlast;
+        o.out_img[3 * pix + 0] = fmaf(T, bg0, acc_c0);
+        o.out_img[3 * pix + 1] = fmaf(T, bg1, acc_c1);
+        o.out_img[3 * pix + 2] = fmaf(T, bg2, acc_c2);
+        o.out_normal[3 * pix + 0] = acc_n0;
+        o.out_normal[3 * pix + 1] = acc_n1;
+        o.out_normal[3 * pix + 2] = acc_n2;
+        o.out_depth[pix] = depth;
+        o.out_reg[pix] = reg;
+        o.out_reg_s[3 * pix + 0] = S0;
+        o.out_reg_s[3 * pix + 1] = S1;
+        o.out_reg_s[3 * pix + 2] = S2;
+        if (C3) {
+            o.out_texture[3 * pix + 0] = acc_t[0];
+            o.out_texture[3 * pix + 1] = acc_t[1];
+            o.out_texture[3 * pix + 2] = acc_t[2];
+        } else {
+            for (int c = 0; c < C; ++c) o.out_texture[(size_t)C * pix + c] = acc_t[c];
+        }
+    }
+}
+
+// defined in pack.cu
+int launch_pack(int n, const float *means, const float *scales, float glob_scale, const float *quats,
+                const float *opacities, const float *colors, const float *uv0, const float *umap, const float *vmap,
+                const int32_t *texture_dims, const float *viewmat, const float *c2w, float fx, float fy, float cx,
+                float cy, float4 *recs, float2 *mean2d, cudaStream_t s);
+int launch_pad_texture(int64_t num_texels, const float *tex, float4 *tex4, cudaStream_t s);
+
+struct FwdLayout {
+    size_t recs_off, mean2d_off, tex4_off, total;
+};
+
+FwdLayout forward_layout(int n, int64_t num_texels, int channels) {
+    FwdLayout L;
+    size_t off = 0;
+    L.recs_off = off;
+    off = align_up(off + sizeof(float) * REC_FLOATS * (size_t)(n > 0 ? n : 1), 256);
+    L.mean2d_off = off;
+    off = align_up(off + sizeof(float2) * (size_t)(n > 0 ? n : 1), 256);
+    L.tex4_off = off;
+    if (channels == 3) off = align_up(off + sizeof(float4) * (size_t)(num_texels > 0 ? num_texels : 1), 256);
+    L.total = off;
+    return L;
+}
+
+int check_raster_args(const char *who, int img_height, int img_width, int block_width, int n, int64_t num_texels,
+                      int channels, int settings) {
+    GSTEX_REQUIRE(img_height > 0 && img_width > 0, GSTEX_E_INVALID, "%s: image %dx%d", who, img_height, img_width);
+    GSTEX_REQUIRE(block_width > 1 && block_width <= 16, GSTEX_E_INVALID,
+                  "%s: block_width must be between 2 and 16 (got %d)", who, block_width);
+    GSTEX_REQUIRE(n >= 0 && num_texels >= 0 && num_texels < ((int64_t)1 << 31), GSTEX_E_INVALID,
+                  "%s: n = %d, texels = %lld", who, n, (long long)num_texels);
+    GSTEX_REQUIRE(channels >= 1 && channels <= RASTER_MAX_C, GSTEX_E_INVALID,
+                  "%s: texture channels must be in [1, %d] (got %d)", who, RASTER_MAX_C, channels);
+    GSTEX_REQUIRE((settings & ~GSTEX_SET_SUPPORTED) == 0, GSTEX_E_UNSUPPORTED,
+                  "%s: settings 0x%x has bits outside the training path (supported mask 0x%x); the visualisation "
+                  "modes (bits 15-29) are not built", who, settings, GSTEX_SET_SUPPORTED);
+    return GSTEX_OK;
+}
+
+}  // namespace gstex
+
+using namespace gstex;
+
+extern "C" size_t gstex_texture_forward_temp_bytes(int n, int64_t num_texels, int channels) {
+    return forward_layout(n, num_texels, channels).total;
+}
+
+// fills the forward scratch: packed per-view records, projected means, padded texture
+static int texture_pack(int n, int64_t num_texels, int channels, const int32_t *texture_dims, const float *colors,
+                        const float *opacities, const float *means, const float *scales, float glob_scale,
+                        const float *quats, const float *uv0, const float *umap, const float *vmap,
+                        const float *texture, const float *viewmat, const float *c2w, float fx, float fy, float cx,
+                        float cy, void *temp, size_t temp_bytes, cudaStream_t s) {
+    const FwdLayout L = forward_layout(n, num_texels, channels);
+    GSTEX_REQUIRE(temp && temp_bytes >= L.total, GSTEX_E_WORKSPACE, "texture_pack: temp too small (%zu < %zu)",
+                  temp_bytes, L.total);
+    char *base = (char *)temp;
+    int rc = launch_pack(n, means, scales, glob_scale, quats, opacities, colors, uv0, umap, vmap, texture_dims, viewmat,
+                         c2w, fx, fy, cx, cy, (float4 *)(base + L.recs_off), (float2 *)(base + L.mean2d_off), s);
+    if (rc != GSTEX_OK) return rc;
+    if (channels == 3) return launch_pad_texture(num_texels, texture, (float4 *)(base + L.tex4_off), s);
+    return GSTEX_OK;
+}
+
+extern "C" int gstex_texture_pack(int n, int64_t num_texels, int channels, const int32_t *texture_dims,
+                                  const float *colors, const float *opacities, const float *means,
+                                  const float *scales, float glob_scale, const float *quats, const float *uv0,
+                                  const float *umap, const float *vmap, const float *texture, const float *viewmat,
+                                  const float *c2w, float fx, float fy, float cx, float cy, void *temp,
+                                  size_t temp_bytes, gstex_stream_t stream) {
+    GSTEX_REQUIRE(n >= 0 && num_texels >= 0 && channels >= 1 && channels <= RASTER_MAX_C, GSTEX_E_INVALID,
+                  "texture_pack: n = %d, texels = %lld, channels = %d", n, (long long)num_texels, channels);
+    return texture_pack(n, num_texels, channels, texture_dims, colors, opacities, means, scales, glob_scale, quats, uv0,
+                        umap, vmap, texture, viewmat, c2w, fx, fy, cx, cy, temp, temp_bytes, as_stream(stream));
+}
+
+extern "C" int gstex_texture_forward(int img_height, int img_width, int block_width, int n, int64_t num_texels,
+                                     int channels, const int32_t *texture_dims, const int32_t *gaussian_ids_sorted,
+                                     const int32_t *tile_bins, const float *colors, const float *opacities,
+                                     const float *means, const float *scales, float glob_scale, const float *quats,
+                                     const float *uv0, const float *umap, const float *vmap, const float *texture,
+                                     const float *viewmat, const float *c2w, float fx, float fy, float cx, float cy,
+                                     int settings, const float *background, float *out_img, float *out_depth,
+                                     float *out_reg, float *out_texture, float *out_normal, float *final_Ts,
+                                     int32_t *final_idx, int32_t *depth_idx, float *out_reg_s, void *temp,
+                                     size_t temp_bytes, gstex_stream_t stream) {
+    int rc = check_raster_args("texture_forward", img_height, img_width, block_width, n, num_texels, channels, settings);
+    if (rc != GSTEX_OK) return rc;
+    const FwdLayout L = forward_layout(n, num_texels, channels);
+    GSTEX_REQUIRE(temp && temp_bytes >= L.total, GSTEX_E_WORKSPACE, "texture_forward: temp too small (%zu < %zu)",
+                  temp_bytes, L.total);
+    cudaStream_t s = as_stream(stream);
+    char *base = (char *)temp;
+    float4 *recs = (float4 *)(base + L.recs_off);
+    float2 *mean2d = (float2 *)(base + L.mean2d_off);
+    float4 *tex4 = (float4 *)(base + L.tex4_off);
+    rc = texture_pack(n, num_texels, channels, texture_dims, colors, opacities, means, scales, glob_scale, quats, uv0,
+                      umap, vmap, texture, viewmat, c2w, fx, fy, cx, cy, temp, temp_bytes, s);
+    if (rc != GSTEX_OK) return rc;
+    RasterCommon p;
+    p.img_w = img_width;
+    p.img_h = img_height;
+    p.tiles_x = ceil_div(img_width, block_width);
+    p.bw = block_width;
+    p.nthreads = ceil_div(block_width * block_width, 32) * 32;
+    p.settings = settings;
+    p.channels = channels;
+    p.ids = gaussian_ids_sorted;
+    p.bins = (const int2 *)tile_bins;
+    p.recs = recs;
+    p.mean2d = mean2d;
+    p.tex4 = tex4;
+    p.tex = texture;
+    p.viewmat = viewmat;
+    p.c2w = c2w;
+    p.background = background;
+    p.fx = fx; p.fy = fy; p.cx = cx; p.cy = cy;
+    ForwardOut o{out_img, out_depth, out_reg, out_texture, out_normal, final_Ts, out_reg_s, final_idx, depth_idx};
+    const dim3 grid(p.tiles_x, ceil_div(img_height, block_width));
+    const bool blur = (settings & GSTEX_SET_BLUR) != 0;
+    if (channels == 3) {
+        if (blur) raster_forward_kernel<true, true><<<grid, p.nthreads, 0, s>>>(p, o);
+        else raster_forward_kernel<true, false><<<grid, p.nthreads, 0, s>>>(p, o);
+    } else {
+        if (blur) raster_forward_kernel<false, true><<<grid, p.nthreads, 0, s>>>(p, o);
+        else raster_forward_kernel<false, false><<<grid, p.nthreads, 0, s>>>(p, o);
+    }
+    GSTEX_LAUNCH_OK("raster_forward_kernel");
+    return GSTEX_OK;
+}

@@ -1,0 +1,197 @@
+/*
+ * gstex_b200.h -- C ABI of libgstex_b200.so, the B200 (sm_100a) textured-2DGS rasteriser.
+ *
+ * This is the drop-in boundary for the reference's pybind module `gstex_cuda`
+ * (victor-rong/GStex_cuda, gstex_cuda/cuda/csrc/ext.cpp:8-25).  Every entry point
+ * names the reference interface it replaces.  Rules for all entry points:
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless
+ *     its name ends in `_host`; float = fp32, ids = int32, keys = int64;
+ *   - the callee never allocates, never synchronises and never throws: outputs
+ *     and scratch space are provided by the caller (query the *_bytes functions);
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*; 0 = legacy
+ *     default stream) of the CURRENT device;
+ *   - returns 0 on success, a negative GSTEX_E_* code otherwise;
+ *     gstex_last_error() returns a thread-local message for the last failure.
+ * Layout conventions are the reference's: viewmat / c2w 4x4 row-major,
+ * quats (w,x,y,z) pre-normalised, scales linear, texture (X, C) row = texel,
+ * texture_dims (N,3) int32 {h, w, first_texel}, images (H, W, ...) row-major.
+ */
+#ifndef GSTEX_B200_H
+#define GSTEX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSTEX_OK 0
+#define GSTEX_E_INVALID (-1)   /* bad argument (size, block width, channel count ...) */
+#define GSTEX_E_CUDA (-2)      /* a CUDA runtime call / launch failed */
+#define GSTEX_E_WORKSPACE (-3) /* scratch buffer too small */
+#define GSTEX_E_UNSUPPORTED (-4) /* settings bits outside the training path (visualisation modes) */
+
+typedef void *gstex_stream_t;
+
+const char *gstex_last_error(void);
+int gstex_abi_version(void);
+
+/* ---- settings bits, texture.cu:54-65 / :381-386 ---------------------------------------- */
+#define GSTEX_SET_NEAREST (1 << 2)       /* nearest texel instead of bilinear */
+#define GSTEX_SET_PROPAGATE_UV (1 << 8)  /* UV gradient flows to means / uv maps */
+#define GSTEX_SET_BLUR (1 << 9)          /* 2-D screen-space blur floor */
+#define GSTEX_SET_NDC (1 << 10)          /* distortion on NDC depth */
+#define GSTEX_SET_SUPPORTED (GSTEX_SET_NEAREST | GSTEX_SET_PROPAGATE_UV | GSTEX_SET_BLUR | GSTEX_SET_NDC)
+
+/* ======================================================================================== *
+ * (1) projection, screen AABB, tile count
+ * ======================================================================================== */
+
+/* replaces get_aabb_2d_tensor, get_aabb_2d.cu:91-125 (kernel :11-89).
+ * centers, extents: (n,2), fully written. */
+int gstex_get_aabb_2d(int n, const float *means, const float *scales, float glob_scale, const float *quats,
+                      const float *viewmat, float fx, float fy, float cx, float cy, float *centers,
+                      float *extents, gstex_stream_t stream);
+
+/* replaces the torch ops of get_num_tiles_hit_2d, gstex_cuda/get_aabb_2d.py:70-92 (floor based). */
+int gstex_num_tiles_hit_2d(int n, const float *centers, const float *extents, int img_height, int img_width,
+                           int block_width, int32_t *num_tiles_hit, gstex_stream_t stream);
+
+/* replaces the torch ops of project_points(clip=False), gstex_cuda/get_aabb_2d.py:22-32.
+ * pix may be NULL. viewmat: row-major 4x4 (first 12 floats read). */
+int gstex_project_points(int n, const float *means, const float *viewmat, float fx, float fy, float cx,
+                         float cy, float *pix, float *depths, gstex_stream_t stream);
+
+/* fused replacement of example.py:148-152 (project_points + get_aabb_2d + get_num_tiles_hit_2d):
+ * one pass over the Gaussians.  Tile counts use the same truncation rule as the key emitter
+ * (helpers.cuh:37-51), which equals the floor rule after clamping for power-of-two block widths.
+ * Gaussians whose extents are both <= 1e-4 (clipped, forward.cu:32) count 0 tiles. */
+int gstex_project_aabb_count(int n, const float *means, const float *scales, float glob_scale,
+                             const float *quats, const float *viewmat, float fx, float fy, float cx, float cy,
+                             int img_height, int img_width, int block_width, float *centers, float *extents,
+                             float *depths, int32_t *num_tiles_hit, gstex_stream_t stream);
+
+/* ======================================================================================== *
+ * (2) tile binning
+ * ======================================================================================== */
+
+/* replaces torch.cumsum(int32) of compute_cumulative_intersects, gstex_cuda/utils.py:40-59.
+ * Inclusive scan; out[n-1] is the number of intersections (read it on the host only if you must). */
+size_t gstex_scan_temp_bytes(int n);
+int gstex_cumsum_i32(int n, const int32_t *in, int32_t *out, void *temp, size_t temp_bytes,
+                     gstex_stream_t stream);
+
+/* replaces map_gaussian_to_intersects_tensor, bindings.cu:77-121 (kernel forward.cu:13-71), wrapped=false.
+ * isect_ids (m) int64 = (tile_id << 32) | depth bits, gaussian_ids (m) int32.  Slots of Gaussians the
+ * emitter skips are NOT written: zero-fill the outputs first to reproduce the reference exactly.
+ * num_intersects is the capacity of the two outputs; writes past it are dropped (the reference would
+ * write out of bounds when cum_tiles_hit disagrees with the emitter's own tile count). */
+int gstex_map_gaussian_to_intersects(int n, int64_t num_intersects, const float *centers, const float *extents,
+                                     const float *depths, const int32_t *cum_tiles_hit, int tiles_x, int tiles_y,
+                                     int block_width, int64_t *isect_ids, int32_t *gaussian_ids,
+                                     gstex_stream_t stream);
+
+/* replaces torch.sort(int64) + torch.gather, gstex_cuda/utils.py:159-160: stable ascending LSD radix sort
+ * of signed 64-bit keys carrying int32 values.  `end_bit` (1..64): keys are known to be non-negative and
+ * < 2^end_bit (64 = no assumption).  If d_count is non-NULL the number of valid elements is
+ * min(*d_count, m) read on the device (no host sync); elements past it are left untouched. */
+size_t gstex_sort_temp_bytes(int64_t m);
+int gstex_sort_pairs(int64_t m, const int64_t *keys_in, const int32_t *vals_in, int64_t *keys_out,
+                     int32_t *vals_out, int end_bit, const int32_t *d_count, void *temp, size_t temp_bytes,
+                     gstex_stream_t stream);
+
+/* replaces get_tile_bin_edges_tensor, bindings.cu:123-140 (kernel forward.cu:76-98).
+ * tile_bins (num_tiles,2) int32 must be zero-filled by the caller (as torch::zeros does). */
+int gstex_get_tile_bin_edges(int64_t m, const int64_t *isect_ids_sorted, int32_t *tile_bins,
+                             const int32_t *d_count, gstex_stream_t stream);
+
+/* ======================================================================================== *
+ * (3) rasterise forward / (4) rasterise backward
+ * ======================================================================================== */
+
+/* Scratch needed by gstex_texture_forward / gstex_texture_backward for n Gaussians, x texels with
+ * c channels.  The forward scratch must stay alive and untouched until the matching backward ran
+ * (it holds the per-view packed Gaussian records and the padded texture). */
+size_t gstex_texture_forward_temp_bytes(int n, int64_t num_texels, int channels);
+size_t gstex_texture_backward_temp_bytes(int n, int64_t num_texels, int channels);
+
+/* Fills the forward scratch (per-view packed records + padded texture) without rasterising.  The
+ * reference's texture_backward is a pure function of its arguments (texture.cuh:120-168); a caller that
+ * invokes the backward without having run gstex_texture_forward for the same inputs packs first. */
+int gstex_texture_pack(int n, int64_t num_texels, int channels, const int32_t *texture_dims, const float *colors,
+                       const float *opacities, const float *means, const float *scales, float glob_scale,
+                       const float *quats, const float *uv0, const float *umap, const float *vmap,
+                       const float *texture, const float *viewmat, const float *c2w, float fx, float fy, float cx,
+                       float cy, void *temp, size_t temp_bytes, gstex_stream_t stream);
+
+/* replaces texture_forward_tensor, texture.cu:766-901 (kernel :11-329).
+ * Outputs (all fully written): out_img (H,W,3), out_depth (H,W), out_reg (H,W), out_texture (H,W,C),
+ * out_normal (H,W,3), final_Ts (H,W), final_idx (H,W) int32, depth_idx (H,W) int32, out_reg_s (H,W,3).
+ * background: 3 floats on the device. */
+int gstex_texture_forward(int img_height, int img_width, int block_width, int n, int64_t num_texels,
+                          int channels, const int32_t *texture_dims, const int32_t *gaussian_ids_sorted,
+                          const int32_t *tile_bins, const float *colors, const float *opacities,
+                          const float *means, const float *scales, float glob_scale, const float *quats,
+                          const float *uv0, const float *umap, const float *vmap, const float *texture,
+                          const float *viewmat, const float *c2w, float fx, float fy, float cx, float cy,
+                          int settings, const float *background, float *out_img, float *out_depth,
+                          float *out_reg, float *out_texture, float *out_normal, float *final_Ts,
+                          int32_t *final_idx, int32_t *depth_idx, float *out_reg_s, void *temp,
+                          size_t temp_bytes, gstex_stream_t stream);
+
+/* replaces texture_backward_tensor, texture.cu:915-1053 (kernel :331-760).
+ * fwd_temp: the scratch the matching forward call filled.  Gradients (n,3) (n,1) (n,3) (n,3) (n,4) (n,1,2)
+ * (n,1,3) (n,1,3) (X,C): if accumulate == 0 they are overwritten (no zero-fill needed), otherwise the
+ * view's gradient is added to what they hold (multi-view accumulation). */
+int gstex_texture_backward(int img_height, int img_width, int block_width, int n, int64_t num_texels,
+                           int channels, const int32_t *texture_dims, const int32_t *gaussian_ids_sorted,
+                           const int32_t *tile_bins, const float *colors, const float *opacities,
+                           const float *means, const float *scales, float glob_scale, const float *quats,
+                           const float *uv0, const float *umap, const float *vmap, const float *texture,
+                           const float *viewmat, const float *c2w, float fx, float fy, float cx, float cy,
+                           int settings, const float *background, const float *final_Ts,
+                           const int32_t *final_idx, const int32_t *depth_idx, const float *final_s,
+                           const float *v_out_img, const float *v_out_depth, const float *v_out_reg,
+                           const float *v_out_alpha, const float *v_out_texture, const float *v_out_normal,
+                           float *v_colors, float *v_opacity, float *v_means, float *v_scales, float *v_quats,
+                           float *v_uv0, float *v_umap, float *v_vmap, float *v_texture, int accumulate,
+                           const void *fwd_temp, void *temp, size_t temp_bytes, gstex_stream_t stream);
+
+/* ======================================================================================== *
+ * spherical harmonics, texture sampling
+ * ======================================================================================== */
+
+/* replaces compute_sh_forward_tensor / compute_sh_backward_tensor, bindings.cu:18-75 (sh.cuh:212-253).
+ * coeffs (n,K,3) with K = num_sh_bases(degree); colors (n,3).  Backward writes all K rows (rows beyond
+ * num_sh_bases(degrees_to_use) are zero); with accumulate != 0 it adds instead. */
+int gstex_sh_forward(int n, int degree, int degrees_to_use, const float *viewdirs, const float *coeffs,
+                     float *colors, gstex_stream_t stream);
+int gstex_sh_backward(int n, int degree, int degrees_to_use, const float *viewdirs, const float *v_colors,
+                      float *v_coeffs, int accumulate, gstex_stream_t stream);
+
+/* replaces texture_sample_forward_tensor / texture_sample_backward_tensor, texture_sample.cu:72-141.
+ * uv is clamped to [0,1] (documented behaviour, texture_sample.py:26-30).  The backward is the intended
+ * scatter (the reference kernel reads the wrong buffer, texture_sample.cu:58, and is unreachable):
+ * v_texture (X,C) must be zero-filled by the caller. */
+int gstex_texture_sample_forward(int num_queries, int channels, const int32_t *texture_dims, const float *uvs,
+                                 const float *texture, float *output, gstex_stream_t stream);
+int gstex_texture_sample_backward(int num_queries, int channels, const int32_t *texture_dims, const float *uvs,
+                                  const float *v_output, float *v_texture, gstex_stream_t stream);
+
+/* ======================================================================================== *
+ * fused per-view training step (project -> bin -> sort -> raster fwd -> loss -> raster bwd), no host sync
+ * ======================================================================================== */
+
+/* Fused image loss of example.py:189-209 and its gradient w.r.t. the rasteriser outputs:
+ *   loss = mean((out_texture - gt)^2) + mean(out_reg) + mean(nx^2 + ny^2 + (1-nz)^2)
+ * loss_accum[0] += loss (atomic, one add per block); v_* are fully written. */
+int gstex_image_loss(int img_height, int img_width, const float *out_texture, const float *out_reg,
+                     const float *out_normal, const float *gt, float *loss_accum, float *v_out_img,
+                     float *v_out_depth, float *v_out_reg, float *v_out_alpha, float *v_out_texture,
+                     float *v_out_normal, gstex_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSTEX_B200_H */

@@ -341,7 +341,7 @@ static void sh_basis(int deg, const float *dir, float *Y) {
     Y[15] = -0.5900435899266435f * x * (xx - 3.f * yy);
     if (deg < 4) return;
     Y[16] = 2.5033429417967046f * xy * (xx - yy);
-    Y[17] = (float)(-1.7701307697799304 * (double)(yz * (3.f * xx - yy))); /* sh.cuh:25: constant lacks the f suffix */
+    Y[17] = -1.7701307697799304f * yz * (3.f * xx - yy); /* sh.cuh:25 lacks the f suffix, but the array is float */
     Y[18] = 0.9461746957575601f * xy * (7.f * zz - 1.f);
     Y[19] = -0.6690465435572892f * yz * (7.f * zz - 3.f);
     Y[20] = 0.10578554691520431f * (zz * (35.f * zz - 30.f) + 3.f);

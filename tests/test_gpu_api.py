@@ -1,0 +1,125 @@
+"""-m gpu: the public autograd API (texture_gaussians and friends) end to end, example.py style."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from gstex_cuda_b200.texture import texture_gaussians
+from gstex_cuda_b200.get_aabb_2d import get_aabb_2d, get_num_tiles_hit_2d, project_points, get_aabb_2d_torch
+from gstex_cuda_b200._torch_impl import normalized_quat_to_rotmat
+from gstex_cuda_b200.scenes import random_small_scene
+from gpu_util import DEV, to_np, assert_close_frac
+
+pytestmark = pytest.mark.gpu
+
+
+def _loss(outputs, gt):
+    """example.py:189-209"""
+    out_texture, out_reg, out_normal = outputs[4][:, :, :3], outputs[2], outputs[5]
+    return (torch.nn.functional.mse_loss(out_texture, gt) + out_reg.mean()
+            + (out_normal[:, :, 0] ** 2 + out_normal[:, :, 1] ** 2 + (1 - out_normal[:, :, 2]) ** 2).mean())
+
+
+def test_example_style_training_step_matches_oracle():
+    s = random_small_scene(120, 96, 80, seed=8, device=DEV)
+    H, W, bw = s["H"], s["W"], 16
+    leaves = {k: s[k].clone().requires_grad_(True) for k in
+              ("colors", "opacities", "means", "scales", "quats", "uv0", "umap", "vmap", "texture")}
+    intr = s["intrins"]
+    _, depths = project_points(leaves["means"], s["viewmat"], intr)
+    centers, extents = get_aabb_2d(leaves["means"], leaves["scales"], 1, leaves["quats"], s["viewmat"], intr)
+    nth = get_num_tiles_hit_2d(centers, extents, H, W, bw)
+    outs = texture_gaussians(s["texture_info"], s["texture_dims"], centers, extents, depths, nth, leaves["colors"],
+                             leaves["opacities"], leaves["means"], leaves["scales"], 1, leaves["quats"], leaves["uv0"],
+                             leaves["umap"], leaves["vmap"], leaves["texture"], s["viewmat"], s["c2w"], *intr, H, W, bw,
+                             1 << 8, s["background"])
+    assert [tuple(o.shape) for o in outs] == [(H, W, 3), (H, W), (H, W), (H, W), (H, W, 3), (H, W, 3)]
+    loss = _loss(outs, s["target"])
+    loss.backward()
+
+    # oracle: same pipeline on the CPU, gradients of the same loss injected by hand
+    npz = {k: to_np(v) for k, v in s.items() if torch.is_tensor(v)}
+    b = oracle.bin_view(npz["means"], npz["scales"], 1.0, npz["quats"], npz["viewmat"], intr, H, W, bw)
+    fx, fy, cx, cy = intr
+    args = (H, W, bw, npz["texture_dims"], b["gaussian_ids_sorted"], b["tile_bins"], npz["colors"], npz["opacities"],
+            npz["means"], npz["scales"], 1.0, npz["quats"], npz["uv0"], npz["umap"], npz["vmap"], npz["texture"],
+            npz["viewmat"], npz["c2w"], fx, fy, cx, cy, 1 << 8, npz["background"])
+    f = oracle.texture_forward(*args)
+    for k, o in zip(("out_img", "out_depth", "out_reg"), outs[:3]):
+        assert_close_frac(k, to_np(o), f[k], 1e-4, 2e-5, 2e-3)
+    assert_close_frac("out_alpha", to_np(outs[3]), 1 - f["final_Ts"], 1e-4, 2e-5, 2e-3)
+    P = H * W
+    gt = npz["target"]
+    v_tex = 2 * (f["out_texture"] - gt) / (3 * P)
+    n_ = f["out_normal"]
+    v_n = np.stack([2 * n_[..., 0], 2 * n_[..., 1], -2 * (1 - n_[..., 2])], -1) / P
+    zeros = np.zeros((H, W), np.float32)
+    g = oracle.texture_backward(*args, f["final_Ts"], f["final_idx"], f["depth_idx"], f["out_reg_s"],
+                                np.zeros((H, W, 3), np.float32), zeros, np.full((H, W), 1.0 / P, np.float32), zeros,
+                                v_tex.astype(np.float32), v_n.astype(np.float32))
+    for k_leaf, k_o in (("colors", "v_colors"), ("opacities", "v_opacity"), ("means", "v_means"), ("scales", "v_scales"),
+                        ("quats", "v_quats"), ("uv0", "v_uv0"), ("umap", "v_umap"), ("vmap", "v_vmap"),
+                        ("texture", "v_texture")):
+        ref = g[k_o]
+        got = to_np(leaves[k_leaf].grad).reshape(ref.shape)
+        assert_close_frac(k_o, got, ref, 2e-3, 1e-9 + 2e-4 * float(np.abs(ref).max()), 2e-3)
+
+
+def test_no_intersections_returns_background():
+    s = random_small_scene(5, 32, 32, seed=2, device=DEV)
+    s["means"][:, 2] = -20.0  # all behind the camera
+    intr = s["intrins"]
+    means = s["means"].clone().requires_grad_(True)
+    _, depths = project_points(means, s["viewmat"], intr)
+    centers, extents = get_aabb_2d(means, s["scales"], 1, s["quats"], s["viewmat"], intr)
+    nth = get_num_tiles_hit_2d(centers, extents, 32, 32, 16)
+    assert int(nth.sum()) == 0
+    outs = texture_gaussians(s["texture_info"], s["texture_dims"], centers, extents, depths, nth, s["colors"],
+                             s["opacities"], means, s["scales"], 1, s["quats"], s["uv0"], s["umap"], s["vmap"],
+                             s["texture"], s["viewmat"], s["c2w"], *intr, 32, 32, 16, 1 << 8, s["background"])
+    assert torch.allclose(outs[0], s["background"].expand(32, 32, 3))
+    outs[0].sum().backward()
+    assert float(means.grad.abs().max()) == 0.0
+
+
+def test_uint8_colors_and_default_background():
+    s = random_small_scene(30, 48, 48, seed=3, device=DEV)
+    intr = s["intrins"]
+    _, depths = project_points(s["means"], s["viewmat"], intr)
+    centers, extents = get_aabb_2d(s["means"], s["scales"], 1, s["quats"], s["viewmat"], intr)
+    nth = get_num_tiles_hit_2d(centers, extents, 48, 48, 16)
+    c8 = (s["colors"] * 255).to(torch.uint8)
+    a = texture_gaussians(s["texture_info"], s["texture_dims"], centers, extents, depths, nth, c8, s["opacities"],
+                          s["means"], s["scales"], 1, s["quats"], s["uv0"], s["umap"], s["vmap"], s["texture"],
+                          s["viewmat"], s["c2w"], *intr, 48, 48, 16, 1 << 8)
+    b = texture_gaussians(s["texture_info"], s["texture_dims"], centers, extents, depths, nth, c8.float() / 255,
+                          s["opacities"], s["means"], s["scales"], 1, s["quats"], s["uv0"], s["umap"], s["vmap"],
+                          s["texture"], s["viewmat"], s["c2w"], *intr, 48, 48, 16, 1 << 8,
+                          torch.ones(3, device=DEV))
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    with pytest.raises(AssertionError):
+        texture_gaussians(s["texture_info"], s["texture_dims"], centers, extents, depths, nth, c8, s["opacities"],
+                          s["means"], s["scales"], 1, s["quats"], s["uv0"], s["umap"], s["vmap"], s["texture"],
+                          s["viewmat"], s["c2w"], *intr, 48, 48, 32, 1 << 8)
+
+
+def test_project_points_autograd_and_aabb_torch_twin():
+    s = random_small_scene(200, 64, 64, seed=4, device=DEV)
+    intr = s["intrins"]
+    m = s["means"].clone().requires_grad_(True)
+    pix, depths = project_points(m, s["viewmat"], intr)
+    (pix.sum() * 0.01 + (depths ** 2).sum()).backward()
+    m2 = s["means"].clone().requires_grad_(True)
+    pv = m2 @ s["viewmat"][:3, :3].T + s["viewmat"][:3, 3]
+    rw = 1.0 / (pv[:, 2] + 1e-6)
+    pix2 = torch.stack([pv[:, 0] * rw * intr[0] + intr[2], pv[:, 1] * rw * intr[1] + intr[3]], -1)
+    (pix2.sum() * 0.01 + (pv[:, 2] ** 2).sum()).backward()
+    torch.testing.assert_close(pix, pix2, rtol=1e-5, atol=1e-3)
+    torch.testing.assert_close(m.grad, m2.grad, rtol=1e-4, atol=1e-5)
+    c, e = get_aabb_2d(s["means"], s["scales"], 1.0, s["quats"], s["viewmat"], intr)
+    ct, et = get_aabb_2d_torch(s["means"], s["scales"], 1.0, s["quats"], s["viewmat"], intr)
+    torch.testing.assert_close(c, ct, rtol=1e-4, atol=1e-2)
+    torch.testing.assert_close(e, et, rtol=1e-4, atol=1e-2)
+    R = normalized_quat_to_rotmat(s["quats"])
+    torch.testing.assert_close(R @ R.transpose(-1, -2), torch.eye(3, device=DEV).expand_as(R), rtol=1e-4, atol=1e-5)

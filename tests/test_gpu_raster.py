@@ -1,0 +1,160 @@
+"""-m gpu: rasterise forward / backward (through the reference-shaped backend -> C ABI) vs the CPU oracle.
+
+Tolerances (fp32; the oracle evaluates the reference's quat->R / ray-plane chain, the kernels the
+homography form, so results differ by rounding only):
+  images            rtol 1e-4, atol 2e-5
+  final_idx / depth_idx  exact, except that alpha / transmittance threshold decisions (alpha < 1/255,
+                    T(1-alpha) <= 1e-4, T > 0.5) can flip on values within rounding of the threshold:
+                    at most 0.2 % of the pixels may differ; the same allowance applies to the float images
+                    (a flipped median-depth Gaussian changes out_depth discontinuously)
+  gradients         rtol 2e-3, atol 1e-4 * max|g|  (the backward is fed OUR forward's saved state on both
+                    sides, so forward flips do not leak into the gradient comparison)
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from gstex_cuda_b200.scenes import random_small_scene, synthetic_scene
+from gstex_cuda_b200 import sh as SH
+from gpu_util import (DEV, to_np, bin_cuda, forward_cuda, backward_cuda, forward_oracle, backward_oracle, random_vout,
+                      compare_forward, compare_backward)
+
+pytestmark = pytest.mark.gpu
+
+FLIP = 2e-3
+
+
+def _golden_scene(golden_dir, name):
+    g = dict(np.load(os.path.join(golden_dir, name)))
+    s = {}
+    for k in ("means", "scales", "quats", "colors", "opacities", "uv0", "umap", "vmap", "texture", "viewmat", "c2w",
+              "background"):
+        s[k] = torch.from_numpy(g[k]).to(DEV).contiguous()
+    s["texture_dims"] = torch.from_numpy(g["texture_dims"]).to(DEV)
+    s.update(H=int(g["H"]), W=int(g["W"]), block_width=int(g["block_width"]), settings=int(g["settings"]),
+             glob_scale=float(g["glob_scale"]), intrins=tuple(float(v) for v in g["intrins"]),
+             num_points=g["means"].shape[0], texture_info=(g["means"].shape[0], 1, g["texture"].shape[1]))
+    ids = torch.from_numpy(g["gaussian_ids_sorted"]).to(DEV)
+    bins = torch.from_numpy(g["tile_bins"]).to(DEV)
+    vout = {k: torch.from_numpy(g[k]).to(DEV).contiguous() for k in
+            ("v_out_img", "v_out_depth", "v_out_reg", "v_out_alpha", "v_out_texture", "v_out_normal")}
+    return g, s, ids, bins, vout
+
+
+@pytest.mark.parametrize("name", ["torch_impl_raster_c1.npz", "torch_impl_raster_b.npz", "torch_impl_raster_nouv.npz"])
+def test_golden_torch_impl_fixture(golden_dir, name):
+    """CUDA vs the vectors made by the reference's own _torch_impl (+ torch autograd)."""
+    g, s, ids, bins, vout = _golden_scene(golden_dir, name)
+    f, scratch = forward_cuda(s, ids, bins)
+    for k in ("out_img", "out_reg", "out_texture", "out_normal", "out_depth"):
+        np.testing.assert_allclose(to_np(f[k]), g[k], rtol=1e-4, atol=2e-5, err_msg=k)
+    np.testing.assert_allclose(1 - to_np(f["final_Ts"]), g["out_alpha"], rtol=1e-4, atol=2e-5)
+    b = backward_cuda(s, ids, bins, f, vout, scratch=scratch)
+    for k in ("v_colors", "v_means", "v_scales", "v_quats", "v_uv0", "v_umap", "v_vmap", "v_texture"):
+        ref = g[k]
+        np.testing.assert_allclose(to_np(b[k]).reshape(ref.shape), ref, rtol=2e-3,
+                                   atol=1e-6 + 1e-4 * float(np.abs(ref).max()), err_msg=k)
+    ref = g["v_opacities"]
+    np.testing.assert_allclose(to_np(b["v_opacity"]).reshape(ref.shape), ref, rtol=2e-3,
+                               atol=1e-6 + 1e-4 * float(np.abs(ref).max()))
+    # backward without the forward scratch (re-packs) gives the same gradients bit for bit ... up to atomics order
+    b2 = backward_cuda(s, ids, bins, f, vout, scratch=None)
+    for k in oracle.BWD_KEYS:
+        np.testing.assert_allclose(to_np(b2[k]), to_np(b[k]), rtol=1e-4, atol=1e-7 + 1e-5 * float(to_np(b[k]).__abs__().max()))
+
+
+CASES = [
+    # n, W, H, bw, settings, channels, seed
+    (10, 32, 32, 16, 1 << 8, 3, 1),
+    (200, 96, 64, 16, 1 << 8, 3, 2),          # non-square
+    (200, 70, 45, 16, 1 << 8, 3, 3),          # image not a multiple of the tile
+    (300, 64, 64, 8, 1 << 8, 3, 4),           # 8x8 tiles
+    (150, 50, 50, 10, 1 << 8, 3, 5),          # tile whose thread count is not a warp multiple
+    (400, 96, 96, 16, 0, 3, 6),               # no UV gradient
+    (400, 96, 96, 16, (1 << 8) | (1 << 9), 3, 7),    # blur
+    (400, 96, 96, 16, (1 << 8) | (1 << 10), 3, 8),   # ndc distortion
+    (400, 96, 96, 16, (1 << 8) | (1 << 2), 3, 9),    # nearest texel
+    (300, 64, 64, 16, 1 << 8, 5, 10),         # generic channel count
+    (300, 64, 64, 16, 1 << 8, 1, 11),
+    (3000, 160, 128, 16, 1 << 8, 3, 12),      # long lists: several 128-record stages per tile, early termination
+]
+
+
+@pytest.mark.parametrize("n,W,H,bw,settings,C,seed", CASES)
+def test_raster_forward_backward_vs_oracle(n, W, H, bw, settings, C, seed):
+    s = random_small_scene(n, W, H, seed=seed, channels=C, device=DEV)
+    s["settings"], s["block_width"] = settings, bw
+    b = bin_cuda(s, bw)
+    ids, bins = b["gaussian_ids_sorted"], b["tile_bins"]
+    f_c, scratch = forward_cuda(s, ids, bins)
+    f_o = forward_oracle(s, to_np(ids), to_np(bins))
+    print(f"case n={n} {W}x{H} bw={bw} settings={settings:#x} C={C}: M={b['num_intersects']}")
+    compare_forward(f_c, f_o, max_bad_frac=FLIP, int_bad_frac=FLIP)
+    vout = random_vout(s, seed)
+    b_c = backward_cuda(s, ids, bins, f_c, vout, scratch=scratch)
+    b_o = backward_oracle(s, to_np(ids), to_np(bins), f_c, vout)
+    compare_backward(b_c, b_o, max_bad_frac=FLIP)
+    if not (settings & (1 << 8)):
+        for k in ("v_uv0", "v_umap", "v_vmap"):
+            assert float(b_c[k].abs().max()) == 0.0  # exactly zero without bit 8
+    assert float(b_c["v_scales"][:, 2].abs().max()) == 0.0  # quirk 10
+
+
+def test_opaque_stack_terminates_and_caps_alpha():
+    """Many opaque, overlapping Gaussians: alpha cap 0.99 and the T(1-alpha) <= 1e-4 stop rule are hit."""
+    s = random_small_scene(500, 64, 64, seed=21, device=DEV, spread=2.0, scale_pow=0.1)
+    s["opacities"][:] = 1.0
+    b = bin_cuda(s)
+    f_c, scratch = forward_cuda(s, b["gaussian_ids_sorted"], b["tile_bins"])
+    f_o = forward_oracle(s, to_np(b["gaussian_ids_sorted"]), to_np(b["tile_bins"]))
+    assert float((f_o["final_Ts"] < 1e-2).mean()) > 0.2  # the scene really saturates
+    compare_forward(f_c, f_o, max_bad_frac=FLIP, int_bad_frac=FLIP)
+    vout = random_vout(s, 5)
+    b_c = backward_cuda(s, b["gaussian_ids_sorted"], b["tile_bins"], f_c, vout, scratch=scratch)
+    b_o = backward_oracle(s, to_np(b["gaussian_ids_sorted"]), to_np(b["tile_bins"]), f_c, vout)
+    compare_backward(b_c, b_o, max_bad_frac=FLIP)
+
+
+def test_behind_camera_and_empty_tiles():
+    s = random_small_scene(60, 64, 64, seed=33, device=DEV)
+    s["means"][:20, 2] = -9.5  # behind the camera at z = -8 -> clipped, never listed
+    s["means"][20:, 0] = s["means"][20:, 0].abs() * 0.3 + 1.0  # everything on the right half: empty tiles on the left
+    b = bin_cuda(s)
+    bins = to_np(b["tile_bins"])
+    assert (bins[:, 0] == bins[:, 1]).any()
+    f_c, scratch = forward_cuda(s, b["gaussian_ids_sorted"], b["tile_bins"])
+    f_o = forward_oracle(s, to_np(b["gaussian_ids_sorted"]), to_np(b["tile_bins"]))
+    compare_forward(f_c, f_o, max_bad_frac=FLIP, int_bad_frac=FLIP)
+    vout = random_vout(s, 1)
+    b_c = backward_cuda(s, b["gaussian_ids_sorted"], b["tile_bins"], f_c, vout, scratch=scratch)
+    b_o = backward_oracle(s, to_np(b["gaussian_ids_sorted"]), to_np(b["tile_bins"]), f_c, vout)
+    compare_backward(b_c, b_o, max_bad_frac=FLIP)
+    assert float(b_c["v_means"][:20].abs().max()) == 0.0
+
+
+def test_c4_style_scene_reduced():
+    """BASELINE config 4 at reduced size (20k Gaussians, 320x180, SH degree 3, 4x4 texels): the scene
+    statistics of the headline benchmark (sub-pixel to few-pixel Gaussians) at a size the oracle finishes."""
+    s = synthetic_scene(20000, 320, 180, seed=1234, device=DEV)
+    dirs = s["means"] - s["c2w"][:3, 3]
+    s["colors"] = torch.clamp(SH.spherical_harmonics(3, dirs, s["sh_coeffs"]) + 0.5, 0.0, 1.0).contiguous()
+    b = bin_cuda(s)
+    ids, bins = b["gaussian_ids_sorted"], b["tile_bins"]
+    print("M =", b["num_intersects"])
+    f_c, scratch = forward_cuda(s, ids, bins)
+    f_o = forward_oracle(s, to_np(ids), to_np(bins))
+    compare_forward(f_c, f_o, rtol=1e-3, atol=2e-4, max_bad_frac=FLIP, int_bad_frac=5e-3)
+    vout = random_vout(s, 3)
+    b_c = backward_cuda(s, ids, bins, f_c, vout, scratch=scratch)
+    b_o = backward_oracle(s, to_np(ids), to_np(bins), f_c, vout)
+    compare_backward(b_c, b_o, rtol=5e-3, rel_atol=5e-4, max_bad_frac=5e-3)
+
+
+def test_unsupported_settings_fail_loudly():
+    s = random_small_scene(10, 32, 32, seed=1, device=DEV)
+    b = bin_cuda(s)
+    with pytest.raises(RuntimeError, match="settings"):
+        forward_cuda(s, b["gaussian_ids_sorted"], b["tile_bins"], settings=(1 << 8) | (1 << 16))
