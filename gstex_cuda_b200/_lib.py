@@ -47,6 +47,14 @@ _PROTOS = {
     "gstex_texture_sample_forward": (c_i, [c_i, c_i, c_fp, c_fp, c_fp, c_fp, c_fp]),
     "gstex_texture_sample_backward": (c_i, [c_i, c_i, c_fp, c_fp, c_fp, c_fp, c_fp]),
     "gstex_image_loss": (c_i, [c_i, c_i] + [c_fp] * 11 + [c_fp]),
+    "gstex_pad_texture": (c_i, [c_i64, c_fp, c_fp, c_fp]),
+    "gstex_unpad_texture_grad": (c_i, [c_i64, c_fp, c_fp, c_i, c_fp]),
+    "gstex_pack_records": (c_i, [c_i] + [c_fp] * 5 + [c_f] + [c_fp] * 6 + [c_f] * 4 + [c_fp, c_fp, c_fp]),
+    "gstex_raster_forward": (c_i, [c_i] * 5 + [c_fp] * 7 + [c_f] * 4 + [c_fp] * 10 + [c_fp]),
+    "gstex_raster_backward": (c_i, [c_i] * 5 + [c_fp] * 7 + [c_f] * 4 + [c_fp] * 11 + [c_fp, c_fp] + [c_fp]),
+    "gstex_raster_epilogue": (c_i, [c_i, c_fp, c_fp, c_f] + [c_fp] * 5 + [c_f] * 4 + [c_fp] * 9 + [c_i, c_fp]),
+    "gstex_sh_colors_forward": (c_i, [c_i, c_i, c_i] + [c_fp] * 5 + [c_fp]),
+    "gstex_sh_colors_backward": (c_i, [c_i, c_i, c_i] + [c_fp] * 5 + [c_i, c_fp]),
 }
 
 # entry points that may be absent from an older build of the library (checked lazily)

@@ -5,7 +5,7 @@
 // epilogue_kernel: per-Gaussian gradient moments (written by the backward rasteriser) -> gradients of
 //                  means / scales / quats / opacity / colour / uv0 / umap / vmap.  No atomics, no zero-fill.
 // Both mirror tests/formulation.py::pack_record / ::epilogue line by line (same names).
-#include "common.cuh"
+#include "raster.cuh"
 
 namespace gstex {
 

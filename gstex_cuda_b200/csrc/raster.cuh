@@ -170,4 +170,47 @@ struct RasterCommon {
     float fx, fy, cx, cy;
 };
 
+struct ForwardOut {
+    float *out_img, *out_depth, *out_reg, *out_texture, *out_normal, *final_Ts, *out_reg_s;
+    int32_t *final_idx, *depth_idx;
+};
+
+struct BackwardIn {
+    const float *final_Ts, *final_s;
+    const int32_t *final_idx, *depth_idx;
+    const float *v_img, *v_depth, *v_reg, *v_alpha, *v_tex, *v_normal;
+};
+
+struct BackwardOut {
+    float4 *acc;    // n x 8 float4 moment lines (zero-filled before the launch)
+    float4 *vtex4;  // X x float4 texel gradients (channels == 3; accumulated into)
+    float *vtex;    // X x C texel gradients (generic channel count; accumulated into)
+};
+
+struct FwdLayout {
+    size_t recs_off, mean2d_off, tex4_off, total;
+};
+
+// host-side launchers shared between the reference-shaped entry points and the staged ones (pipeline.cu)
+RasterCommon make_raster_common(int img_height, int img_width, int block_width, int channels, int settings,
+                                const int32_t *ids, const int32_t *tile_bins, const float4 *recs, const float2 *mean2d,
+                                const float4 *tex4, const float *tex, const float *viewmat, const float *c2w,
+                                const float *background, float fx, float fy, float cx, float cy);
+int launch_raster_forward(const RasterCommon &p, const ForwardOut &o, cudaStream_t s);
+int launch_raster_backward(const RasterCommon &p, const BackwardIn &in, const BackwardOut &o, cudaStream_t s);
+int launch_pack(int n, const float *means, const float *scales, float glob_scale, const float *quats,
+                const float *opacities, const float *colors, const float *uv0, const float *umap, const float *vmap,
+                const int32_t *texture_dims, const float *viewmat, const float *c2w, float fx, float fy, float cx,
+                float cy, float4 *recs, float2 *mean2d, cudaStream_t s);
+int launch_epilogue(int n, const float *means, const float *scales, float glob_scale, const float *quats,
+                    const float *umap, const float *vmap, const float *viewmat, const float *c2w, float fx, float fy,
+                    float cx, float cy, const float4 *acc, float *v_colors, float *v_opacity, float *v_means,
+                    float *v_scales, float *v_quats, float *v_uv0, float *v_umap, float *v_vmap, int accumulate,
+                    cudaStream_t s);
+int launch_pad_texture(int64_t num_texels, const float *tex, float4 *tex4, cudaStream_t s);
+int launch_unpad_texture_grad(int64_t num_texels, const float4 *g4, float *v_texture, int accumulate, cudaStream_t s);
+FwdLayout forward_layout(int n, int64_t num_texels, int channels);
+int check_raster_args(const char *who, int img_height, int img_width, int block_width, int n, int64_t num_texels,
+                      int channels, int settings);
+
 }  // namespace gstex

@@ -18,18 +18,6 @@
 
 namespace gstex {
 
-struct BackwardIn {
-    const float *final_Ts, *final_s;
-    const int32_t *final_idx, *depth_idx;
-    const float *v_img, *v_depth, *v_reg, *v_alpha, *v_tex, *v_normal;
-};
-
-struct BackwardOut {
-    float4 *acc;    // n x 8 float4 moment lines (zero-filled before the launch)
-    float4 *vtex4;  // X x float4 texel gradients (channels == 3, zero-filled)
-    float *vtex;    // X x C texel gradients (generic channel count)
-};
-
 // Sum the 32 per-lane slots over the warp.  Returns, in every lane, the totals of quad (lane >> 2).
 __device__ __forceinline__ float4 warp_reduce_slots(float (&a)[32], int lane) {
     const unsigned full = 0xffffffffu;
@@ -258,19 +246,19 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS) raster_backward_kernel(con
     }
 }
 
-// defined in pack.cu / raster_forward.cu
-int launch_epilogue(int n, const float *means, const float *scales, float glob_scale, const float *quats,
-                    const float *umap, const float *vmap, const float *viewmat, const float *c2w, float fx, float fy,
-                    float cx, float cy, const float4 *acc, float *v_colors, float *v_opacity, float *v_means,
-                    float *v_scales, float *v_quats, float *v_uv0, float *v_umap, float *v_vmap, int accumulate,
-                    cudaStream_t s);
-int launch_unpad_texture_grad(int64_t num_texels, const float4 *g4, float *v_texture, int accumulate, cudaStream_t s);
-struct FwdLayout {
-    size_t recs_off, mean2d_off, tex4_off, total;
-};
-FwdLayout forward_layout(int n, int64_t num_texels, int channels);
-int check_raster_args(const char *who, int img_height, int img_width, int block_width, int n, int64_t num_texels,
-                      int channels, int settings);
+int launch_raster_backward(const RasterCommon &p, const BackwardIn &in, const BackwardOut &o, cudaStream_t s) {
+    const dim3 grid(p.tiles_x, ceil_div(p.img_h, p.bw));
+    const bool blur = (p.settings & GSTEX_SET_BLUR) != 0;
+    if (p.channels == 3) {
+        if (blur) raster_backward_kernel<true, true><<<grid, p.nthreads, 0, s>>>(p, in, o);
+        else raster_backward_kernel<true, false><<<grid, p.nthreads, 0, s>>>(p, in, o);
+    } else {
+        if (blur) raster_backward_kernel<false, true><<<grid, p.nthreads, 0, s>>>(p, in, o);
+        else raster_backward_kernel<false, false><<<grid, p.nthreads, 0, s>>>(p, in, o);
+    }
+    GSTEX_LAUNCH_OK("raster_backward_kernel");
+    return GSTEX_OK;
+}
 
 struct BwdLayout {
     size_t acc_off, vtex4_off, total;
@@ -326,37 +314,15 @@ extern "C" int gstex_texture_backward(
         GSTEX_CUDA_OK(cudaMemsetAsync(v_texture, 0, sizeof(float) * (size_t)channels * (size_t)num_texels, s));
     }
 
-    RasterCommon p;
-    p.img_w = img_width;
-    p.img_h = img_height;
-    p.tiles_x = ceil_div(img_width, block_width);
-    p.bw = block_width;
-    p.nthreads = ceil_div(block_width * block_width, 32) * 32;
-    p.settings = settings;
-    p.channels = channels;
-    p.ids = gaussian_ids_sorted;
-    p.bins = (const int2 *)tile_bins;
-    p.recs = (const float4 *)(fbase + FL.recs_off);
-    p.mean2d = (const float2 *)(fbase + FL.mean2d_off);
-    p.tex4 = (const float4 *)(fbase + FL.tex4_off);
-    p.tex = texture;
-    p.viewmat = viewmat;
-    p.c2w = c2w;
-    p.background = background;
-    p.fx = fx; p.fy = fy; p.cx = cx; p.cy = cy;
+    const RasterCommon p = make_raster_common(
+        img_height, img_width, block_width, channels, settings, gaussian_ids_sorted, tile_bins,
+        (const float4 *)(fbase + FL.recs_off), (const float2 *)(fbase + FL.mean2d_off),
+        (const float4 *)(fbase + FL.tex4_off), texture, viewmat, c2w, background, fx, fy, cx, cy);
     BackwardIn in{final_Ts, final_s, final_idx, depth_idx, v_out_img, v_out_depth, v_out_reg, v_out_alpha, v_out_texture,
                   v_out_normal};
     BackwardOut o{acc, vtex4, v_texture};
-    const dim3 grid(p.tiles_x, ceil_div(img_height, block_width));
-    const bool blur = (settings & GSTEX_SET_BLUR) != 0;
-    if (channels == 3) {
-        if (blur) raster_backward_kernel<true, true><<<grid, p.nthreads, 0, s>>>(p, in, o);
-        else raster_backward_kernel<true, false><<<grid, p.nthreads, 0, s>>>(p, in, o);
-    } else {
-        if (blur) raster_backward_kernel<false, true><<<grid, p.nthreads, 0, s>>>(p, in, o);
-        else raster_backward_kernel<false, false><<<grid, p.nthreads, 0, s>>>(p, in, o);
-    }
-    GSTEX_LAUNCH_OK("raster_backward_kernel");
+    rc = launch_raster_backward(p, in, o, s);
+    if (rc != GSTEX_OK) return rc;
     rc = launch_epilogue(n, means, scales, glob_scale, quats, umap, vmap, viewmat, c2w, fx, fy, cx, cy, acc, v_colors,
                          v_opacity, v_means, v_scales, v_quats, v_uv0, v_umap, v_vmap, accumulate, s);
     if (rc != GSTEX_OK) return rc;

@@ -15,11 +15,6 @@
 
 namespace gstex {
 
-struct ForwardOut {
-    float *out_img, *out_depth, *out_reg, *out_texture, *out_normal, *final_Ts, *out_reg_s;
-    int32_t *final_idx, *depth_idx;
-};
-
 // C3 = true : 3-channel texture read through the padded float4 copy, accumulators in registers.
 // C3 = false: runtime channel count (<= 64) read from the caller's (X,C) array (slow generic path).
 template <bool C3, bool BLUR>
@@ -154,16 +149,44 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS) raster_forward_kernel(cons
     }
 }
 
-// defined in pack.cu
-int launch_pack(int n, const float *means, const float *scales, float glob_scale, const float *quats,
-                const float *opacities, const float *colors, const float *uv0, const float *umap, const float *vmap,
-                const int32_t *texture_dims, const float *viewmat, const float *c2w, float fx, float fy, float cx,
-                float cy, float4 *recs, float2 *mean2d, cudaStream_t s);
-int launch_pad_texture(int64_t num_texels, const float *tex, float4 *tex4, cudaStream_t s);
+RasterCommon make_raster_common(int img_height, int img_width, int block_width, int channels, int settings,
+                                const int32_t *ids, const int32_t *tile_bins, const float4 *recs, const float2 *mean2d,
+                                const float4 *tex4, const float *tex, const float *viewmat, const float *c2w,
+                                const float *background, float fx, float fy, float cx, float cy) {
+    RasterCommon p;
+    p.img_w = img_width;
+    p.img_h = img_height;
+    p.tiles_x = ceil_div(img_width, block_width);
+    p.bw = block_width;
+    p.nthreads = ceil_div(block_width * block_width, 32) * 32;
+    p.settings = settings;
+    p.channels = channels;
+    p.ids = ids;
+    p.bins = (const int2 *)tile_bins;
+    p.recs = recs;
+    p.mean2d = mean2d;
+    p.tex4 = tex4;
+    p.tex = tex;
+    p.viewmat = viewmat;
+    p.c2w = c2w;
+    p.background = background;
+    p.fx = fx; p.fy = fy; p.cx = cx; p.cy = cy;
+    return p;
+}
 
-struct FwdLayout {
-    size_t recs_off, mean2d_off, tex4_off, total;
-};
+int launch_raster_forward(const RasterCommon &p, const ForwardOut &o, cudaStream_t s) {
+    const dim3 grid(p.tiles_x, ceil_div(p.img_h, p.bw));
+    const bool blur = (p.settings & GSTEX_SET_BLUR) != 0;
+    if (p.channels == 3) {
+        if (blur) raster_forward_kernel<true, true><<<grid, p.nthreads, 0, s>>>(p, o);
+        else raster_forward_kernel<true, false><<<grid, p.nthreads, 0, s>>>(p, o);
+    } else {
+        if (blur) raster_forward_kernel<false, true><<<grid, p.nthreads, 0, s>>>(p, o);
+        else raster_forward_kernel<false, false><<<grid, p.nthreads, 0, s>>>(p, o);
+    }
+    GSTEX_LAUNCH_OK("raster_forward_kernel");
+    return GSTEX_OK;
+}
 
 FwdLayout forward_layout(int n, int64_t num_texels, int channels) {
     FwdLayout L;
@@ -253,34 +276,9 @@ extern "C" int gstex_texture_forward(int img_height, int img_width, int block_wi
     rc = texture_pack(n, num_texels, channels, texture_dims, colors, opacities, means, scales, glob_scale, quats, uv0,
                       umap, vmap, texture, viewmat, c2w, fx, fy, cx, cy, temp, temp_bytes, s);
     if (rc != GSTEX_OK) return rc;
-    RasterCommon p;
-    p.img_w = img_width;
-    p.img_h = img_height;
-    p.tiles_x = ceil_div(img_width, block_width);
-    p.bw = block_width;
-    p.nthreads = ceil_div(block_width * block_width, 32) * 32;
-    p.settings = settings;
-    p.channels = channels;
-    p.ids = gaussian_ids_sorted;
-    p.bins = (const int2 *)tile_bins;
-    p.recs = recs;
-    p.mean2d = mean2d;
-    p.tex4 = tex4;
-    p.tex = texture;
-    p.viewmat = viewmat;
-    p.c2w = c2w;
-    p.background = background;
-    p.fx = fx; p.fy = fy; p.cx = cx; p.cy = cy;
+    const RasterCommon p = make_raster_common(img_height, img_width, block_width, channels, settings,
+                                              gaussian_ids_sorted, tile_bins, recs, mean2d, tex4, texture, viewmat,
+                                              c2w, background, fx, fy, cx, cy);
     ForwardOut o{out_img, out_depth, out_reg, out_texture, out_normal, final_Ts, out_reg_s, final_idx, depth_idx};
-    const dim3 grid(p.tiles_x, ceil_div(img_height, block_width));
-    const bool blur = (settings & GSTEX_SET_BLUR) != 0;
-    if (channels == 3) {
-        if (blur) raster_forward_kernel<true, true><<<grid, p.nthreads, 0, s>>>(p, o);
-        else raster_forward_kernel<true, false><<<grid, p.nthreads, 0, s>>>(p, o);
-    } else {
-        if (blur) raster_forward_kernel<false, true><<<grid, p.nthreads, 0, s>>>(p, o);
-        else raster_forward_kernel<false, false><<<grid, p.nthreads, 0, s>>>(p, o);
-    }
-    GSTEX_LAUNCH_OK("raster_forward_kernel");
-    return GSTEX_OK;
+    return launch_raster_forward(p, o, s);
 }

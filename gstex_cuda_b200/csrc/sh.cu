@@ -97,6 +97,71 @@ __global__ void __launch_bounds__(256) sh_backward_kernel(int n, int K, const fl
     }
 }
 
+// Fused view-dependent colour: colours = clamp(SH(mean - camera origin) + 0.5, 0, 1)  (the torch glue around
+// the SH op in GStex-style trainers).  mask bit c = channel c was not clamped.
+template <int DEG>
+__global__ void __launch_bounds__(256) sh_colors_forward_kernel(int n, int K, const float *__restrict__ means,
+                                                                const float *__restrict__ c2w,
+                                                                const float *__restrict__ coeffs,
+                                                                float *__restrict__ colors,
+                                                                uint8_t *__restrict__ mask) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    constexpr int KU = (DEG + 1) * (DEG + 1);
+    float Y[KU];
+    const Vec3 dir = mk3(means[3 * i] - c2w[3], means[3 * i + 1] - c2w[7], means[3 * i + 2] - c2w[11]);
+    sh_basis(DEG, dir, Y);
+    const float *__restrict__ c = coeffs + (size_t)i * K * 3;
+    float v[3] = {0.5f, 0.5f, 0.5f};
+#pragma unroll
+    for (int k = 0; k < KU; ++k) {
+        v[0] = fmaf(Y[k], c[3 * k], v[0]);
+        v[1] = fmaf(Y[k], c[3 * k + 1], v[1]);
+        v[2] = fmaf(Y[k], c[3 * k + 2], v[2]);
+    }
+    unsigned m = 0;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        if (v[ch] > 0.f && v[ch] < 1.f) m |= 1u << ch;
+        colors[3 * i + ch] = fminf(fmaxf(v[ch], 0.f), 1.f);
+    }
+    mask[i] = (uint8_t)m;
+}
+
+template <int DEG>
+__global__ void __launch_bounds__(256) sh_colors_backward_kernel(int n, int K, const float *__restrict__ means,
+                                                                 const float *__restrict__ c2w,
+                                                                 const float *__restrict__ v_colors,
+                                                                 const uint8_t *__restrict__ mask,
+                                                                 float *__restrict__ v_coeffs, int accumulate) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    constexpr int KU = (DEG + 1) * (DEG + 1);
+    float Y[KU];
+    const Vec3 dir = mk3(means[3 * i] - c2w[3], means[3 * i + 1] - c2w[7], means[3 * i + 2] - c2w[11]);
+    sh_basis(DEG, dir, Y);
+    const unsigned m = mask[i];
+    const float vr = (m & 1u) ? v_colors[3 * i] : 0.f, vg = (m & 2u) ? v_colors[3 * i + 1] : 0.f;
+    const float vb = (m & 4u) ? v_colors[3 * i + 2] : 0.f;
+    float *__restrict__ o = v_coeffs + (size_t)i * K * 3;
+    if (accumulate) {
+#pragma unroll
+        for (int k = 0; k < KU; ++k) {
+            o[3 * k] += Y[k] * vr;
+            o[3 * k + 1] += Y[k] * vg;
+            o[3 * k + 2] += Y[k] * vb;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < KU; ++k) {
+            o[3 * k] = Y[k] * vr;
+            o[3 * k + 1] = Y[k] * vg;
+            o[3 * k + 2] = Y[k] * vb;
+        }
+        for (int k = KU * 3; k < K * 3; ++k) o[k] = 0.f;
+    }
+}
+
 }  // namespace gstex
 
 using namespace gstex;
@@ -142,5 +207,42 @@ extern "C" int gstex_sh_backward(int n, int degree, int degrees_to_use, const fl
         default: sh_backward_kernel<4><<<grid, 256, 0, s>>>(n, K, viewdirs, v_colors, v_coeffs, accumulate); break;
     }
     GSTEX_LAUNCH_OK("sh_backward_kernel");
+    return GSTEX_OK;
+}
+
+extern "C" int gstex_sh_colors_forward(int n, int degree, int degrees_to_use, const float *means, const float *c2w,
+                                       const float *coeffs, float *colors, uint8_t *mask, gstex_stream_t stream) {
+    int rc = check_sh("sh_colors_forward", n, degree, degrees_to_use);
+    if (rc != GSTEX_OK) return rc;
+    if (n == 0) return GSTEX_OK;
+    const int K = sh_num_bases(degree), grid = ceil_div(n, 256);
+    cudaStream_t s = as_stream(stream);
+    switch (degrees_to_use) {
+        case 0: sh_colors_forward_kernel<0><<<grid, 256, 0, s>>>(n, K, means, c2w, coeffs, colors, mask); break;
+        case 1: sh_colors_forward_kernel<1><<<grid, 256, 0, s>>>(n, K, means, c2w, coeffs, colors, mask); break;
+        case 2: sh_colors_forward_kernel<2><<<grid, 256, 0, s>>>(n, K, means, c2w, coeffs, colors, mask); break;
+        case 3: sh_colors_forward_kernel<3><<<grid, 256, 0, s>>>(n, K, means, c2w, coeffs, colors, mask); break;
+        default: sh_colors_forward_kernel<4><<<grid, 256, 0, s>>>(n, K, means, c2w, coeffs, colors, mask); break;
+    }
+    GSTEX_LAUNCH_OK("sh_colors_forward_kernel");
+    return GSTEX_OK;
+}
+
+extern "C" int gstex_sh_colors_backward(int n, int degree, int degrees_to_use, const float *means, const float *c2w,
+                                        const float *v_colors, const uint8_t *mask, float *v_coeffs, int accumulate,
+                                        gstex_stream_t stream) {
+    int rc = check_sh("sh_colors_backward", n, degree, degrees_to_use);
+    if (rc != GSTEX_OK) return rc;
+    if (n == 0) return GSTEX_OK;
+    const int K = sh_num_bases(degree), grid = ceil_div(n, 256);
+    cudaStream_t s = as_stream(stream);
+    switch (degrees_to_use) {
+        case 0: sh_colors_backward_kernel<0><<<grid, 256, 0, s>>>(n, K, means, c2w, v_colors, mask, v_coeffs, accumulate); break;
+        case 1: sh_colors_backward_kernel<1><<<grid, 256, 0, s>>>(n, K, means, c2w, v_colors, mask, v_coeffs, accumulate); break;
+        case 2: sh_colors_backward_kernel<2><<<grid, 256, 0, s>>>(n, K, means, c2w, v_colors, mask, v_coeffs, accumulate); break;
+        case 3: sh_colors_backward_kernel<3><<<grid, 256, 0, s>>>(n, K, means, c2w, v_colors, mask, v_coeffs, accumulate); break;
+        default: sh_colors_backward_kernel<4><<<grid, 256, 0, s>>>(n, K, means, c2w, v_colors, mask, v_coeffs, accumulate); break;
+    }
+    GSTEX_LAUNCH_OK("sh_colors_backward_kernel");
     return GSTEX_OK;
 }

@@ -191,6 +191,47 @@ int gstex_image_loss(int img_height, int img_width, const float *out_texture, co
                      float *v_out_depth, float *v_out_reg, float *v_out_alpha, float *v_out_texture,
                      float *v_out_normal, gstex_stream_t stream);
 
+/* ---- staged entry points (host side: gstex_cuda_b200/pipeline.py) ---------------------------------------
+ * The stages gstex_texture_forward / gstex_texture_backward run internally, exposed so that a multi-view step
+ * pads the texture once, packs records per view and accumulates all views into one gradient arena.
+ * recs: n x 32 floats, mean2d: n x 2 floats, acc: n x 32 floats (zero-filled by the caller per view),
+ * tex / vtex: (X,4) padded when channels == 3, else the caller's (X,C) layout; vtex is accumulated into. */
+int gstex_pad_texture(int64_t num_texels, const float *texture, float *tex4, gstex_stream_t stream);
+int gstex_unpad_texture_grad(int64_t num_texels, const float *g4, float *v_texture, int accumulate,
+                             gstex_stream_t stream);
+int gstex_pack_records(int n, const int32_t *texture_dims, const float *colors, const float *opacities,
+                       const float *means, const float *scales, float glob_scale, const float *quats,
+                       const float *uv0, const float *umap, const float *vmap, const float *viewmat,
+                       const float *c2w, float fx, float fy, float cx, float cy, float *recs, float *mean2d,
+                       gstex_stream_t stream);
+int gstex_raster_forward(int img_height, int img_width, int block_width, int channels, int settings,
+                         const int32_t *gaussian_ids_sorted, const int32_t *tile_bins, const float *recs,
+                         const float *mean2d, const float *tex, const float *viewmat, const float *c2w, float fx,
+                         float fy, float cx, float cy, const float *background, float *out_img, float *out_depth,
+                         float *out_reg, float *out_texture, float *out_normal, float *final_Ts,
+                         int32_t *final_idx, int32_t *depth_idx, float *out_reg_s, gstex_stream_t stream);
+int gstex_raster_backward(int img_height, int img_width, int block_width, int channels, int settings,
+                          const int32_t *gaussian_ids_sorted, const int32_t *tile_bins, const float *recs,
+                          const float *mean2d, const float *tex, const float *viewmat, const float *c2w, float fx,
+                          float fy, float cx, float cy, const float *background, const float *final_Ts,
+                          const int32_t *final_idx, const int32_t *depth_idx, const float *final_s,
+                          const float *v_out_img, const float *v_out_depth, const float *v_out_reg,
+                          const float *v_out_alpha, const float *v_out_texture, const float *v_out_normal,
+                          float *acc, float *vtex, gstex_stream_t stream);
+int gstex_raster_epilogue(int n, const float *means, const float *scales, float glob_scale, const float *quats,
+                          const float *umap, const float *vmap, const float *viewmat, const float *c2w, float fx,
+                          float fy, float cx, float cy, const float *acc, float *v_colors, float *v_opacity,
+                          float *v_means, float *v_scales, float *v_quats, float *v_uv0, float *v_umap,
+                          float *v_vmap, int accumulate, gstex_stream_t stream);
+
+/* Fused view-dependent colour around the SH op: colors = clamp(SH(means - camera origin) + 0.5, 0, 1);
+ * mask (n bytes) records which channels were not clamped and gates the backward. */
+int gstex_sh_colors_forward(int n, int degree, int degrees_to_use, const float *means, const float *c2w,
+                            const float *coeffs, float *colors, uint8_t *mask, gstex_stream_t stream);
+int gstex_sh_colors_backward(int n, int degree, int degrees_to_use, const float *means, const float *c2w,
+                             const float *v_colors, const uint8_t *mask, float *v_coeffs, int accumulate,
+                             gstex_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

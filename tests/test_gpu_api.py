@@ -62,12 +62,12 @@ def test_example_style_training_step_matches_oracle():
                         ("texture", "v_texture")):
         ref = g[k_o]
         got = to_np(leaves[k_leaf].grad).reshape(ref.shape)
-        assert_close_frac(k_o, got, ref, 2e-3, 1e-9 + 2e-4 * float(np.abs(ref).max()), 2e-3)
+        assert_close_frac(k_o, got, ref, 2e-3, 1e-9 + 2e-4 * float(np.abs(ref).max()), 2e-3, 12, 0.05)
 
 
 def test_no_intersections_returns_background():
     s = random_small_scene(5, 32, 32, seed=2, device=DEV)
-    s["means"][:, 2] = -20.0  # all behind the camera
+    s["means"][:, 0] = 1000.0  # far outside the frustum: AABBs miss every tile
     intr = s["intrins"]
     means = s["means"].clone().requires_grad_(True)
     _, depths = project_points(means, s["viewmat"], intr)
@@ -123,3 +123,24 @@ def test_project_points_autograd_and_aabb_torch_twin():
     torch.testing.assert_close(e, et, rtol=1e-4, atol=1e-2)
     R = normalized_quat_to_rotmat(s["quats"])
     torch.testing.assert_close(R @ R.transpose(-1, -2), torch.eye(3, device=DEV).expand_as(R), rtol=1e-4, atol=1e-5)
+
+
+def test_clipped_gaussians_reproduce_reference_zero_slots():
+    """Reference quirk: a clipped Gaussian (mean behind the near plane) whose projected mean is on
+    screen counts one tile in get_num_tiles_hit_2d but is skipped by the key emitter, leaving zero-filled slots
+    (key 0 -> tile 0, Gaussian 0).  The drop-in API path reproduces that bit for bit."""
+    s = random_small_scene(6, 32, 32, seed=2, device=DEV)
+    s["means"][3:, 2] = -8.0  # z_view = 0 <= 0.01: clipped
+    s["means"][3:, :2] *= 0.01
+    intr = s["intrins"]
+    _, depths = project_points(s["means"], s["viewmat"], intr)
+    centers, extents = get_aabb_2d(s["means"], s["scales"], 1, s["quats"], s["viewmat"], intr)
+    nth = get_num_tiles_hit_2d(centers, extents, 32, 32, 16)
+    assert (to_np(extents)[3:] == 0).all() and (to_np(nth)[3:] == 1).all()
+    from gstex_cuda_b200.utils import compute_cumulative_intersects, bin_and_sort_gaussians
+    m, cum = compute_cumulative_intersects(nth)
+    isect, gids, isect_s, gids_s, bins = bin_and_sort_gaussians(6, m, centers, extents, depths, cum, (2, 2, 1), 16)
+    b = oracle.bin_and_sort_gaussians(6, m, to_np(centers), to_np(extents), to_np(depths), to_np(cum), (2, 2, 1), 16)
+    for got, want in zip((isect, gids, isect_s, gids_s, bins), b):
+        np.testing.assert_array_equal(to_np(got), want)
+    assert int((to_np(isect) == 0).sum()) == 3

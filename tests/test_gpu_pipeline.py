@@ -1,0 +1,96 @@
+"""-m gpu: the fused multi-view step (gstex_cuda_b200.pipeline) against the reference-shaped API path it fuses,
+and against the CPU oracle for the SH-colour stage."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from gstex_cuda_b200 import sh as SH
+from gstex_cuda_b200.pipeline import FusedTrainStep, DataParallelTrainStep
+from gstex_cuda_b200.scenes import synthetic_scene, circle_cameras
+from gstex_cuda_b200.texture import texture_gaussians
+from gstex_cuda_b200.get_aabb_2d import get_aabb_2d, get_num_tiles_hit_2d, project_points
+from gpu_util import DEV, to_np, assert_close_frac
+
+pytestmark = pytest.mark.gpu
+
+PARAMS = ("means", "scales", "quats", "opacities", "sh_coeffs", "uv0", "umap", "vmap", "texture")
+
+
+def _api_step(s, cams, targets):
+    """The same training step through the public autograd API (one view at a time, torch glue for SH+0.5 clamp and
+    the example.py loss), gradients accumulated by autograd."""
+    leaves = {k: s[k].clone().requires_grad_(True) for k in PARAMS}
+    H, W, bw, intr = s["H"], s["W"], 16, s["intrins"]
+    total = 0.0
+    for (vm, c2w), gt in zip(cams, targets):
+        dirs = leaves["means"].detach() - c2w[:3, 3]
+        colors = torch.clamp(SH.spherical_harmonics(s["sh_degree"], dirs, leaves["sh_coeffs"]) + 0.5, 0.0, 1.0)
+        _, depths = project_points(leaves["means"].detach(), vm, intr)
+        centers, extents = get_aabb_2d(leaves["means"].detach(), leaves["scales"].detach(), 1.0, leaves["quats"].detach(), vm, intr)
+        nth = get_num_tiles_hit_2d(centers, extents, H, W, bw)
+        outs = texture_gaussians(s["texture_info"], s["texture_dims"], centers, extents, depths, nth, colors,
+                                 leaves["opacities"], leaves["means"], leaves["scales"], 1.0, leaves["quats"], leaves["uv0"],
+                                 leaves["umap"], leaves["vmap"], leaves["texture"], vm, c2w, *intr, H, W, bw, 1 << 8,
+                                 s["background"])
+        n_ = outs[5]
+        loss = (torch.nn.functional.mse_loss(outs[4], gt) + outs[2].mean()
+                + (n_[..., 0] ** 2 + n_[..., 1] ** 2 + (1 - n_[..., 2]) ** 2).mean())
+        loss.backward()
+        total += float(loss)
+    return total, {k: v.grad for k, v in leaves.items()}
+
+
+@pytest.mark.parametrize("nviews", [1, 3])
+def test_fused_step_matches_api_path(nviews):
+    s = synthetic_scene(30000, 320, 192, seed=7, device=DEV)
+    cams = [(s["viewmat"], s["c2w"])] + [(a.to(DEV), b.to(DEV)) for a, b in circle_cameras(8)[1:nviews]]
+    g = torch.Generator().manual_seed(1)
+    targets = [torch.rand(s["H"], s["W"], 3, generator=g).to(DEV) for _ in range(nviews)]
+    fused = FusedTrainStep({k: s[k] for k in PARAMS}, s["texture_dims"], s["H"], s["W"], intrins=s["intrins"],
+                           sh_degree=s["sh_degree"], background=s["background"])
+    loss = fused.step(cams, targets)
+    m = fused.check_overflow()
+    assert m > 0
+    loss_api, grads = _api_step(s, cams, targets)
+    assert abs(float(loss) - loss_api) <= 1e-4 * abs(loss_api) + 1e-6
+    names = dict(means="v_means", scales="v_scales", quats="v_quats", opacities="v_opacity", sh_coeffs="v_sh_coeffs",
+                 uv0="v_uv0", umap="v_umap", vmap="v_vmap", texture="v_texture")
+    for k, gk in names.items():
+        ref = to_np(grads[k])
+        got = to_np(fused.grads[gk]).reshape(ref.shape)
+        # same kernels on both sides: only the order of the atomic additions differs
+        assert_close_frac(gk, got, ref, 1e-3, 1e-9 + 2e-5 * float(np.abs(ref).max()), 1e-4, 12, 0.05)
+    # a second step on the same object reuses every buffer and gives the same result
+    loss2 = float(fused.step(cams, targets))
+    assert abs(loss2 - float(loss)) <= 1e-5 * abs(loss2) + 1e-7
+
+
+def test_sh_colors_fused_matches_oracle():
+    from gstex_cuda_b200 import _lib
+    s = synthetic_scene(5000, 64, 64, seed=3, device=DEV)
+    n = s["num_points"]
+    colors = torch.empty((n, 3), device=DEV)
+    mask = torch.empty((n,), dtype=torch.uint8, device=DEV)
+    lib = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    assert lib.gstex_sh_colors_forward(n, 3, 3, s["means"].data_ptr(), s["c2w"].data_ptr(), s["sh_coeffs"].data_ptr(),
+                                       colors.data_ptr(), mask.data_ptr(), st) == 0
+    dirs = to_np(s["means"]) - to_np(s["c2w"])[:3, 3]
+    raw = oracle.sh_forward(3, 3, dirs, to_np(s["sh_coeffs"])) + 0.5
+    np.testing.assert_allclose(to_np(colors), np.clip(raw, 0, 1), rtol=2e-5, atol=2e-6)
+    v = torch.randn(n, 3, device=DEV)
+    vco = torch.empty((n, 16, 3), device=DEV)
+    assert lib.gstex_sh_colors_backward(n, 3, 3, s["means"].data_ptr(), s["c2w"].data_ptr(), v.data_ptr(),
+                                        mask.data_ptr(), vco.data_ptr(), 0, st) == 0
+    gate = ((raw > 0) & (raw < 1)).astype(np.float32)
+    want = oracle.sh_backward(3, 3, dirs, to_np(v) * gate)
+    safe = np.abs(raw - np.clip(raw, 1e-5, 1 - 1e-5)) == 0  # ignore colours within rounding of the clamp
+    ok = safe.all(axis=1)
+    np.testing.assert_allclose(to_np(vco)[ok], want[ok], rtol=2e-5, atol=2e-6)
+
+
+def test_view_sharding_is_a_partition():
+    for nv, ws in ((64, 8), (7, 4), (3, 8), (64, 1)):
+        parts = [DataParallelTrainStep.shard(nv, r, ws) for r in range(ws)]
+        assert sorted(sum(parts, [])) == list(range(nv))

@@ -8,7 +8,9 @@ homography form, so results differ by rounding only):
                     at most 0.2 % of the pixels may differ; the same allowance applies to the float images
                     (a flipped median-depth Gaussian changes out_depth discontinuously)
   gradients         rtol 2e-3, atol 1e-4 * max|g|  (the backward is fed OUR forward's saved state on both
-                    sides, so forward flips do not leak into the gradient comparison)
+                    sides, so forward flips do not leak into the gradient comparison); the backward's own
+                    alpha < 1/255 test can still flip for a pair within rounding of the threshold, which moves
+                    one Gaussian's entries: <= 12 entries per tensor may exceed the tolerance, by <= 5 % of max|g|
 """
 import os
 
@@ -105,12 +107,12 @@ def test_raster_forward_backward_vs_oracle(n, W, H, bw, settings, C, seed):
 
 def test_opaque_stack_terminates_and_caps_alpha():
     """Many opaque, overlapping Gaussians: alpha cap 0.99 and the T(1-alpha) <= 1e-4 stop rule are hit."""
-    s = random_small_scene(500, 64, 64, seed=21, device=DEV, spread=2.0, scale_pow=0.1)
+    s = random_small_scene(2000, 64, 64, seed=21, device=DEV, spread=4.0, scale_pow=0.05)
     s["opacities"][:] = 1.0
     b = bin_cuda(s)
     f_c, scratch = forward_cuda(s, b["gaussian_ids_sorted"], b["tile_bins"])
     f_o = forward_oracle(s, to_np(b["gaussian_ids_sorted"]), to_np(b["tile_bins"]))
-    assert float((f_o["final_Ts"] < 1e-2).mean()) > 0.2  # the scene really saturates
+    assert float((f_o["final_Ts"] < 1e-3).mean()) > 0.2  # the scene really saturates (stop rule reached)
     compare_forward(f_c, f_o, max_bad_frac=FLIP, int_bad_frac=FLIP)
     vout = random_vout(s, 5)
     b_c = backward_cuda(s, b["gaussian_ids_sorted"], b["tile_bins"], f_c, vout, scratch=scratch)
