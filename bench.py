@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""Headline benchmark: forward+backward Mpixels/s of the textured-2DGS rasteriser hot path at 1080p with
+1M textured Gaussians (BASELINE.json), on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference algorithm on the host cores (CPU oracle port)
+
+A "step" is one training step of the hot path over one batch of synthetic views:
+  SH colours -> project / AABB / tile count -> scan -> key emit -> radix sort -> tile ranges -> pack ->
+  rasterise forward -> image loss (example.py:189-209) -> rasterise backward -> per-Gaussian epilogue ->
+  SH backward [-> NCCL all-reduce of the gradient arena when N > 1].
+N = 1 : BASELINE config 4 - one 1920x1080 view per step (the front camera of SURVEY 8d C4).
+N > 1 : BASELINE config 5 - 64 orbit views per step, sharded round-robin over the ranks, replicated
+        parameters, one all-reduce of the 0.43 GB fp32 gradient arena per step  (strong scaling).
+`value` = pixels rendered (forward+backward) by all ranks / device time (max over ranks), inputs resident in HBM.
+`e2e`   = the same metric through the reference-shaped public API (project_points, get_aabb_2d,
+          get_num_tiles_hit_2d, texture_gaussians, autograd) with the step's inputs (camera matrices and target
+          image) copied from pinned host memory and the loss read back, inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "fwd+bwd Mpixels/sec at 1080p, 1M textured Gaussians"
+UNIT = "Mpixel/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--points", type=int, default=1_000_000)
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--views", type=int, default=0, help="views per step (0: 1 at N=1, 64 at N>1)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the frame in the CPU sample (0 = auto)")
+    return ap.parse_args()
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks: sample nvidia-smi while the timed region runs
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for r in self.rows:
+            c = [x.strip() for x in r.split(",")]
+            if len(c) < 6:
+                continue
+            try:
+                sm.append(float(c[0]))
+                smax = float(c[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm (oracle port) on the host cores, on a crop of the same workload
+# --------------------------------------------------------------------------------------------------
+def cpu_step(scene_np, rows: int):
+    """One forward+backward of the top `rows` rows of the frame with the CPU oracle.  Returns seconds."""
+    import numpy as np
+
+    import oracle
+
+    s = scene_np
+    H, W, bw = rows, s["W"], 16
+    fx, fy, cx, cy = s["intrins"]
+    t0 = time.perf_counter()
+    dirs = s["means"] - s["c2w"][:3, 3]
+    raw = oracle.sh_forward(s["sh_degree"], s["sh_degree"], dirs, s["sh_coeffs"]) + 0.5
+    colors = np.clip(raw, 0.0, 1.0).astype(np.float32)
+    b = oracle.bin_view(s["means"], s["scales"], 1.0, s["quats"], s["viewmat"], s["intrins"], H, W, bw)
+    args = (H, W, bw, s["texture_dims"], b["gaussian_ids_sorted"], b["tile_bins"], colors, s["opacities"], s["means"],
+            s["scales"], 1.0, s["quats"], s["uv0"], s["umap"], s["vmap"], s["texture"], s["viewmat"], s["c2w"], fx, fy,
+            cx, cy, 1 << 8, s["background"])
+    f = oracle.texture_forward(*args)
+    P = H * W
+    gt = s["target"][:H]
+    v_tex = (2.0 * (f["out_texture"] - gt) / (3 * P)).astype(np.float32)
+    n_ = f["out_normal"]
+    v_n = (np.stack([2 * n_[..., 0], 2 * n_[..., 1], -2 * (1 - n_[..., 2])], -1) / P).astype(np.float32)
+    z = np.zeros((H, W), np.float32)
+    g = oracle.texture_backward(*args, f["final_Ts"], f["final_idx"], f["depth_idx"], f["out_reg_s"],
+                                np.zeros((H, W, 3), np.float32), z, np.full((H, W), 1.0 / P, np.float32), z, v_tex, v_n)
+    gate = ((raw > 0) & (raw < 1)).astype(np.float32)
+    oracle.sh_backward(s["sh_degree"], s["sh_degree"], dirs, g["v_colors"] * gate)
+    return time.perf_counter() - t0
+
+
+def scene_to_numpy(scene):
+    import torch
+
+    return {k: (v.detach().cpu().numpy() if torch.is_tensor(v) else v) for k, v in scene.items()}
+
+
+def run_reference(args, rank: int):
+    """--impl reference: rank 0 times the CPU oracle (a port of the reference's algorithm; the reference's own
+    CPU twin is Python and cannot travel to the GPU box) on a bounded crop, with all host threads."""
+    if rank != 0:
+        return
+    import oracle
+    from gstex_cuda_b200.scenes import synthetic_scene
+
+    scene = scene_to_numpy(synthetic_scene(args.points, args.width, args.height, seed=1234))
+    cores = oracle.num_threads()
+    rows = args.cpu_rows or 128
+    rows = min(args.height, max(16, rows // 16 * 16))
+    for _ in range(min(args.warmup, 1)):
+        cpu_step(scene, rows)
+    times = [cpu_step(scene, rows) for _ in range(max(1, args.steps))]
+    t = sum(times) / len(times)
+    value = rows * args.width / t / 1e6
+    sample = f"top {rows} of {args.height} rows of the C4 frame ({args.width}x{rows} px), {args.points} Gaussians, fwd+bwd"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+        "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * t, "higher_is_better": True,
+        "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C4 crop on host cores: " + sample, "gaussians": args.points, "sh_degree": 3,
+                   "texels_per_gaussian": 16, "width": args.width, "height": rows},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from gstex_cuda_b200.pipeline import FusedTrainStep, DataParallelTrainStep
+    from gstex_cuda_b200.scenes import synthetic_scene, circle_cameras
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (the product has no CPU path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+    H, W, N = args.height, args.width, args.points
+
+    scene = synthetic_scene(N, W, H, seed=1234, device=dev)
+    params = {k: scene[k] for k in ("means", "scales", "quats", "opacities", "sh_coeffs", "uv0", "umap", "vmap", "texture")}
+    views = args.views or (1 if world == 1 else 64)
+    if views == 1:
+        cams = [(scene["viewmat"], scene["c2w"])]
+        workload = "C4: 1 view/step, front camera"
+    else:
+        cams = [(a.to(dev), b.to(dev)) for a, b in circle_cameras(views)]
+        workload = f"C5: {views} orbit views/step sharded over {world} GPU(s), NCCL all-reduce of the gradient arena"
+    mine = DataParallelTrainStep.shard(views, rank, world)
+    gen = torch.Generator().manual_seed(99)
+    targets_host = {}
+    for v in range(views):
+        t = torch.rand(H, W, 3, generator=gen)
+        if v in mine:
+            targets_host[v] = t.pin_memory()
+    targets = [targets_host[v].to(dev) if v in targets_host else None for v in range(views)]
+
+    fused = FusedTrainStep(params, scene["texture_dims"], H, W, intrins=scene["intrins"], sh_degree=scene["sh_degree"],
+                           background=scene["background"], max_intersects=12 * N)
+    dp = DataParallelTrainStep(fused, rank, world)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up --------------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        dp.step(cams, targets)
+    barrier()
+    m_max = fused.check_overflow()
+
+    # ---- timed region: exactly K steps ----------------------------------------------------------------
+    fused.time_kernels = True
+    fused.kernel_events = []
+    launches0 = fused.launches
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = dp.step(cams, targets)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    elapsed_ms = e0.elapsed_time(e1)
+    launches = fused.launches - launches0
+    fused.time_kernels = False
+    el = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+    lc = torch.tensor([launches], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lc, op=dist.ReduceOp.SUM)
+    elapsed_ms = float(el.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = views * H * W / (ms_per_step * 1e-3) / 1e6
+    loss_val = float(loss.item())
+
+    # per-kernel device time inside the timed region (CUDA events on the launching stream)
+    ktime = {}
+    for name, a, b in fused.kernel_events:
+        ktime.setdefault(name, []).append(a.elapsed_time(b))
+    kavg = {k: sum(v) / len(v) for k, v in ktime.items()}
+    m_view0 = int(fused.cum[-1].item())  # intersections of the last view rendered by this rank
+
+    # ---- roofline of the dominant kernel -----------------------------------------------------------------
+    peak, peak_src = hbm_peak()
+    X, C, P = scene["texture"].shape[0], 3, H * W
+    M = m_view0
+    bytes_bwd = 104 * M + 12 * X + 72 * P + 100 * N + 12 * X      # SURVEY 8d, "raster bwd"
+    bytes_fwd = 104 * M + 12 * X + 68 * P                          # SURVEY 8d, "raster fwd"
+    bytes_step = 628 * N + 380 * M + 140 * P + 36 * X              # SURVEY 8d, whole step per view
+    dom = max(("raster_backward", "raster_forward"), key=lambda k: kavg.get(k, 0.0))
+    dom_bytes = bytes_bwd if dom == "raster_backward" else bytes_fwd
+    dom_ms = kavg.get(dom, float("nan"))
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms == dom_ms and dom_ms > 0 else None
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")) as f:
+            traffic = json.load(f).get(dom)
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_ms,
+                "share_of_step": (dom_ms * len(mine) / ms_per_step) if dom_ms == dom_ms else None,
+                "step": {"algorithmic_bytes_per_view": bytes_step,
+                         "achieved": bytes_step * len(mine) / (ms_per_step * 1e-3) / 1e9,
+                         "frac": bytes_step * len(mine) / (ms_per_step * 1e-3) / 1e9 / peak},
+                "kernel_ms": kavg}
+
+    # ---- end to end through the public (reference-shaped) API, host buffers -------------------------------
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, scene, cams, mine, targets_host, dev, world, views)
+
+    # ---- CPU baseline (oracle port) on a bounded crop, rank 0 at N=1 only -----------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import oracle
+
+        rows = args.cpu_rows or 256
+        rows = min(H, max(16, rows // 16 * 16))
+        t = cpu_step(scene_to_numpy(scene), rows)
+        cpu = {"value": rows * W / t / 1e6, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
+               "sample": f"top {rows} of {H} rows of the C4 frame ({W}x{rows} px, fwd+bwd, {t:.1f} s of wall time)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload, "gaussians": N, "sh_degree": 3, "texels_per_gaussian": 16,
+                       "texture_channels": 3, "width": W, "height": H, "views_per_step": views, "block_width": 16,
+                       "settings": 256, "intersections_last_view": M, "max_intersections_seen": m_max,
+                       "l2": "inputs (0.9 GB of parameters, records and textures per view) are larger than the 126 MB L2",
+                       "loss": loss_val},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(lc.item()), "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, scene, cams, mine, targets_host, dev, world, views):
+    """The metric through the drop-in public API with host inputs: per step and per view, copy the camera matrices
+    and the target image from pinned host memory, run project/AABB/count + texture_gaussians + loss + backward via
+    autograd, and read the loss back."""
+    import torch
+    import torch.distributed as dist
+
+    from gstex_cuda_b200 import sh as SH
+    from gstex_cuda_b200.get_aabb_2d import get_aabb_2d, get_num_tiles_hit_2d, project_points
+    from gstex_cuda_b200.texture import texture_gaussians
+
+    H, W, bw, intr = args.height, args.width, 16, scene["intrins"]
+    leaves = {k: scene[k].clone().requires_grad_(True) for k in
+              ("means", "scales", "quats", "opacities", "sh_coeffs", "uv0", "umap", "vmap", "texture")}
+    cams_host = [(a.cpu().pin_memory(), b.cpu().pin_memory()) for a, b in cams]
+    h2d = sum(targets_host[v].numel() * 4 + 2 * 64 for v in mine)
+
+    def one_step():
+        total = None
+        for v in mine:
+            vm = cams_host[v][0].to(dev, non_blocking=True)
+            c2w = cams_host[v][1].to(dev, non_blocking=True)
+            gt = targets_host[v].to(dev, non_blocking=True)
+            dirs = leaves["means"].detach() - c2w[:3, 3]
+            colors = torch.clamp(SH.spherical_harmonics(3, dirs, leaves["sh_coeffs"]) + 0.5, 0.0, 1.0)
+            _, depths = project_points(leaves["means"].detach(), vm, intr)
+            centers, extents = get_aabb_2d(leaves["means"].detach(), leaves["scales"].detach(), 1.0,
+                                           leaves["quats"].detach(), vm, intr)
+            nth = get_num_tiles_hit_2d(centers, extents, H, W, bw)
+            outs = texture_gaussians(scene["texture_info"], scene["texture_dims"], centers, extents, depths, nth, colors,
+                                     leaves["opacities"], leaves["means"], leaves["scales"], 1.0, leaves["quats"],
+                                     leaves["uv0"], leaves["umap"], leaves["vmap"], leaves["texture"], vm, c2w, *intr, H,
+                                     W, bw, 1 << 8, scene["background"])
+            n_ = outs[5]
+            loss = (torch.nn.functional.mse_loss(outs[4], gt) + outs[2].mean()
+                    + (n_[..., 0] ** 2 + n_[..., 1] ** 2 + (1 - n_[..., 2]) ** 2).mean())
+            loss.backward()
+            total = loss.detach() if total is None else total + loss.detach()
+        if world > 1:
+            for t in leaves.values():
+                dist.all_reduce(t.grad)
+        val = float(total.item())  # device -> host read of the step's result
+        for t in leaves.values():
+            t.grad = None
+        return val
+
+    steps = max(3, min(args.steps, 10 if views == 1 else 3))
+    for _ in range(2):
+        one_step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        one_step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    return {"value": views * H * W / (ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+            "d2h_bytes_per_step": 4, "ms_per_step": ms, "steps": steps,
+            "api": "project_points + get_aabb_2d + get_num_tiles_hit_2d + texture_gaussians (autograd), torch glue for "
+                   "SH+0.5 clamp and the example.py loss"}
+
+
+if __name__ == "__main__":
+    main()

@@ -96,8 +96,12 @@ class FusedTrainStep:
         self.vout = dict(v_out_img=torch.empty((H, W, 3), **f32), v_out_depth=torch.empty((H, W), **f32),
                          v_out_reg=torch.empty((H, W), **f32), v_out_alpha=torch.empty((H, W), **f32),
                          v_out_texture=torch.empty((H, W, C), **f32), v_out_normal=torch.empty((H, W, 3), **f32))
-        self.kernel_launches_per_view = 0
         self.max_count_seen = torch.zeros(1, **i32)
+        # bookkeeping for bench.py: number of libgstex_b200 kernels launched, optional per-kernel CUDA events
+        self.launches = 0
+        self.time_kernels = False
+        self.kernel_events: List[Tuple[str, torch.cuda.Event, torch.cuda.Event]] = []
+        self._sort_launches = 4 + 3 * (8 if self.end_bit >= 57 else -(-self.end_bit // 8))
 
     # ------------------------------------------------------------------------------------------
     def _s(self) -> int:
@@ -107,11 +111,31 @@ class FusedTrainStep:
         if rc != 0:
             raise RuntimeError(f"{what} failed (code {rc}): {_lib.last_error()}")
 
+    def _timed(self, name: str):
+        """Context manager recording a CUDA event pair around one kernel launch (bench.py roofline)."""
+        step = self
+
+        class _T:
+            def __enter__(self_inner):
+                if step.time_kernels:
+                    self_inner.a = torch.cuda.Event(enable_timing=True)
+                    self_inner.a.record()
+
+            def __exit__(self_inner, *exc):
+                if step.time_kernels:
+                    b = torch.cuda.Event(enable_timing=True)
+                    b.record()
+                    step.kernel_events.append((name, self_inner.a, b))
+                return False
+
+        return _T()
+
     def begin_step(self) -> None:
         """Once per optimiser step: pad the texture, clear the texel-gradient buffer and the loss."""
         lib, s = self.lib, self._s()
         if self.C == 3:
             self._ck(lib.gstex_pad_texture(self.X, self.p["texture"].data_ptr(), self.tex4.data_ptr(), s), "pad_texture")
+            self.launches += 1
             self.vtex4.zero_()
         else:
             self.grads["v_texture"].zero_()
@@ -145,11 +169,13 @@ class FusedTrainStep:
                  "pack_records")
         tex = self.tex4 if self.C == 3 else p["texture"]
         o = self.out
-        self._ck(lib.gstex_raster_forward(H, W, bw, self.C, self.settings, P(self.ids_sorted), P(self.tile_bins),
-                                          P(self.recs), P(self.mean2d), P(tex), P(viewmat), P(c2w), fx, fy, cx, cy,
-                                          P(self.background), P(o["out_img"]), P(o["out_depth"]), P(o["out_reg"]),
-                                          P(o["out_texture"]), P(o["out_normal"]), P(o["final_Ts"]), P(o["final_idx"]),
-                                          P(o["depth_idx"]), P(o["out_reg_s"]), s), "raster_forward")
+        with self._timed("raster_forward"):
+            self._ck(lib.gstex_raster_forward(H, W, bw, self.C, self.settings, P(self.ids_sorted), P(self.tile_bins),
+                                              P(self.recs), P(self.mean2d), P(tex), P(viewmat), P(c2w), fx, fy, cx, cy,
+                                              P(self.background), P(o["out_img"]), P(o["out_depth"]), P(o["out_reg"]),
+                                              P(o["out_texture"]), P(o["out_normal"]), P(o["final_Ts"]),
+                                              P(o["final_idx"]), P(o["depth_idx"]), P(o["out_reg_s"]), s), "raster_forward")
+        self.launches += 1 + 1 + 3 + 1 + self._sort_launches + 1 + 1 + 1  # sh, project, scan, emit, sort, edges, pack, raster
         return o
 
     def view_loss(self, target: torch.Tensor) -> None:
@@ -160,6 +186,7 @@ class FusedTrainStep:
                                            P(target), P(self.loss), P(v["v_out_img"]), P(v["v_out_depth"]),
                                            P(v["v_out_reg"]), P(v["v_out_alpha"]), P(v["v_out_texture"]),
                                            P(v["v_out_normal"]), self._s()), "image_loss")
+        self.launches += 1
 
     def view_backward(self, viewmat: torch.Tensor, c2w: torch.Tensor, vout: Optional[Dict[str, torch.Tensor]] = None) -> None:
         """Rasterise backward + epilogue + SH backward of the view last rendered; accumulates into the arena."""
@@ -175,12 +202,15 @@ class FusedTrainStep:
             self.v_colors.zero_()  # colours are per view (they feed this view's SH backward), never accumulated
         tex = self.tex4 if self.C == 3 else p["texture"]
         vtex = self.vtex4 if self.C == 3 else g["v_texture"]
-        self._ck(lib.gstex_raster_backward(H, W, bw, self.C, self.settings, P(self.ids_sorted), P(self.tile_bins),
-                                           P(self.recs), P(self.mean2d), P(tex), P(viewmat), P(c2w), fx, fy, cx, cy,
-                                           P(self.background), P(o["final_Ts"]), P(o["final_idx"]), P(o["depth_idx"]),
-                                           P(o["out_reg_s"]), P(v["v_out_img"]), P(v["v_out_depth"]), P(v["v_out_reg"]),
-                                           P(v["v_out_alpha"]), P(v["v_out_texture"]), P(v["v_out_normal"]), P(self.acc),
-                                           P(vtex), s), "raster_backward")
+        with self._timed("raster_backward"):
+            self._ck(lib.gstex_raster_backward(H, W, bw, self.C, self.settings, P(self.ids_sorted), P(self.tile_bins),
+                                               P(self.recs), P(self.mean2d), P(tex), P(viewmat), P(c2w), fx, fy, cx, cy,
+                                               P(self.background), P(o["final_Ts"]), P(o["final_idx"]),
+                                               P(o["depth_idx"]), P(o["out_reg_s"]), P(v["v_out_img"]),
+                                               P(v["v_out_depth"]), P(v["v_out_reg"]), P(v["v_out_alpha"]),
+                                               P(v["v_out_texture"]), P(v["v_out_normal"]), P(self.acc), P(vtex), s),
+                     "raster_backward")
+        self.launches += 3  # raster backward, epilogue, SH backward
         self._ck(lib.gstex_raster_epilogue(n, P(p["means"]), P(p["scales"]), self.glob_scale, P(p["quats"]), P(p["umap"]),
                                            P(p["vmap"]), P(viewmat), P(c2w), fx, fy, cx, cy, P(self.acc), P(self.v_colors),
                                            P(g["v_opacity"]), P(g["v_means"]), P(g["v_scales"]), P(g["v_quats"]),
@@ -194,6 +224,7 @@ class FusedTrainStep:
         if self.C == 3:
             self._ck(self.lib.gstex_unpad_texture_grad(self.X, self.vtex4.data_ptr(), self.grads["v_texture"].data_ptr(), 0,
                                                        self._s()), "unpad_texture_grad")
+            self.launches += 1
 
     def step(self, cameras: Sequence[Tuple[torch.Tensor, torch.Tensor]], targets: Sequence[torch.Tensor]) -> torch.Tensor:
         """forward + loss + backward for every (viewmat, c2w) of this rank; returns the summed loss (device)."""
