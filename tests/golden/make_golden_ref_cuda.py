@@ -1,0 +1,100 @@
+"""Generate golden vectors from the UNMODIFIED reference CUDA extension (oracle/_ref/gstex_ref_C.so, built by
+oracle/build_ref.py) on a GPU box:
+
+    gpurun -- 'python tests/golden/make_golden_ref_cuda.py'      # writes gpurun_out/golden/ref_cuda_*.npz
+
+The files are then copied to tests/golden/ and committed; tests/test_oracle_golden_ref_cuda.py (CPU) checks the
+oracle against them, which pins the oracle to the reference's own CUDA rasteriser (quirks included: alpha cap
+0.99, skip / stop rules, median depth, final-sum distortion gradient).  Inputs are stored in the fixture.
+"""
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from gstex_cuda_b200.scenes import random_small_scene  # noqa: E402  (scene generator only: plain torch)
+
+DEV = "cuda:0"
+OUT = os.path.join(ROOT, "gpurun_out", "golden")
+
+
+def load_ref():
+    so = os.path.join(ROOT, "oracle", "_ref", "gstex_ref_C.so")
+    spec = importlib.util.spec_from_file_location("gstex_ref_C", so)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+def make(ref, name, n, W, H, bw, settings, C, seed, opaque=False):
+    s = random_small_scene(n, W, H, seed=seed, channels=C, device=DEV)
+    if opaque:
+        s["opacities"][:] = 1.0
+    fx, fy, cx, cy = s["intrins"]
+    tb = ((W + bw - 1) // bw, (H + bw - 1) // bw, 1)
+    # reference pipeline, example.py:146-152 + texture.py:195-222 (torch glue restated with torch ops)
+    vm = s["viewmat"]
+    depths = (s["means"] @ vm[:3, :3].T + vm[:3, 3])[:, 2].contiguous()
+    centers, extents = ref.get_aabb_2d(s["means"], s["scales"], 1.0, s["quats"], vm, fx, fy, cx, cy)
+    tl = torch.floor((centers - extents) / bw).to(torch.int32)
+    br = torch.floor((centers + extents) / bw + 1).to(torch.int32)
+    tmin = torch.stack([tl[:, 0].clamp(0, tb[0]), tl[:, 1].clamp(0, tb[1])], -1)
+    tmax = torch.stack([br[:, 0].clamp(0, tb[0]), br[:, 1].clamp(0, tb[1])], -1)
+    nth = ((tmax - tmin)[:, 0] * (tmax - tmin)[:, 1]).to(torch.int32)
+    cum = torch.cumsum(nth, 0, dtype=torch.int32)
+    m = int(cum[-1])
+    isect, gids = ref.map_gaussian_to_intersects(n, m, centers, extents, depths, cum, tb, bw, False)
+    isect_s, perm = torch.sort(isect)
+    gids_s = torch.gather(gids, 0, perm)
+    bins = ref.get_tile_bin_edges(m, isect_s, tb)
+    outs = ref.texture_forward(tb, (bw, bw, 1), (W, H, 1), (n, 1, C), s["texture_dims"], gids_s, bins, s["colors"],
+                               s["opacities"], s["means"], s["scales"], 1.0, s["quats"], s["uv0"], s["umap"], s["vmap"],
+                               s["texture"], vm, s["c2w"], fx, fy, cx, cy, settings, s["background"])
+    g = torch.Generator().manual_seed(seed)
+    mk = lambda *shape: torch.randn(*shape, generator=g).to(DEV)  # noqa: E731
+    vout = dict(v_out_img=mk(H, W, 3), v_out_depth=0.1 * mk(H, W), v_out_reg=0.1 * mk(H, W), v_out_alpha=mk(H, W),
+                v_out_texture=mk(H, W, C), v_out_normal=mk(H, W, 3))
+    grads = ref.texture_backward(H, W, bw, (n, 1, C), s["texture_dims"], gids_s, bins, s["colors"], s["opacities"],
+                                 s["means"], s["scales"], 1.0, s["quats"], s["uv0"], s["umap"], s["vmap"], s["texture"],
+                                 vm, s["c2w"], fx, fy, cx, cy, settings, s["background"], outs[5], outs[6], outs[7],
+                                 outs[8], vout["v_out_img"], vout["v_out_depth"], vout["v_out_reg"], vout["v_out_alpha"],
+                                 vout["v_out_texture"], vout["v_out_normal"])
+    torch.cuda.synchronize()
+    d = dict(H=H, W=W, block_width=bw, settings=settings, glob_scale=1.0, intrins=np.array(s["intrins"], np.float32),
+             centers=npy(centers), extents=npy(extents), depths=npy(depths), num_tiles_hit=npy(nth),
+             cum_tiles_hit=npy(cum), isect_ids=npy(isect), gaussian_ids=npy(gids), isect_ids_sorted=npy(isect_s),
+             gaussian_ids_sorted=npy(gids_s), tile_bins=npy(bins))
+    for k in ("means", "scales", "quats", "colors", "opacities", "uv0", "umap", "vmap", "texture", "texture_dims",
+              "viewmat", "c2w", "background"):
+        d[k] = npy(s[k])
+    for k, o in zip(("out_img", "out_depth", "out_reg", "out_texture", "out_normal", "final_Ts", "final_idx",
+                     "depth_idx", "out_reg_s"), outs):
+        d[k] = npy(o)
+    for k, v in vout.items():
+        d[k] = npy(v)
+    for k, v in zip(("v_colors", "v_opacity", "v_means", "v_scales", "v_quats", "v_uv0", "v_umap", "v_vmap", "v_texture"),
+                    grads):
+        d[k] = npy(v)
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, name), **d)
+    print(name, "M =", m, "bytes =", os.path.getsize(os.path.join(OUT, name)))
+
+
+if __name__ == "__main__":
+    ref = load_ref()
+    make(ref, "ref_cuda_a.npz", 60, 48, 48, 16, 1 << 8, 3, 101)
+    make(ref, "ref_cuda_nonsquare.npz", 150, 80, 48, 16, 1 << 8, 3, 102)
+    make(ref, "ref_cuda_opaque.npz", 300, 48, 48, 16, 1 << 8, 3, 103, opaque=True)
+    make(ref, "ref_cuda_blur_ndc.npz", 100, 48, 48, 16, (1 << 8) | (1 << 9) | (1 << 10), 3, 104)
+    make(ref, "ref_cuda_nearest_nouv_c5.npz", 100, 48, 48, 8, (1 << 2), 5, 105)

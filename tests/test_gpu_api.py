@@ -130,8 +130,8 @@ def test_clipped_gaussians_reproduce_reference_zero_slots():
     screen counts one tile in get_num_tiles_hit_2d but is skipped by the key emitter, leaving zero-filled slots
     (key 0 -> tile 0, Gaussian 0).  The drop-in API path reproduces that bit for bit."""
     s = random_small_scene(6, 32, 32, seed=2, device=DEV)
-    s["means"][3:, 2] = -8.0  # z_view = 0 <= 0.01: clipped
-    s["means"][3:, :2] *= 0.01
+    s["means"][3:, 2] = -8.0 + 0.005  # z_view = 0.005 <= 0.01: clipped
+    s["means"][3:, :2] = 0.0           # projects onto the principal point -> on screen
     intr = s["intrins"]
     _, depths = project_points(s["means"], s["viewmat"], intr)
     centers, extents = get_aabb_2d(s["means"], s["scales"], 1, s["quats"], s["viewmat"], intr)
