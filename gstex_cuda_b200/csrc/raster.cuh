@@ -145,6 +145,11 @@ __device__ __forceinline__ void tile_pixel(int bw, int tr, int &lx, int &ly) {
     }
 }
 
+// Shared-memory stage layout: quad k of staged record r lives at float4 slot r*8 + (k ^ (r & 7)).
+// The XOR swizzle keeps the warp-uniform reads of the compositing loop broadcasts (one wavefront) and makes
+// the per-lane reads of the culling pass (lane <-> record, 128-byte stride) bank-conflict free.
+__device__ __forceinline__ int quad_slot(int r, int k) { return (r << 3) + (k ^ (r & 7)); }
+
 // Stage `cnt` records (ids[first..first+cnt)) into shared memory with 16-byte cp.async copies: eight
 // consecutive threads fetch one 128-byte record (one cache line), so both the global reads and the
 // shared-memory writes are fully coalesced / conflict-free.
@@ -152,10 +157,90 @@ __device__ __forceinline__ void stage_records(float4 *__restrict__ dst, const fl
                                               const int32_t *__restrict__ ids, int first, int cnt, int tr,
                                               int nthreads) {
     for (int c = tr; c < cnt * 8; c += nthreads) {
-        const int g = ids[first + (c >> 3)];
-        __pipeline_memcpy_async(dst + c, recs + (size_t)g * 8 + (c & 7), 16);
+        const int r = c >> 3, k = c & 7;
+        const int g = ids[first + r];
+        __pipeline_memcpy_async(dst + quad_slot(r, k), recs + (size_t)g * 8 + k, 16);
     }
     __pipeline_commit();
+}
+
+// ------------------------------------------------------------------------------------------
+// Warp-level culling.  Each warp owns a small pixel rectangle (8x4 for 16x16 tiles).  Before a staged
+// batch is composited, lane j tests records j, j+32, ... against the rectangle with an interval bound of
+// the three affine forms:  |N1| >= |N1(c)| - r1,  |N2| >= |N2(c)| - r2,  |D| <= |D(c)| + r3  over the
+// rectangle (c = its centre, r* = |P.x| hx + |P.y| hy), hence  q = (N1^2+N2^2)/D^2 >= q_min  and
+// alpha <= opac * 2^-q_min.  A record whose bound is below 0.0039 (< 1/255, 0.55 % margin for the
+// approximate ex2 / rounding) is skipped by every pixel of the warp (reference texture.cu:213), so the
+// warp never evaluates it.  Survivor indices are compacted per warp, order preserved.
+// Deviation from the reference, documented in DESIGN.md section 3: the reference tests the stop rule
+// T(1-alpha) <= 1e-4 even for Gaussians it skips; a culled Gaussian (alpha < 1/255) can only trip it when
+// T lies in (1e-4, 1.0039e-4], in which case the pixel here runs on to the next surviving Gaussian.
+// ------------------------------------------------------------------------------------------
+struct WarpRect {
+    float cx, cy, hx, hy;  // centre and half extents (pixel centres) of the warp's live pixels
+    bool any;              // at least one live pixel
+};
+
+__device__ __forceinline__ WarpRect make_warp_rect(int col, int row, bool inside) {
+    const unsigned full = 0xffffffffu;
+    const int big = 1 << 28;
+    const int x0 = __reduce_min_sync(full, inside ? col : big), x1 = __reduce_max_sync(full, inside ? col : -big);
+    const int y0 = __reduce_min_sync(full, inside ? row : big), y1 = __reduce_max_sync(full, inside ? row : -big);
+    WarpRect r;
+    r.any = x1 >= x0;
+    r.cx = 0.5f * (float)(x0 + x1) + 0.5f;
+    r.cy = 0.5f * (float)(y0 + y1) + 0.5f;
+    r.hx = 0.5f * (float)(x1 - x0);
+    r.hy = 0.5f * (float)(y1 - y0);
+    return r;
+}
+
+constexpr float CULL_ALPHA = 0.0039f;  // < 1/255 = 0.0039216
+
+template <bool BLUR>
+__device__ __forceinline__ bool record_culled(const float4 q0, const float4 q1, const float4 q2, const float4 q3,
+                                              const WarpRect &wr, const float2 *__restrict__ mean2d) {
+    const float ex = wr.cx - q0.x, ey = wr.cy - q0.y;
+    const float n1 = fmaf(q1.x, ex, fmaf(q1.y, ey, q1.z));
+    const float n2 = fmaf(q2.x, ex, fmaf(q2.y, ey, q2.z));
+    const float d = fmaf(q3.x, ex, fmaf(q3.y, ey, q1.w));
+    const float r1 = fmaf(fabsf(q1.x), wr.hx, fabsf(q1.y) * wr.hy);
+    const float r2 = fmaf(fabsf(q2.x), wr.hx, fabsf(q2.y) * wr.hy);
+    const float r3 = fmaf(fabsf(q3.x), wr.hx, fabsf(q3.y) * wr.hy);
+    const float m1 = fmaxf(fabsf(n1) - r1, 0.f), m2 = fmaxf(fabsf(n2) - r2, 0.f);
+    const float m3 = fmaxf(fabsf(d) + r3, 1e-5f);  // >= the kernels' clamp 1e-6*|R_w|
+    const float rd = fast_rcp(m3);
+    const float l1 = m1 * rd, l2 = m2 * rd;
+    float bound = q0.w * fast_exp2(-fmaf(l1, l1, l2 * l2));
+    if (BLUR) {  // the blur branch can only raise alpha: opac * exp(-|mean2d - p|^2)
+        const float2 m = mean2d[__float_as_int(q2.w)];
+        const float dx = fmaxf(fabsf(m.x - wr.cx) - wr.hx, 0.f), dy = fmaxf(fabsf(m.y - wr.cy) - wr.hy, 0.f);
+        bound = fmaxf(bound, q0.w * __expf(-fmaf(dx, dx, dy * dy)));
+    }
+    return bound < CULL_ALPHA;
+}
+
+// Builds the warp's survivor list for staged records [lo, hi) of stage S; returns the survivor count.
+template <bool BLUR>
+__device__ __forceinline__ int build_survivors(const float4 *__restrict__ S, int lo, int hi, const WarpRect &wr,
+                                               const float2 *__restrict__ mean2d, uint8_t *__restrict__ list,
+                                               int lane) {
+    const unsigned full = 0xffffffffu, lt = (1u << lane) - 1u;
+    int n = 0;
+    for (int k = lo; k < hi; k += 32) {
+        const int r = k + lane;
+        bool keep = false;
+        if (r < hi) {
+            const float4 q0 = S[quad_slot(r, 0)], q1 = S[quad_slot(r, 1)], q2 = S[quad_slot(r, 2)],
+                         q3 = S[quad_slot(r, 3)];
+            keep = !record_culled<BLUR>(q0, q1, q2, q3, wr, mean2d);
+        }
+        const unsigned m = __ballot_sync(full, keep);
+        if (keep) list[n + __popc(m & lt)] = (uint8_t)r;
+        n += __popc(m);
+    }
+    __syncwarp();
+    return n;
 }
 
 struct RasterCommon {

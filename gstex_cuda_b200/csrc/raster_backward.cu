@@ -60,6 +60,7 @@ template <bool C3, bool BLUR>
 __global__ void __launch_bounds__(RASTER_MAX_THREADS) raster_backward_kernel(const RasterCommon p, const BackwardIn in,
                                                                             const BackwardOut o) {
     __shared__ float4 stage[2][RASTER_BATCH * 8];
+    __shared__ uint8_t survivors[RASTER_MAX_THREADS / 32][RASTER_BATCH];
     __shared__ int block_last;
 
     const int tr = threadIdx.x, lane = tr & 31;
@@ -70,6 +71,8 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS) raster_backward_kernel(con
     const bool inside = (tr < p.bw * p.bw) && col < p.img_w && row < p.img_h;
     const int pix = inside ? row * p.img_w + col : 0;
     const PixelConsts pc = make_pixel(col, row, p.c2w, p.viewmat, p.fx, p.fy, p.cx, p.cy);
+    const WarpRect wr = make_warp_rect(col, row, inside);
+    uint8_t *__restrict__ my_list = survivors[tr >> 5];
     const bool use_ndc = (p.settings & GSTEX_SET_NDC) != 0;
     const bool bilinear = !(p.settings & GSTEX_SET_NEAREST);
     const bool prop_uv = (p.settings & GSTEX_SET_PROPAGATE_UV) != 0;
@@ -120,9 +123,14 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS) raster_backward_kernel(con
         }
         __syncthreads();
         const float4 *__restrict__ S = stage[b & 1];
-        for (int i = min(cnt - 1, warp_last - first); i >= 0; --i) {
+        // warp-level culling (raster.cuh): same survivor set as the forward pass, walked back to front
+        const int nsurv = build_survivors<BLUR>(S, 0, min(cnt, warp_last - first + 1), wr, p.mean2d, my_list, lane);
+        for (int si = nsurv - 1; si >= 0; --si) {
+            const int i = my_list[si];
             const int idx = first + i;
-            const float4 q0 = S[i * 8 + 0], q1 = S[i * 8 + 1], q2 = S[i * 8 + 2], q3 = S[i * 8 + 3];
+            const int sw = i & 7;
+            const float4 *__restrict__ R = S + (i << 3);
+            const float4 q0 = R[sw], q1 = R[1 ^ sw], q2 = R[2 ^ sw], q3 = R[3 ^ sw];
             bool valid = inside && idx <= bfinal;
             PairEval pe;
             if (valid) {
@@ -135,7 +143,7 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS) raster_backward_kernel(con
 #pragma unroll
             for (int k = 0; k < 32; ++k) a[k] = 0.f;
             if (valid) {
-                const float4 q4 = S[i * 8 + 4], q5 = S[i * 8 + 5], q6 = S[i * 8 + 6], q7 = S[i * 8 + 7];
+                const float4 q4 = R[4 ^ sw], q5 = R[5 ^ sw], q6 = R[6 ^ sw], q7 = R[7 ^ sw];
                 const float alpha = pe.alpha;
                 T *= 1.f / (1.f - alpha);  // reference texture.cu:579-580
                 const float vis = alpha * T;

@@ -20,14 +20,17 @@ namespace gstex {
 template <bool C3, bool BLUR>
 __global__ void __launch_bounds__(RASTER_MAX_THREADS) raster_forward_kernel(const RasterCommon p, const ForwardOut o) {
     __shared__ float4 stage[2][RASTER_BATCH * 8];
+    __shared__ uint8_t survivors[RASTER_MAX_THREADS / 32][RASTER_BATCH];
 
-    const int tr = threadIdx.x;
+    const int tr = threadIdx.x, lane = tr & 31;
+    uint8_t *__restrict__ my_list = survivors[tr >> 5];
     const int tile = blockIdx.y * p.tiles_x + blockIdx.x;
     int lx, ly;
     tile_pixel(p.bw, tr, lx, ly);
     const int col = blockIdx.x * p.bw + lx, row = blockIdx.y * p.bw + ly;
     const bool inside = (tr < p.bw * p.bw) && col < p.img_w && row < p.img_h;
     const PixelConsts pc = make_pixel(col, row, p.c2w, p.viewmat, p.fx, p.fy, p.cx, p.cy);
+    const WarpRect wr = make_warp_rect(col, row, inside);
     const bool use_ndc = (p.settings & GSTEX_SET_NDC) != 0;
     const bool bilinear = !(p.settings & GSTEX_SET_NEAREST);
     const int C = C3 ? 3 : p.channels;
@@ -61,9 +64,14 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS) raster_forward_kernel(cons
         // stage b is visible to the whole CTA after this barrier; leave if every pixel is finished
         if (__syncthreads_count(done) >= p.nthreads) break;
         const float4 *__restrict__ S = stage[b & 1];
+        // warp-level culling: the warp walks only the records that can reach alpha >= 1/255 on its patch
+        const int nsurv = __all_sync(0xffffffffu, done) ? 0 : build_survivors<BLUR>(S, 0, cnt, wr, p.mean2d, my_list, lane);
         if (!done) {
-            for (int i = 0; i < cnt; ++i) {
-                const float4 q0 = S[i * 8 + 0], q1 = S[i * 8 + 1], q2 = S[i * 8 + 2], q3 = S[i * 8 + 3];
+            for (int si = 0; si < nsurv; ++si) {
+                const int i = my_list[si];
+                const int sw = i & 7;
+                const float4 *__restrict__ R = S + (i << 3);
+                const float4 q0 = R[sw], q1 = R[1 ^ sw], q2 = R[2 ^ sw], q3 = R[3 ^ sw];
                 PairEval pe;
                 eval_pair<BLUR>(q0, q1, q2, q3, pc, p.mean2d, pe);
                 const float next_T = __fmul_rn(T, __fsub_rn(1.f, pe.alpha));
@@ -73,7 +81,7 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS) raster_forward_kernel(cons
                 }
                 if (pair_skipped(pe)) continue;
 
-                const float4 q4 = S[i * 8 + 4], q5 = S[i * 8 + 5], q6 = S[i * 8 + 6], q7 = S[i * 8 + 7];
+                const float4 q4 = R[4 ^ sw], q5 = R[5 ^ sw], q6 = R[6 ^ sw], q7 = R[7 ^ sw];
                 const float vis = pe.alpha * T;
                 acc_c0 = fmaf(q6.x, vis, acc_c0);
                 acc_c1 = fmaf(q6.y, vis, acc_c1);
