@@ -268,7 +268,7 @@ def main():
     for name, a, b in fused.kernel_events:
         ktime.setdefault(name, []).append(a.elapsed_time(b))
     kavg = {k: sum(v) / len(v) for k, v in ktime.items()}
-    m_view0 = int(fused.cum[-1].item())  # intersections of the last view rendered by this rank
+    m_view0 = int(fused.num_isect.item())  # intersections of the last view rendered by this rank
 
     # ---- roofline of the dominant kernel -----------------------------------------------------------------
     peak, peak_src = hbm_peak()

@@ -35,6 +35,8 @@ _PROTOS = {
     "gstex_sort_temp_bytes": (c_sz, [c_i64]),
     "gstex_sort_pairs": (c_i, [c_i64, c_fp, c_fp, c_fp, c_fp, c_i, c_fp, c_fp, c_sz, c_fp]),
     "gstex_get_tile_bin_edges": (c_i, [c_i64, c_fp, c_fp, c_fp, c_fp]),
+    "gstex_bin_tiles_temp_bytes": (c_sz, [c_i, c_i64]),
+    "gstex_bin_tiles": (c_i, [c_i, c_fp, c_fp, c_fp, c_i, c_i, c_i, c_i64, c_fp, c_fp, c_fp, c_fp, c_fp, c_sz, c_fp]),
     "gstex_texture_forward_temp_bytes": (c_sz, [c_i, c_i64, c_i]),
     "gstex_texture_backward_temp_bytes": (c_sz, [c_i, c_i64, c_i]),
     "gstex_texture_pack": (c_i, [c_i, c_i64, c_i] + [c_fp] * 5 + [c_f] + [c_fp] * 7 + [c_f] * 4 + [c_fp, c_sz, c_fp]),

@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(CSRC, "_build")
 LIB = os.path.join(HERE, "libgstex_b200.so")
-SOURCES = ["util.cu", "project.cu", "binning.cu", "pack.cu", "raster_forward.cu", "raster_backward.cu", "sh.cu",
+SOURCES = ["util.cu", "project.cu", "binning.cu", "binning_tiles.cu", "pack.cu", "raster_forward.cu", "raster_backward.cu", "sh.cu",
            "texture_sample.cu", "loss.cu", "pipeline.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xptxas", "-v", "--expt-relaxed-constexpr"]

@@ -46,120 +46,175 @@ __device__ __forceinline__ void sh_basis(int deg, Vec3 dir, float *Y) {
     Y[24] = 0.6258357354491761f * (xx * (xx - 3.f * yy) - yy * (3.f * xx - yy));
 }
 
-template <int DEG>
-__global__ void __launch_bounds__(256) sh_forward_kernel(int n, int K, const float *__restrict__ viewdirs,
-                                                         const float *__restrict__ coeffs,
-                                                         float *__restrict__ colors) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    constexpr int KU = (DEG + 1) * (DEG + 1);
-    float Y[KU];
-    sh_basis(DEG, ld3(viewdirs + 3 * i), Y);
-    const float *__restrict__ c = coeffs + (size_t)i * K * 3;
-    float r = 0.f, g = 0.f, b = 0.f;
-#pragma unroll
-    for (int k = 0; k < KU; ++k) {
-        r = fmaf(Y[k], c[3 * k], r);
-        g = fmaf(Y[k], c[3 * k + 1], g);
-        b = fmaf(Y[k], c[3 * k + 2], b);
-    }
-    colors[3 * i] = r;
-    colors[3 * i + 1] = g;
-    colors[3 * i + 2] = b;
-}
+// ------------------------------------------------------------------------------------------
+// Tiled kernels.  One CTA = SH_ROWS Gaussians = one CONTIGUOUS block of SH_ROWS * L floats (L = 3K) of the
+// coefficient array.  The block is moved between global and shared memory with fully coalesced 16-byte
+// accesses and each thread then works on its own row of the tile (row pitch L|1 floats: odd, so the 32 lanes
+// of a warp hit 32 different banks).  A thread-per-Gaussian kernel reading its 192-byte row directly runs at
+// ~1/6 of HBM bandwidth (measured: 0.30 ms for the 192 MB backward write at N = 1M, degree 3).
+// ------------------------------------------------------------------------------------------
+constexpr int SH_ROWS = 128;
 
-template <int DEG>
-__global__ void __launch_bounds__(256) sh_backward_kernel(int n, int K, const float *__restrict__ viewdirs,
-                                                          const float *__restrict__ v_colors,
-                                                          float *__restrict__ v_coeffs, int accumulate) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    constexpr int KU = (DEG + 1) * (DEG + 1);
-    float Y[KU];
-    sh_basis(DEG, ld3(viewdirs + 3 * i), Y);
-    const float vr = v_colors[3 * i], vg = v_colors[3 * i + 1], vb = v_colors[3 * i + 2];
-    float *__restrict__ o = v_coeffs + (size_t)i * K * 3;
-    if (accumulate) {
-#pragma unroll
-        for (int k = 0; k < KU; ++k) {
-            o[3 * k] += Y[k] * vr;
-            o[3 * k + 1] += Y[k] * vg;
-            o[3 * k + 2] += Y[k] * vb;
+__host__ __device__ inline int sh_pitch(int L) { return L | 1; }
+
+__device__ __forceinline__ void sh_tile_load(float *__restrict__ tile, int pitch, const float *__restrict__ g,
+                                             int rows, int L, bool vec4) {
+    const int total = rows * L;
+    if (vec4) {
+        const float4 *__restrict__ g4 = reinterpret_cast<const float4 *>(g);
+        for (int q = threadIdx.x; q < (total >> 2); q += blockDim.x) {
+            const float4 v = g4[q];
+            const int e = q << 2, r = e / L, c = e - r * L;  // L % 4 == 0: the four floats share a row
+            float *__restrict__ d = tile + r * pitch + c;
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
         }
     } else {
-#pragma unroll
-        for (int k = 0; k < KU; ++k) {
-            o[3 * k] = Y[k] * vr;
-            o[3 * k + 1] = Y[k] * vg;
-            o[3 * k + 2] = Y[k] * vb;
+        for (int e = threadIdx.x; e < total; e += blockDim.x) {
+            const int r = e / L, c = e - r * L;
+            tile[r * pitch + c] = g[e];
         }
-        for (int k = KU * 3; k < K * 3; ++k) o[k] = 0.f;  // rows beyond degrees_to_use (torch::zeros upstream)
     }
 }
 
-// Fused view-dependent colour: colours = clamp(SH(mean - camera origin) + 0.5, 0, 1)  (the torch glue around
-// the SH op in GStex-style trainers).  mask bit c = channel c was not clamped.
-template <int DEG>
-__global__ void __launch_bounds__(256) sh_colors_forward_kernel(int n, int K, const float *__restrict__ means,
-                                                                const float *__restrict__ c2w,
-                                                                const float *__restrict__ coeffs,
-                                                                float *__restrict__ colors,
-                                                                uint8_t *__restrict__ mask) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+__device__ __forceinline__ void sh_tile_store(const float *__restrict__ tile, int pitch, float *__restrict__ g,
+                                              int rows, int L, bool vec4, int accumulate) {
+    const int total = rows * L;
+    if (vec4) {
+        float4 *__restrict__ g4 = reinterpret_cast<float4 *>(g);
+        for (int q = threadIdx.x; q < (total >> 2); q += blockDim.x) {
+            const int e = q << 2, r = e / L, c = e - r * L;
+            const float *__restrict__ d = tile + r * pitch + c;
+            float4 v = make_float4(d[0], d[1], d[2], d[3]);
+            if (accumulate) {
+                const float4 old = g4[q];
+                v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
+            }
+            g4[q] = v;
+        }
+    } else {
+        for (int e = threadIdx.x; e < total; e += blockDim.x) {
+            const int r = e / L, c = e - r * L;
+            const float v = tile[r * pitch + c];
+            g[e] = accumulate ? g[e] + v : v;
+        }
+    }
+}
+
+// FUSED = false: colours = SH(viewdirs) . coeffs                       (reference sh.cuh:212-232)
+// FUSED = true : dirs = means - camera origin; colours = clamp(SH + 0.5, 0, 1); mask bit c = channel c not clamped
+//                (the torch glue around the SH op in GStex-style trainers)
+template <int DEG, bool FUSED>
+__global__ void __launch_bounds__(SH_ROWS) sh_forward_tiled(int n, int K, const float *__restrict__ dirs_or_means,
+                                                            const float *__restrict__ c2w,
+                                                            const float *__restrict__ coeffs,
+                                                            float *__restrict__ colors, uint8_t *__restrict__ mask,
+                                                            int vec4) {
+    extern __shared__ float sh_tile[];
     constexpr int KU = (DEG + 1) * (DEG + 1);
+    const int L = 3 * K, pitch = sh_pitch(L);
+    const int row0 = blockIdx.x * SH_ROWS, rows = min(SH_ROWS, n - row0);
+    sh_tile_load(sh_tile, pitch, coeffs + (size_t)row0 * L, rows, L, vec4 != 0);
+    __syncthreads();
+    const int t = threadIdx.x, i = row0 + t;
+    if (t >= rows) return;
+    Vec3 dir = ld3(dirs_or_means + 3 * (size_t)i);
+    if (FUSED) dir = mk3(dir.x - c2w[3], dir.y - c2w[7], dir.z - c2w[11]);
     float Y[KU];
-    const Vec3 dir = mk3(means[3 * i] - c2w[3], means[3 * i + 1] - c2w[7], means[3 * i + 2] - c2w[11]);
     sh_basis(DEG, dir, Y);
-    const float *__restrict__ c = coeffs + (size_t)i * K * 3;
-    float v[3] = {0.5f, 0.5f, 0.5f};
+    const float *__restrict__ c = sh_tile + t * pitch;
+    float v[3];
+    v[0] = v[1] = v[2] = FUSED ? 0.5f : 0.f;
 #pragma unroll
     for (int k = 0; k < KU; ++k) {
         v[0] = fmaf(Y[k], c[3 * k], v[0]);
         v[1] = fmaf(Y[k], c[3 * k + 1], v[1]);
         v[2] = fmaf(Y[k], c[3 * k + 2], v[2]);
     }
-    unsigned m = 0;
+    if (FUSED) {
+        unsigned m = 0;
 #pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
-        if (v[ch] > 0.f && v[ch] < 1.f) m |= 1u << ch;
-        colors[3 * i + ch] = fminf(fmaxf(v[ch], 0.f), 1.f);
+        for (int ch = 0; ch < 3; ++ch) {
+            if (v[ch] > 0.f && v[ch] < 1.f) m |= 1u << ch;
+            v[ch] = fminf(fmaxf(v[ch], 0.f), 1.f);
+        }
+        mask[i] = (uint8_t)m;
     }
-    mask[i] = (uint8_t)m;
+    colors[3 * (size_t)i] = v[0];
+    colors[3 * (size_t)i + 1] = v[1];
+    colors[3 * (size_t)i + 2] = v[2];
 }
 
-template <int DEG>
-__global__ void __launch_bounds__(256) sh_colors_backward_kernel(int n, int K, const float *__restrict__ means,
-                                                                 const float *__restrict__ c2w,
-                                                                 const float *__restrict__ v_colors,
-                                                                 const uint8_t *__restrict__ mask,
-                                                                 float *__restrict__ v_coeffs, int accumulate) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+// v_coeffs[b, c] = Y_b * v_colors[c] for b < num_bases(degrees_to_use), 0 beyond (reference sh.cuh:234-253; no
+// gradient to the directions).  FUSED gates v_colors with the clamp mask of the forward pass.
+template <int DEG, bool FUSED>
+__global__ void __launch_bounds__(SH_ROWS) sh_backward_tiled(int n, int K, const float *__restrict__ dirs_or_means,
+                                                             const float *__restrict__ c2w,
+                                                             const float *__restrict__ v_colors,
+                                                             const uint8_t *__restrict__ mask,
+                                                             float *__restrict__ v_coeffs, int accumulate, int vec4) {
+    extern __shared__ float sh_tile[];
     constexpr int KU = (DEG + 1) * (DEG + 1);
-    float Y[KU];
-    const Vec3 dir = mk3(means[3 * i] - c2w[3], means[3 * i + 1] - c2w[7], means[3 * i + 2] - c2w[11]);
-    sh_basis(DEG, dir, Y);
-    const unsigned m = mask[i];
-    const float vr = (m & 1u) ? v_colors[3 * i] : 0.f, vg = (m & 2u) ? v_colors[3 * i + 1] : 0.f;
-    const float vb = (m & 4u) ? v_colors[3 * i + 2] : 0.f;
-    float *__restrict__ o = v_coeffs + (size_t)i * K * 3;
-    if (accumulate) {
+    const int L = 3 * K, pitch = sh_pitch(L);
+    const int row0 = blockIdx.x * SH_ROWS, rows = min(SH_ROWS, n - row0);
+    const int t = threadIdx.x, i = row0 + t;
+    if (t < rows) {
+        Vec3 dir = ld3(dirs_or_means + 3 * (size_t)i);
+        if (FUSED) dir = mk3(dir.x - c2w[3], dir.y - c2w[7], dir.z - c2w[11]);
+        float Y[KU];
+        sh_basis(DEG, dir, Y);
+        float vr = v_colors[3 * (size_t)i], vg = v_colors[3 * (size_t)i + 1], vb = v_colors[3 * (size_t)i + 2];
+        if (FUSED) {
+            const unsigned m = mask[i];
+            vr = (m & 1u) ? vr : 0.f;
+            vg = (m & 2u) ? vg : 0.f;
+            vb = (m & 4u) ? vb : 0.f;
+        }
+        float *__restrict__ c = sh_tile + t * pitch;
 #pragma unroll
         for (int k = 0; k < KU; ++k) {
-            o[3 * k] += Y[k] * vr;
-            o[3 * k + 1] += Y[k] * vg;
-            o[3 * k + 2] += Y[k] * vb;
+            c[3 * k] = Y[k] * vr;
+            c[3 * k + 1] = Y[k] * vg;
+            c[3 * k + 2] = Y[k] * vb;
         }
-    } else {
-#pragma unroll
-        for (int k = 0; k < KU; ++k) {
-            o[3 * k] = Y[k] * vr;
-            o[3 * k + 1] = Y[k] * vg;
-            o[3 * k + 2] = Y[k] * vb;
-        }
-        for (int k = KU * 3; k < K * 3; ++k) o[k] = 0.f;
+        for (int k = KU * 3; k < L; ++k) c[k] = 0.f;  // rows beyond degrees_to_use (torch::zeros upstream)
     }
+    __syncthreads();
+    sh_tile_store(sh_tile, pitch, v_coeffs + (size_t)row0 * L, rows, L, vec4 != 0, accumulate);
+}
+
+template <bool FUSED>
+static int launch_sh_forward(int n, int degree, int degrees_to_use, const float *dirs_or_means, const float *c2w,
+                             const float *coeffs, float *colors, uint8_t *mask, cudaStream_t s) {
+    const int K = sh_num_bases(degree), L = 3 * K, grid = ceil_div(n, SH_ROWS);
+    const size_t smem = sizeof(float) * SH_ROWS * sh_pitch(L);
+    const int vec4 = (L % 4 == 0) && ((uintptr_t)coeffs % 16 == 0);
+    switch (degrees_to_use) {
+        case 0: sh_forward_tiled<0, FUSED><<<grid, SH_ROWS, smem, s>>>(n, K, dirs_or_means, c2w, coeffs, colors, mask, vec4); break;
+        case 1: sh_forward_tiled<1, FUSED><<<grid, SH_ROWS, smem, s>>>(n, K, dirs_or_means, c2w, coeffs, colors, mask, vec4); break;
+        case 2: sh_forward_tiled<2, FUSED><<<grid, SH_ROWS, smem, s>>>(n, K, dirs_or_means, c2w, coeffs, colors, mask, vec4); break;
+        case 3: sh_forward_tiled<3, FUSED><<<grid, SH_ROWS, smem, s>>>(n, K, dirs_or_means, c2w, coeffs, colors, mask, vec4); break;
+        default: sh_forward_tiled<4, FUSED><<<grid, SH_ROWS, smem, s>>>(n, K, dirs_or_means, c2w, coeffs, colors, mask, vec4); break;
+    }
+    GSTEX_LAUNCH_OK("sh_forward_tiled");
+    return GSTEX_OK;
+}
+
+template <bool FUSED>
+static int launch_sh_backward(int n, int degree, int degrees_to_use, const float *dirs_or_means, const float *c2w,
+                              const float *v_colors, const uint8_t *mask, float *v_coeffs, int accumulate,
+                              cudaStream_t s) {
+    const int K = sh_num_bases(degree), L = 3 * K, grid = ceil_div(n, SH_ROWS);
+    const size_t smem = sizeof(float) * SH_ROWS * sh_pitch(L);
+    const int vec4 = (L % 4 == 0) && ((uintptr_t)v_coeffs % 16 == 0);
+    switch (degrees_to_use) {
+        case 0: sh_backward_tiled<0, FUSED><<<grid, SH_ROWS, smem, s>>>(n, K, dirs_or_means, c2w, v_colors, mask, v_coeffs, accumulate, vec4); break;
+        case 1: sh_backward_tiled<1, FUSED><<<grid, SH_ROWS, smem, s>>>(n, K, dirs_or_means, c2w, v_colors, mask, v_coeffs, accumulate, vec4); break;
+        case 2: sh_backward_tiled<2, FUSED><<<grid, SH_ROWS, smem, s>>>(n, K, dirs_or_means, c2w, v_colors, mask, v_coeffs, accumulate, vec4); break;
+        case 3: sh_backward_tiled<3, FUSED><<<grid, SH_ROWS, smem, s>>>(n, K, dirs_or_means, c2w, v_colors, mask, v_coeffs, accumulate, vec4); break;
+        default: sh_backward_tiled<4, FUSED><<<grid, SH_ROWS, smem, s>>>(n, K, dirs_or_means, c2w, v_colors, mask, v_coeffs, accumulate, vec4); break;
+    }
+    GSTEX_LAUNCH_OK("sh_backward_tiled");
+    return GSTEX_OK;
 }
 
 }  // namespace gstex
@@ -179,17 +234,7 @@ extern "C" int gstex_sh_forward(int n, int degree, int degrees_to_use, const flo
     int rc = check_sh("sh_forward", n, degree, degrees_to_use);
     if (rc != GSTEX_OK) return rc;
     if (n == 0) return GSTEX_OK;
-    const int K = sh_num_bases(degree), grid = ceil_div(n, 256);
-    cudaStream_t s = as_stream(stream);
-    switch (degrees_to_use) {
-        case 0: sh_forward_kernel<0><<<grid, 256, 0, s>>>(n, K, viewdirs, coeffs, colors); break;
-        case 1: sh_forward_kernel<1><<<grid, 256, 0, s>>>(n, K, viewdirs, coeffs, colors); break;
-        case 2: sh_forward_kernel<2><<<grid, 256, 0, s>>>(n, K, viewdirs, coeffs, colors); break;
-        case 3: sh_forward_kernel<3><<<grid, 256, 0, s>>>(n, K, viewdirs, coeffs, colors); break;
-        default: sh_forward_kernel<4><<<grid, 256, 0, s>>>(n, K, viewdirs, coeffs, colors); break;
-    }
-    GSTEX_LAUNCH_OK("sh_forward_kernel");
-    return GSTEX_OK;
+    return launch_sh_forward<false>(n, degree, degrees_to_use, viewdirs, nullptr, coeffs, colors, nullptr, as_stream(stream));
 }
 
 extern "C" int gstex_sh_backward(int n, int degree, int degrees_to_use, const float *viewdirs, const float *v_colors,
@@ -197,17 +242,7 @@ extern "C" int gstex_sh_backward(int n, int degree, int degrees_to_use, const fl
     int rc = check_sh("sh_backward", n, degree, degrees_to_use);
     if (rc != GSTEX_OK) return rc;
     if (n == 0) return GSTEX_OK;
-    const int K = sh_num_bases(degree), grid = ceil_div(n, 256);
-    cudaStream_t s = as_stream(stream);
-    switch (degrees_to_use) {
-        case 0: sh_backward_kernel<0><<<grid, 256, 0, s>>>(n, K, viewdirs, v_colors, v_coeffs, accumulate); break;
-        case 1: sh_backward_kernel<1><<<grid, 256, 0, s>>>(n, K, viewdirs, v_colors, v_coeffs, accumulate); break;
-        case 2: sh_backward_kernel<2><<<grid, 256, 0, s>>>(n, K, viewdirs, v_colors, v_coeffs, accumulate); break;
-        case 3: sh_backward_kernel<3><<<grid, 256, 0, s>>>(n, K, viewdirs, v_colors, v_coeffs, accumulate); break;
-        default: sh_backward_kernel<4><<<grid, 256, 0, s>>>(n, K, viewdirs, v_colors, v_coeffs, accumulate); break;
-    }
-    GSTEX_LAUNCH_OK("sh_backward_kernel");
-    return GSTEX_OK;
+    return launch_sh_backward<false>(n, degree, degrees_to_use, viewdirs, nullptr, v_colors, nullptr, v_coeffs, accumulate, as_stream(stream));
 }
 
 extern "C" int gstex_sh_colors_forward(int n, int degree, int degrees_to_use, const float *means, const float *c2w,
@@ -215,17 +250,7 @@ extern "C" int gstex_sh_colors_forward(int n, int degree, int degrees_to_use, co
     int rc = check_sh("sh_colors_forward", n, degree, degrees_to_use);
     if (rc != GSTEX_OK) return rc;
     if (n == 0) return GSTEX_OK;
-    const int K = sh_num_bases(degree), grid = ceil_div(n, 256);
-    cudaStream_t s = as_stream(stream);
-    switch (degrees_to_use) {
-        case 0: sh_colors_forward_kernel<0><<<grid, 256, 0, s>>>(n, K, means, c2w, coeffs, colors, mask); break;
-        case 1: sh_colors_forward_kernel<1><<<grid, 256, 0, s>>>(n, K, means, c2w, coeffs, colors, mask); break;
-        case 2: sh_colors_forward_kernel<2><<<grid, 256, 0, s>>>(n, K, means, c2w, coeffs, colors, mask); break;
-        case 3: sh_colors_forward_kernel<3><<<grid, 256, 0, s>>>(n, K, means, c2w, coeffs, colors, mask); break;
-        default: sh_colors_forward_kernel<4><<<grid, 256, 0, s>>>(n, K, means, c2w, coeffs, colors, mask); break;
-    }
-    GSTEX_LAUNCH_OK("sh_colors_forward_kernel");
-    return GSTEX_OK;
+    return launch_sh_forward<true>(n, degree, degrees_to_use, means, c2w, coeffs, colors, mask, as_stream(stream));
 }
 
 extern "C" int gstex_sh_colors_backward(int n, int degree, int degrees_to_use, const float *means, const float *c2w,
@@ -234,15 +259,5 @@ extern "C" int gstex_sh_colors_backward(int n, int degree, int degrees_to_use, c
     int rc = check_sh("sh_colors_backward", n, degree, degrees_to_use);
     if (rc != GSTEX_OK) return rc;
     if (n == 0) return GSTEX_OK;
-    const int K = sh_num_bases(degree), grid = ceil_div(n, 256);
-    cudaStream_t s = as_stream(stream);
-    switch (degrees_to_use) {
-        case 0: sh_colors_backward_kernel<0><<<grid, 256, 0, s>>>(n, K, means, c2w, v_colors, mask, v_coeffs, accumulate); break;
-        case 1: sh_colors_backward_kernel<1><<<grid, 256, 0, s>>>(n, K, means, c2w, v_colors, mask, v_coeffs, accumulate); break;
-        case 2: sh_colors_backward_kernel<2><<<grid, 256, 0, s>>>(n, K, means, c2w, v_colors, mask, v_coeffs, accumulate); break;
-        case 3: sh_colors_backward_kernel<3><<<grid, 256, 0, s>>>(n, K, means, c2w, v_colors, mask, v_coeffs, accumulate); break;
-        default: sh_colors_backward_kernel<4><<<grid, 256, 0, s>>>(n, K, means, c2w, v_colors, mask, v_coeffs, accumulate); break;
-    }
-    GSTEX_LAUNCH_OK("sh_colors_backward_kernel");
-    return GSTEX_OK;
+    return launch_sh_backward<true>(n, degree, degrees_to_use, means, c2w, v_colors, mask, v_coeffs, accumulate, as_stream(stream));
 }

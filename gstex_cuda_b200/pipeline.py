@@ -4,11 +4,12 @@ SH backward, for every view of the rank's share of a batch, with NO host synchro
 
 This is the host side of the hot path for BASELINE configs 4 and 5.  It replaces, per view,
 the ~60 torch/extension launches and the blocking ``.item()`` of the reference trainer (example.py:121-209,
-utils.py:58) with ~35 launches of libgstex_b200 kernels on one stream over preallocated buffers:
+utils.py:58) with ~16 launches of libgstex_b200 kernels on one stream over preallocated buffers:
 
-* the intersection count never leaves the device: every stage after the scan reads it from ``cum[n-1]``;
-  key / id buffers have a fixed capacity (``max_intersects``) and the emitter drops what does not fit -
-  ``check_overflow()`` reports it when the caller next synchronises anyway;
+* binning is the fused bucket-by-tile + per-tile shared-memory sort of csrc/binning_tiles.cu (bit-identical ids and
+  tile ranges, no cumulative sum, no global 64-bit sort); the intersection count never leaves the device, the id
+  buffer has a fixed capacity (``max_intersects``) and what does not fit is dropped - ``check_overflow()`` reports
+  it when the caller next synchronises anyway;
 * the texture is padded to float4 once per step, texel gradients of all views accumulate in one padded
   buffer and are un-padded once per step;
 * parameter gradients of all views accumulate in ONE contiguous fp32 arena (``grad_arena``), which is what
@@ -81,11 +82,10 @@ class FusedTrainStep:
         # ---- per-view buffers
         self.colors, self.mask, self.v_colors = torch.empty((n, 3), **f32), torch.empty((n,), dtype=torch.uint8, device=dev), torch.empty((n, 3), **f32)
         self.centers, self.extents, self.depths = torch.empty((n, 2), **f32), torch.empty((n, 2), **f32), torch.empty((n,), **f32)
-        self.nth, self.cum = torch.empty((n,), **i32), torch.empty((n,), **i32)
-        self.scan_temp = torch.empty((self.lib.gstex_scan_temp_bytes(n),), dtype=torch.uint8, device=dev)
-        self.keys, self.keys_sorted = torch.empty((self.cap,), dtype=torch.int64, device=dev), torch.empty((self.cap,), dtype=torch.int64, device=dev)
-        self.ids, self.ids_sorted = torch.empty((self.cap,), **i32), torch.empty((self.cap,), **i32)
-        self.sort_temp = torch.empty((self.lib.gstex_sort_temp_bytes(self.cap),), dtype=torch.uint8, device=dev)
+        self.nth = torch.empty((n,), **i32)
+        self.ids_sorted = torch.empty((self.cap,), **i32)
+        self.num_isect = torch.zeros((1,), **i32)
+        self.bin_temp = torch.empty((self.lib.gstex_bin_tiles_temp_bytes(self.num_tiles, self.cap),), dtype=torch.uint8, device=dev)
         self.tile_bins = torch.empty((self.num_tiles, 2), **i32)
         self.recs, self.mean2d, self.acc = torch.empty((n, 32), **f32), torch.empty((n, 2), **f32), torch.empty((n, 32), **f32)
         self.out = dict(out_img=torch.empty((H, W, 3), **f32), out_depth=torch.empty((H, W), **f32),
@@ -101,7 +101,7 @@ class FusedTrainStep:
         self.launches = 0
         self.time_kernels = False
         self.kernel_events: List[Tuple[str, torch.cuda.Event, torch.cuda.Event]] = []
-        self._sort_launches = 4 + 3 * (8 if self.end_bit >= 57 else -(-self.end_bit // 8))
+        self._bin_launches = 6  # tile count, tile scan, scatter, three per-tile sort size classes
 
     # ------------------------------------------------------------------------------------------
     def _s(self) -> int:
@@ -153,16 +153,11 @@ class FusedTrainStep:
         self._ck(lib.gstex_project_aabb_count(n, P(p["means"]), P(p["scales"]), self.glob_scale, P(p["quats"]), P(viewmat),
                                               fx, fy, cx, cy, H, W, bw, P(self.centers), P(self.extents), P(self.depths),
                                               P(self.nth), s), "project_aabb_count")
-        self._ck(lib.gstex_cumsum_i32(n, P(self.nth), P(self.cum), P(self.scan_temp), self.scan_temp.numel(), s), "cumsum")
-        d_count = self.cum.data_ptr() + 4 * (n - 1)  # number of intersections, on the device
-        self._ck(lib.gstex_map_gaussian_to_intersects(n, self.cap, P(self.centers), P(self.extents), P(self.depths),
-                                                      P(self.cum), self.tiles_x, self.tiles_y, bw, P(self.keys),
-                                                      P(self.ids), s), "map_gaussian_to_intersects")
-        self._ck(lib.gstex_sort_pairs(self.cap, P(self.keys), P(self.ids), P(self.keys_sorted), P(self.ids_sorted),
-                                      self.end_bit, d_count, P(self.sort_temp), self.sort_temp.numel(), s), "sort_pairs")
-        self.tile_bins.zero_()
-        self._ck(lib.gstex_get_tile_bin_edges(self.cap, P(self.keys_sorted), P(self.tile_bins), d_count, s), "tile_bin_edges")
-        torch.maximum(self.max_count_seen, self.cum[n - 1:n], out=self.max_count_seen)
+        # fused tile binning: bucket by tile + per-tile shared-memory sort; the intersection count stays on the device
+        self._ck(lib.gstex_bin_tiles(n, P(self.centers), P(self.extents), P(self.depths), self.tiles_x, self.tiles_y, bw,
+                                     self.cap, P(self.ids_sorted), 0, P(self.tile_bins), P(self.num_isect),
+                                     P(self.bin_temp), self.bin_temp.numel(), s), "bin_tiles")
+        torch.maximum(self.max_count_seen, self.num_isect, out=self.max_count_seen)
         self._ck(lib.gstex_pack_records(n, P(self.texture_dims), P(self.colors), P(p["opacities"]), P(p["means"]),
                                         P(p["scales"]), self.glob_scale, P(p["quats"]), P(p["uv0"]), P(p["umap"]),
                                         P(p["vmap"]), P(viewmat), P(c2w), fx, fy, cx, cy, P(self.recs), P(self.mean2d), s),
@@ -175,7 +170,7 @@ class FusedTrainStep:
                                               P(self.background), P(o["out_img"]), P(o["out_depth"]), P(o["out_reg"]),
                                               P(o["out_texture"]), P(o["out_normal"]), P(o["final_Ts"]),
                                               P(o["final_idx"]), P(o["depth_idx"]), P(o["out_reg_s"]), s), "raster_forward")
-        self.launches += 1 + 1 + 3 + 1 + self._sort_launches + 1 + 1 + 1  # sh, project, scan, emit, sort, edges, pack, raster
+        self.launches += 1 + 1 + self._bin_launches + 1 + 1  # sh, project, binning, pack, raster
         return o
 
     def view_loss(self, target: torch.Tensor) -> None:

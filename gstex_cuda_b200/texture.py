@@ -12,7 +12,7 @@ from torch import Tensor
 from torch.autograd import Function
 
 from . import cuda as _C
-from .utils import bin_and_sort_gaussians, compute_cumulative_intersects
+from .utils import bin_and_sort_gaussians, bin_tiles, compute_cumulative_intersects  # noqa: F401
 
 
 def texture_gaussians(texture_info: Tuple[int, int, int], texture_dims: Tensor, centers: Tensor, extents: Tensor,
@@ -66,8 +66,10 @@ class _TextureGaussians(Function):
             ctx.save_for_backward(colors, opacity, means, scales, quats, uv0, umap, vmap, texture)
             return (out_img, zeros, zeros.clone(), zeros.clone(), torch.zeros(img_height, img_width, C, **f32),
                     torch.zeros(img_height, img_width, 3, **f32))
-        _, _, _, gaussian_ids_sorted, tile_bins = bin_and_sort_gaussians(
-            num_points, num_intersects, centers, extents, depths, cum_tiles_hit, tile_bounds, block_width)
+        # same gaussian_ids_sorted / tile_bins as bin_and_sort_gaussians (utils.py:106-162 upstream), from the fused
+        # bucket-by-tile + per-tile sort (csrc/binning_tiles.cu) instead of the global 64-bit key sort
+        gaussian_ids_sorted, tile_bins, _, _ = bin_tiles(centers, extents, depths, tile_bounds, block_width,
+                                                         num_intersects)
         outputs, scratch = _C.texture_forward_ex(
             tile_bounds, block, img_size, texture_info, texture_dims, gaussian_ids_sorted, tile_bins, colors, opacity,
             means, scales, glob_scale, quats, uv0, umap, vmap, texture, viewmat, c2w, fx, fy, cx, cy, settings,

@@ -88,3 +88,30 @@ def bin_and_sort_gaussians(num_points: int, num_intersects: int, centers: Tensor
     isect_ids_sorted, gaussian_ids_sorted = sort_pairs(isect_ids, gaussian_ids)
     tile_bins = get_tile_bin_edges(num_intersects, isect_ids_sorted, tile_bounds)
     return isect_ids, gaussian_ids, isect_ids_sorted, gaussian_ids_sorted, tile_bins
+
+
+def bin_tiles(centers: Tensor, extents: Tensor, depths: Tensor, tile_bounds: Tuple[int, int, int], block_size: int,
+              capacity: int, want_isect_ids: bool = False):
+    """Fused tile binning (csrc/binning_tiles.cu): bucket by tile, then sort each tile's list in shared memory.
+
+    Returns ``(gaussian_ids_sorted[capacity], tile_bins, num_intersects_dev[1], isect_ids_sorted or None)`` -
+    bit-identical to ``bin_and_sort_gaussians`` (utils.py:106-162 upstream) on the first ``num_intersects`` entries,
+    without the cumulative sum, the 64-bit global sort or any host synchronisation."""
+    if not (centers.is_cuda and extents.is_cuda and depths.is_cuda):
+        raise RuntimeError("bin_tiles expects CUDA tensors")
+    centers, extents, depths = centers.contiguous(), extents.contiguous(), depths.contiguous()
+    dev = centers.device
+    n = centers.shape[0]
+    tx, ty = int(tile_bounds[0]), int(tile_bounds[1])
+    lib = _lib.load()
+    ids = torch.empty((capacity,), dtype=torch.int32, device=dev)
+    isect = torch.empty((capacity,), dtype=torch.int64, device=dev) if want_isect_ids else None
+    bins = torch.empty((tx * ty, 2), dtype=torch.int32, device=dev)
+    count = torch.empty((1,), dtype=torch.int32, device=dev)
+    temp = torch.empty((lib.gstex_bin_tiles_temp_bytes(tx * ty, capacity),), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.gstex_bin_tiles(n, centers.data_ptr(), extents.data_ptr(), depths.data_ptr(), tx, ty, int(block_size),
+                                 int(capacity), ids.data_ptr(), isect.data_ptr() if isect is not None else 0,
+                                 bins.data_ptr(), count.data_ptr(), temp.data_ptr(), temp.numel(), _stream(dev))
+    _lib.check(rc, "bin_tiles")
+    return ids, bins, count, isect

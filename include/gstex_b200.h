@@ -106,6 +106,20 @@ int gstex_sort_pairs(int64_t m, const int64_t *keys_in, const int32_t *vals_in, 
 int gstex_get_tile_bin_edges(int64_t m, const int64_t *isect_ids_sorted, int32_t *tile_bins,
                              const int32_t *d_count, gstex_stream_t stream);
 
+/* Fused tile binning for the no-host-sync pipeline: replaces, in one call and with bit-identical
+ * gaussian_ids_sorted / tile_bins, the chain cumsum -> map_gaussian_to_intersects -> sort -> get_tile_bin_edges
+ * (gstex_cuda/utils.py:40-162, forward.cu:13-98).  Buckets the intersections by tile with atomics, then one CTA per
+ * tile sorts its short list by (depth bits, gaussian id) in shared memory (csrc/binning_tiles.cu).
+ * capacity: length of gaussian_ids_sorted / isect_ids_sorted; intersections past it are dropped and tile_bins is
+ * clipped to it.  isect_ids_sorted may be NULL.  tile_bins (num_tiles,2) is fully written ((0,0) for empty tiles).
+ * num_intersects: one int32 on the device = the true number of intersections (compare with capacity to detect
+ * overflow). */
+size_t gstex_bin_tiles_temp_bytes(int num_tiles, int64_t capacity);
+int gstex_bin_tiles(int n, const float *centers, const float *extents, const float *depths, int tiles_x, int tiles_y,
+                    int block_width, int64_t capacity, int32_t *gaussian_ids_sorted, int64_t *isect_ids_sorted,
+                    int32_t *tile_bins, int32_t *num_intersects, void *temp, size_t temp_bytes,
+                    gstex_stream_t stream);
+
 /* ======================================================================================== *
  * (3) rasterise forward / (4) rasterise backward
  * ======================================================================================== */

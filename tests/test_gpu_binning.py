@@ -152,3 +152,48 @@ def test_backend_error_behaviour():
         _C.get_aabb_2d(s["means"].T.contiguous().T, s["scales"], 1.0, s["quats"], s["viewmat"], *s["intrins"])
     with pytest.raises(NotImplementedError):
         _C.texture_edit()
+
+
+# ---- fused tile binning (csrc/binning_tiles.cu) must reproduce the staged path bit for bit -------------------------
+@pytest.mark.parametrize("n,W,H,bw,spread", [
+    (0, 64, 64, 16, 16.0), (1, 64, 64, 16, 16.0), (300, 96, 160, 16, 16.0), (5000, 256, 192, 16, 16.0),
+    (800, 100, 60, 8, 16.0),
+    (6000, 32, 32, 16, 4.0),      # ~1.5-6 k entries per tile: the 64 KB shared-memory class
+    (40000, 32, 16, 16, 4.0),     # > 8192 entries per tile: the global-memory class
+    (200000, 640, 360, 16, 16.0),
+])
+def test_bin_tiles_matches_staged_path(n, W, H, bw, spread):
+    if n == 0:
+        z = torch.zeros((0, 2), device=DEV)
+        ids, bins, cnt, _ = U.bin_tiles(z, z, torch.zeros((0,), device=DEV), ((W + bw - 1) // bw, (H + bw - 1) // bw, 1), bw, 16)
+        assert int(cnt.item()) == 0 and int(bins.abs().sum().item()) == 0
+        return
+    s = random_small_scene(n, W, H, seed=n + 5, spread=spread, device=DEV)
+    if n >= 300:  # equal depths inside a tile: ties must come out in Gaussian order
+        s["means"][::7, 2] = s["means"][3, 2]
+    b = bin_cuda(s, bw)
+    m = b["num_intersects"]
+    ids, bins, cnt, isect = U.bin_tiles(b["centers"], b["extents"], b["depths"], b["tile_bounds"], bw, m + 13,
+                                        want_isect_ids=True)
+    torch.cuda.synchronize()
+    assert int(cnt.item()) == m
+    assert torch.equal(bins, b["tile_bins"])
+    assert torch.equal(ids[:m], b["gaussian_ids_sorted"])
+    assert torch.equal(isect[:m], b["isect_ids_sorted"])
+    print(f"  M = {m}, longest tile list = {int((bins[:, 1] - bins[:, 0]).max().item())}")
+
+
+def test_bin_tiles_capacity_overflow_is_clipped():
+    s = random_small_scene(3000, 128, 128, seed=4, device=DEV)
+    b = bin_cuda(s, 16)
+    m = b["num_intersects"]
+    cap = m // 2
+    ids, bins, cnt, _ = U.bin_tiles(b["centers"], b["extents"], b["depths"], b["tile_bounds"], 16, cap)
+    torch.cuda.synchronize()
+    assert int(cnt.item()) == m                     # the true count is reported (overflow is detectable) ...
+    assert int(bins.max().item()) <= cap            # ... and nothing points past the buffers
+    full = b["tile_bins"]
+    whole = (full[:, 1] <= cap) & (full[:, 1] > full[:, 0])   # tiles entirely inside the capacity are intact
+    assert torch.equal(bins[whole], full[whole])
+    last = int(full[whole][:, 1].max().item())
+    assert torch.equal(ids[:last], b["gaussian_ids_sorted"][:last])
