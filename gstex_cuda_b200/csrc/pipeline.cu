@@ -36,15 +36,16 @@ extern "C" int gstex_raster_forward(int img_height, int img_width, int block_wid
                                     float fx, float fy, float cx, float cy, const float *background, float *out_img,
                                     float *out_depth, float *out_reg, float *out_texture, float *out_normal,
                                     float *final_Ts, int32_t *final_idx, int32_t *depth_idx, float *out_reg_s,
+                                    uint32_t *masks, int64_t mask_entries, const int32_t *d_num_intersects,
                                     gstex_stream_t stream) {
     int rc = check_raster_args("raster_forward", img_height, img_width, block_width, 0, 0, channels, settings);
     if (rc != GSTEX_OK) return rc;
     const RasterCommon p = make_raster_common(img_height, img_width, block_width, channels, settings,
                                               gaussian_ids_sorted, tile_bins, (const float4 *)recs,
                                               (const float2 *)mean2d, (const float4 *)tex, tex, viewmat, c2w,
-                                              background, fx, fy, cx, cy);
+                                              background, fx, fy, cx, cy, masks);
     ForwardOut o{out_img, out_depth, out_reg, out_texture, out_normal, final_Ts, out_reg_s, final_idx, depth_idx};
-    return launch_raster_forward(p, o, as_stream(stream));
+    return launch_raster_forward(p, o, mask_entries, d_num_intersects, as_stream(stream));
 }
 
 extern "C" int gstex_raster_backward(int img_height, int img_width, int block_width, int channels, int settings,
@@ -54,13 +55,15 @@ extern "C" int gstex_raster_backward(int img_height, int img_width, int block_wi
                                      const float *final_Ts, const int32_t *final_idx, const int32_t *depth_idx,
                                      const float *final_s, const float *v_out_img, const float *v_out_depth,
                                      const float *v_out_reg, const float *v_out_alpha, const float *v_out_texture,
-                                     const float *v_out_normal, float *acc, float *vtex, gstex_stream_t stream) {
+                                     const float *v_out_normal, const uint32_t *masks, float *acc, float *vtex,
+                                     gstex_stream_t stream) {
     int rc = check_raster_args("raster_backward", img_height, img_width, block_width, 0, 0, channels, settings);
     if (rc != GSTEX_OK) return rc;
     const RasterCommon p = make_raster_common(img_height, img_width, block_width, channels, settings,
                                               gaussian_ids_sorted, tile_bins, (const float4 *)recs,
                                               (const float2 *)mean2d, (const float4 *)tex, tex, viewmat, c2w,
-                                              background, fx, fy, cx, cy);
+                                              background, fx, fy, cx, cy, const_cast<uint32_t *>(masks));
+    GSTEX_REQUIRE(masks != nullptr, GSTEX_E_INVALID, "raster_backward: masks (written by raster_forward) is NULL");
     BackwardIn in{final_Ts, final_s, final_idx, depth_idx, v_out_img, v_out_depth, v_out_reg, v_out_alpha, v_out_texture,
                   v_out_normal};
     BackwardOut o{(float4 *)acc, (float4 *)vtex, vtex};

@@ -253,7 +253,12 @@ struct RasterCommon {
     const float *tex;          // caller's texture (X x C), generic channel count
     const float *viewmat, *c2w, *background;
     float fx, fy, cx, cy;
+    // One 32-bit word per (sorted-list entry, warp of the tile's CTA): the lanes (pixels) that BLENDED the entry in the
+    // forward pass.  Written by the forward rasteriser, read by the backward one, which therefore differentiates
+    // exactly the pairs the forward pass composited (no re-evaluation of the skip / stop rules, no culling pass).
+    uint32_t *masks;
 };
+constexpr int MASK_WARPS = RASTER_MAX_THREADS / 32;  // mask words per list entry
 
 struct ForwardOut {
     float *out_img, *out_depth, *out_reg, *out_texture, *out_normal, *final_Ts, *out_reg_s;
@@ -273,15 +278,18 @@ struct BackwardOut {
 };
 
 struct FwdLayout {
-    size_t recs_off, mean2d_off, tex4_off, total;
+    size_t recs_off, mean2d_off, tex4_off, masks_off, total;
 };
 
 // host-side launchers shared between the reference-shaped entry points and the staged ones (pipeline.cu)
 RasterCommon make_raster_common(int img_height, int img_width, int block_width, int channels, int settings,
                                 const int32_t *ids, const int32_t *tile_bins, const float4 *recs, const float2 *mean2d,
                                 const float4 *tex4, const float *tex, const float *viewmat, const float *c2w,
-                                const float *background, float fx, float fy, float cx, float cy);
-int launch_raster_forward(const RasterCommon &p, const ForwardOut &o, cudaStream_t s);
+                                const float *background, float fx, float fy, float cx, float cy, uint32_t *masks);
+// zeroes the mask words of the first min(*d_count, mask_entries) list entries (d_count == NULL: all mask_entries),
+// then rasterises
+int launch_raster_forward(const RasterCommon &p, const ForwardOut &o, int64_t mask_entries, const int32_t *d_count,
+                          cudaStream_t s);
 int launch_raster_backward(const RasterCommon &p, const BackwardIn &in, const BackwardOut &o, cudaStream_t s);
 int launch_pack(int n, const float *means, const float *scales, float glob_scale, const float *quats,
                 const float *opacities, const float *colors, const float *uv0, const float *umap, const float *vmap,
@@ -294,7 +302,7 @@ int launch_epilogue(int n, const float *means, const float *scales, float glob_s
                     cudaStream_t s);
 int launch_pad_texture(int64_t num_texels, const float *tex, float4 *tex4, cudaStream_t s);
 int launch_unpad_texture_grad(int64_t num_texels, const float4 *g4, float *v_texture, int accumulate, cudaStream_t s);
-FwdLayout forward_layout(int n, int64_t num_texels, int channels);
+FwdLayout forward_layout(int n, int64_t num_texels, int channels, int64_t num_intersects);
 int check_raster_args(const char *who, int img_height, int img_width, int block_width, int n, int64_t num_texels,
                       int channels, int settings);
 

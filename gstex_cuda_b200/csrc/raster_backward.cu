@@ -18,252 +18,382 @@
 
 namespace gstex {
 
-// Sum the 32 per-lane slots over the warp.  Returns, in every lane, the totals of quad (lane >> 2).
-__device__ __forceinline__ float4 warp_reduce_slots(float (&a)[32], int lane) {
-    const unsigned full = 0xffffffffu;
-    {
-        const bool hi = (lane & 16) != 0;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const float send = hi ? a[i] : a[i + 16];
-            const float keep = hi ? a[i + 16] : a[i];
-            a[i] = keep + __shfl_xor_sync(full, send, 16);
-        }
-    }
-    {
-        const bool hi = (lane & 8) != 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float send = hi ? a[i] : a[i + 8];
-            const float keep = hi ? a[i + 8] : a[i];
-            a[i] = keep + __shfl_xor_sync(full, send, 8);
-        }
-    }
-    {
-        const bool hi = (lane & 4) != 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float send = hi ? a[i] : a[i + 4];
-            const float keep = hi ? a[i + 4] : a[i];
-            a[i] = keep + __shfl_xor_sync(full, send, 4);
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        a[i] += __shfl_xor_sync(full, a[i], 2);
-        a[i] += __shfl_xor_sync(full, a[i], 1);
-    }
-    return make_float4(a[0], a[1], a[2], a[3]);
-}
+// ------------------------------------------------------------------------------------------
+// Dense pair-queue backward.
+//
+// The forward pass recorded, per (list entry, warp), the mask of pixels that blended the entry.  On C4 a blended
+// (warp, Gaussian) pair has on average 11 of 32 pixels set, so a kernel that runs the ~400-instruction gradient
+// path "one Gaussian at a time, lane = pixel" wastes two thirds of its issue slots.  Instead each warp
+//   1. compacts the set bits of a run of entries (back to front) into a queue of (entry, pixel) PAIRS,
+//   2. D1, lane = pair : evaluates alpha and the texel fetch, and y = dL/d(vis-weighted value) of the pair
+//                        (colour, normal, texture and distortion terms),
+//   3. scan, lane = pixel: walks its own pairs in list order: T_k = T_{k+1}/(1-alpha_k),
+//                        v_alpha = T_k (y - R), R <- alpha y + (1-alpha) R   (reference texture.cu:579-670),
+//   4. D2, lane = pair : everything that needs v_alpha: texel-gradient reductions, gradients of the five
+//                        affine forms, the 28 moment values; rows go to shared memory and 2 x 14 lanes sum the
+//                        column pairs over the rows of each Gaussian, one RED.64 per column pair and Gaussian.
+// Per-pixel constants (upstream gradients, final distortion sums ...) stay in the registers of the pixel's lane
+// and reach the pair lanes by warp shuffles.  Per pixel the pairs are processed in exactly the reference's order.
+// ------------------------------------------------------------------------------------------
+constexpr int BWD_WARPS = RASTER_MAX_THREADS / 32;
+constexpr int BWD_QCAP = 128;          // pairs per chunk (4 dense iterations)
+constexpr int BWD_ECAP = 16;           // list entries (Gaussians) per chunk: their records are staged per warp
+constexpr int BWD_BATCH = 64;          // list entries whose mask words a warp fetches at a time
+
+template <bool BLUR>
+struct BwdWarpSmem {
+    static constexpr int PITCH = BLUR ? 32 : 28;  // floats per moment row (28 used; 30 with BLUR)
+    float4 rec[BWD_ECAP * 8];          // packed records of the chunk's entries (quad_slot swizzle)
+    float rows[32 * PITCH];            // moment rows of one dense iteration (D2)
+    float e_a[BWD_QCAP];               // alpha (D1) -> vis = alpha * T_k (scan)
+    float e_y[BWD_QCAP];               // y (D1) -> v_alpha (scan)
+    float e_gu[BWD_QCAP], e_gv[BWD_QCAP];  // d(texture term)/du, /dv per unit vis (D1)
+    int row_gid[32];                   // Gaussian id of each row
+    uint32_t sv_mask[BWD_BATCH];       // blend mask of each non-empty entry of the batch
+    int32_t sv_gid[BWD_BATCH];         // its Gaussian id
+    uint16_t q_ent[BWD_QCAP];          // pair -> (chunk-local entry | pixel lane << 8)
+    uint8_t sv_r[BWD_BATCH];           // its position inside the batch
+};
+
+struct PixelShare {  // per-pixel values a pair lane fetches from the pixel's lane
+    float vi0, vi1, vi2, vn0, vn1, vn2, vt0, vt1, vt2, Sf0, Sf1, Sf2, v_reg, v_dep;
+    int dfinal, pix;
+};
 
 template <bool C3, bool BLUR>
-__global__ void __launch_bounds__(RASTER_MAX_THREADS) raster_backward_kernel(const RasterCommon p, const BackwardIn in,
-                                                                            const BackwardOut o) {
-    __shared__ float4 stage[2][RASTER_BATCH * 8];
-    __shared__ uint8_t survivors[RASTER_MAX_THREADS / 32][RASTER_BATCH];
-    __shared__ int block_last;
+__global__ void __launch_bounds__(RASTER_MAX_THREADS, 3) raster_backward_kernel(const RasterCommon p, const BackwardIn in,
+                                                                               const BackwardOut o) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using WS = BwdWarpSmem<BLUR>;
+    constexpr int PITCH = WS::PITCH;
+    const unsigned full = 0xffffffffu;
+    const int tr = threadIdx.x, lane = tr & 31, warp = tr >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    WS &W = reinterpret_cast<WS *>(smem_raw)[warp];
 
-    const int tr = threadIdx.x, lane = tr & 31;
     const int tile = blockIdx.y * p.tiles_x + blockIdx.x;
     int lx, ly;
     tile_pixel(p.bw, tr, lx, ly);
     const int col = blockIdx.x * p.bw + lx, row = blockIdx.y * p.bw + ly;
     const bool inside = (tr < p.bw * p.bw) && col < p.img_w && row < p.img_h;
-    const int pix = inside ? row * p.img_w + col : 0;
     const PixelConsts pc = make_pixel(col, row, p.c2w, p.viewmat, p.fx, p.fy, p.cx, p.cy);
-    const WarpRect wr = make_warp_rect(col, row, inside);
-    uint8_t *__restrict__ my_list = survivors[tr >> 5];
     const bool use_ndc = (p.settings & GSTEX_SET_NDC) != 0;
     const bool bilinear = !(p.settings & GSTEX_SET_NEAREST);
     const bool prop_uv = (p.settings & GSTEX_SET_PROPAGATE_UV) != 0;
     const int C = C3 ? 3 : p.channels;
+    constexpr int NCOL2 = BLUR ? 15 : 14;  // float2 column pairs of a moment row
 
+    PixelShare me;
+    me.pix = inside ? row * p.img_w + col : 0;
     const int2 range = p.bins[tile];
-    const int bfinal = inside ? in.final_idx[pix] : -1;
-    if (tr == 0) block_last = -1;
-    __syncthreads();
-    if (bfinal >= 0) atomicMax(&block_last, bfinal);
-    __syncthreads();
-    const int hi = min(range.y, block_last + 1);
-    const int total = hi - range.x;
-    if (total <= 0) return;
-    const int nbatch = (total + RASTER_BATCH - 1) / RASTER_BATCH;
-    int warp_last = bfinal;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) warp_last = max(warp_last, __shfl_xor_sync(0xffffffffu, warp_last, off));
+    const int bfinal = inside ? in.final_idx[me.pix] : -1;
+    // every warp walks the tile's list on its own, from the last entry one of ITS pixels blended back to the front:
+    // no block-wide staging, no barriers
+    const int warp_last = __reduce_max_sync(full, bfinal);
+    const int hi = min(range.y, warp_last + 1);
+    if (hi <= range.x) return;
+    const int nbatch = (hi - range.x + BWD_BATCH - 1) / BWD_BATCH;
 
-    float T = in.final_Ts[pix];
-    const float Sf0 = in.final_s[3 * pix], Sf1 = in.final_s[3 * pix + 1], Sf2 = in.final_s[3 * pix + 2];
-    const int dfinal = in.depth_idx[pix];
-    const float vi0 = in.v_img[3 * pix], vi1 = in.v_img[3 * pix + 1], vi2 = in.v_img[3 * pix + 2];
-    const float vn0 = in.v_normal[3 * pix], vn1 = in.v_normal[3 * pix + 1], vn2 = in.v_normal[3 * pix + 2];
-    const float v_dep = in.v_depth[pix], v_reg = in.v_reg[pix];
-    float vt0 = 0.f, vt1 = 0.f, vt2 = 0.f;
+    float T = in.final_Ts[me.pix];
+    me.Sf0 = in.final_s[3 * me.pix]; me.Sf1 = in.final_s[3 * me.pix + 1]; me.Sf2 = in.final_s[3 * me.pix + 2];
+    me.dfinal = in.depth_idx[me.pix];
+    me.vi0 = in.v_img[3 * me.pix]; me.vi1 = in.v_img[3 * me.pix + 1]; me.vi2 = in.v_img[3 * me.pix + 2];
+    me.vn0 = in.v_normal[3 * me.pix]; me.vn1 = in.v_normal[3 * me.pix + 1]; me.vn2 = in.v_normal[3 * me.pix + 2];
+    me.v_dep = in.v_depth[me.pix]; me.v_reg = in.v_reg[me.pix];
+    me.vt0 = me.vt1 = me.vt2 = 0.f;
     if (C3) {
-        vt0 = in.v_tex[3 * pix];
-        vt1 = in.v_tex[3 * pix + 1];
-        vt2 = in.v_tex[3 * pix + 2];
+        me.vt0 = in.v_tex[3 * me.pix]; me.vt1 = in.v_tex[3 * me.pix + 1]; me.vt2 = in.v_tex[3 * me.pix + 2];
     }
-    const float *__restrict__ vtp = in.v_tex + (size_t)C * pix;
-    float v_T_run = p.background[0] * vi0 + p.background[1] * vi1 + p.background[2] * vi2 - in.v_alpha[pix];
-
-    // batch j covers [first_j, first_j + cnt_j) counted from the back of [range.x, hi)
-    auto batch_first = [&](int j) { return max(range.x, hi - (j + 1) * RASTER_BATCH); };
-    auto batch_count = [&](int j) { return (hi - j * RASTER_BATCH) - batch_first(j); };
-
-    stage_records(stage[0], p.recs, p.ids, batch_first(0), batch_count(0), tr, p.nthreads);
+    float v_T_run = p.background[0] * me.vi0 + p.background[1] * me.vi1 + p.background[2] * me.vi2 - in.v_alpha[me.pix];
 
     for (int b = 0; b < nbatch; ++b) {
-        const int first = batch_first(b), cnt = batch_count(b);
-        if (b + 1 < nbatch) {
-            stage_records(stage[(b + 1) & 1], p.recs, p.ids, batch_first(b + 1), batch_count(b + 1), tr, p.nthreads);
-            __pipeline_wait_prior(1);
-        } else {
-            __pipeline_wait_prior(0);
-        }
-        __syncthreads();
-        const float4 *__restrict__ S = stage[b & 1];
-        // warp-level culling (raster.cuh): same survivor set as the forward pass, walked back to front
-        const int nsurv = build_survivors<BLUR>(S, 0, min(cnt, warp_last - first + 1), wr, p.mean2d, my_list, lane);
-        for (int si = nsurv - 1; si >= 0; --si) {
-            const int i = my_list[si];
-            const int idx = first + i;
-            const int sw = i & 7;
-            const float4 *__restrict__ R = S + (i << 3);
-            const float4 q0 = R[sw], q1 = R[1 ^ sw], q2 = R[2 ^ sw], q3 = R[3 ^ sw];
-            bool valid = inside && idx <= bfinal;
-            PairEval pe;
-            if (valid) {
-                eval_pair<BLUR>(q0, q1, q2, q3, pc, p.mean2d, pe);
-                valid = !pair_skipped(pe);
+        // batch b covers [first, first + cnt) counted from the back of [range.x, hi)
+        const int first = max(range.x, hi - (b + 1) * BWD_BATCH), cnt = (hi - b * BWD_BATCH) - first;
+        // this warp's non-empty mask words of the batch (and the Gaussian ids), compacted in list order
+        int nsurv = 0;
+        for (int k = 0; k < cnt; k += 32) {
+            const int r = k + lane;
+            const uint32_t mw = r < cnt ? __ldg(p.masks + (size_t)(first + r) * MASK_WARPS + warp) : 0u;
+            const int32_t g = r < cnt ? __ldg(p.ids + first + r) : 0;
+            const unsigned m = __ballot_sync(full, mw != 0u);
+            if (mw != 0u) {
+                const int pos = nsurv + __popc(m & lt);
+                W.sv_r[pos] = (uint8_t)r;
+                W.sv_mask[pos] = mw;
+                W.sv_gid[pos] = g;
             }
-            if (!__any_sync(0xffffffffu, valid)) continue;
+            nsurv += __popc(m);
+        }
+        __syncwarp();
 
-            float a[32];
-#pragma unroll
-            for (int k = 0; k < 32; ++k) a[k] = 0.f;
-            if (valid) {
-                const float4 q4 = R[4 ^ sw], q5 = R[5 ^ sw], q6 = R[6 ^ sw], q7 = R[7 ^ sw];
-                const float alpha = pe.alpha;
-                T *= 1.f / (1.f - alpha);  // reference texture.cu:579-580
-                const float vis = alpha * T;
-                a[A_CR] = vis * vi0;
-                a[A_CG] = vis * vi1;
-                a[A_CB] = vis * vi2;
-                a[A_NX] = vis * vn0;
-                a[A_NY] = vis * vn1;
-                a[A_NZ] = vis * vn2;
-                float v_vis = q6.x * vi0 + q6.y * vi1 + q6.z * vi2 + q7.x * vn0 + q7.y * vn1 + q7.z * vn2;
+        int si = nsurv - 1;
+        while (si >= 0) {
+            // ---------------- build one chunk of pairs: entries si0, si0-1, ... while they fit ----------------
+            const int si0 = si;
+            int np = 0;
+            while (si >= 0 && si0 - si < BWD_ECAP) {
+                const bool mine = ((W.sv_mask[si] >> lane) & 1u) && (first + (int)W.sv_r[si]) <= bfinal;
+                const unsigned m = __ballot_sync(full, mine);
+                const int c = __popc(m);
+                if (np + c > BWD_QCAP) break;
+                if (mine) W.q_ent[np + __popc(m & lt)] = (uint16_t)((si0 - si) | (lane << 8));
+                if (lane == 0) W.sv_mask[si] = m;  // from here on: the pixels that really take part
+                np += c;
+                --si;
+            }
+            // stage the records of the chunk's entries: 8 lanes fetch one 128-byte record
+            {
+                const int ne = si0 - si;
+                for (int t = lane; t < ne * 8; t += 32) {
+                    const int j = t >> 3, q = t & 7;
+                    __pipeline_memcpy_async(W.rec + quad_slot(j, q), p.recs + (size_t)W.sv_gid[si0 - j] * 8 + q, 16);
+                }
+                __pipeline_commit();
+                __pipeline_wait_prior(0);
+            }
+            __syncwarp();
+            const int niter = (np + 31) >> 5;
 
-                // texture fetch VJP (reference texture.cu:594-642, texture_helpers.cuh:252-300)
-                const float nu = fmaf(q4.x, pe.ex, fmaf(q4.y, pe.ey, q4.z));
-                const float nv = fmaf(q5.x, pe.ex, fmaf(q5.y, pe.ey, q5.z));
-                const float du = nu * pe.rD, dv = nv * pe.rD;
-                const float u = clamp01(fmaf(nu, pe.rD, q4.w)), v = clamp01(fmaf(nv, pe.rD, q5.w));
-                TexFetch tf;
-                texel_setup(__float_as_int(q3.z), __float_as_int(q3.w), __float_as_int(q6.w), u, v, bilinear, tf);
-                float v_u = 0.f, v_v = 0.f;
-                if (C3) {
-                    const float4 t0 = __ldg(p.tex4 + tf.idx[0]), t1 = __ldg(p.tex4 + tf.idx[1]);
-                    const float4 t2 = __ldg(p.tex4 + tf.idx[2]), t3 = __ldg(p.tex4 + tf.idx[3]);
-                    const float vv0 = vis * vt0, vv1 = vis * vt1, vv2 = vis * vt2;
-                    if (tf.w[0] != 0.f) atomicAdd(o.vtex4 + tf.idx[0], make_float4(tf.w[0] * vv0, tf.w[0] * vv1, tf.w[0] * vv2, 0.f));
-                    if (tf.w[1] != 0.f) atomicAdd(o.vtex4 + tf.idx[1], make_float4(tf.w[1] * vv0, tf.w[1] * vv1, tf.w[1] * vv2, 0.f));
-                    if (tf.w[2] != 0.f) atomicAdd(o.vtex4 + tf.idx[2], make_float4(tf.w[2] * vv0, tf.w[2] * vv1, tf.w[2] * vv2, 0.f));
-                    if (tf.w[3] != 0.f) atomicAdd(o.vtex4 + tf.idx[3], make_float4(tf.w[3] * vv0, tf.w[3] * vv1, tf.w[3] * vv2, 0.f));
-                    const float val0 = tf.w[0] * t0.x + tf.w[1] * t1.x + tf.w[2] * t2.x + tf.w[3] * t3.x;
-                    const float val1 = tf.w[0] * t0.y + tf.w[1] * t1.y + tf.w[2] * t2.y + tf.w[3] * t3.y;
-                    const float val2 = tf.w[0] * t0.z + tf.w[1] * t1.z + tf.w[2] * t2.z + tf.w[3] * t3.z;
-                    v_vis += val0 * vt0 + val1 * vt1 + val2 * vt2;
-                    if (bilinear && prop_uv) {
-                        const float ofu = 1.f - tf.fu, ofv = 1.f - tf.fv;
-                        const float gu0 = -ofv * t0.x - tf.fv * t1.x + ofv * t2.x + tf.fv * t3.x;
-                        const float gu1 = -ofv * t0.y - tf.fv * t1.y + ofv * t2.y + tf.fv * t3.y;
-                        const float gu2 = -ofv * t0.z - tf.fv * t1.z + ofv * t2.z + tf.fv * t3.z;
-                        const float gv0 = -ofu * t0.x + ofu * t1.x - tf.fu * t2.x + tf.fu * t3.x;
-                        const float gv1 = -ofu * t0.y + ofu * t1.y - tf.fu * t2.y + tf.fu * t3.y;
-                        const float gv2 = -ofu * t0.z + ofu * t1.z - tf.fu * t2.z + tf.fu * t3.z;
-                        v_u = (float)tf.h * (vv0 * gu0 + vv1 * gu1 + vv2 * gu2);
-                        v_v = (float)tf.wd * (vv0 * gv0 + vv1 * gv1 + vv2 * gv2);
-                    }
-                } else {
-                    const float *__restrict__ tx = p.tex;
-                    for (int c = 0; c < C; ++c) {
-                        const float c00 = __ldg(tx + (size_t)tf.idx[0] * C + c), c01 = __ldg(tx + (size_t)tf.idx[1] * C + c);
-                        const float c10 = __ldg(tx + (size_t)tf.idx[2] * C + c), c11 = __ldg(tx + (size_t)tf.idx[3] * C + c);
-                        const float vtc = vtp[c];
-                        const float vv = vis * vtc;
-                        if (tf.w[0] != 0.f) atomicAdd(o.vtex + (size_t)tf.idx[0] * C + c, tf.w[0] * vv);
-                        if (tf.w[1] != 0.f) atomicAdd(o.vtex + (size_t)tf.idx[1] * C + c, tf.w[1] * vv);
-                        if (tf.w[2] != 0.f) atomicAdd(o.vtex + (size_t)tf.idx[2] * C + c, tf.w[2] * vv);
-                        if (tf.w[3] != 0.f) atomicAdd(o.vtex + (size_t)tf.idx[3] * C + c, tf.w[3] * vv);
-                        v_vis += (tf.w[0] * c00 + tf.w[1] * c01 + tf.w[2] * c10 + tf.w[3] * c11) * vtc;
-                        if (bilinear && prop_uv) {
-                            v_u += (float)tf.h * (vv * (-(1.f - tf.fv) * c00 - tf.fv * c01 + (1.f - tf.fv) * c10 + tf.fv * c11));
-                            v_v += (float)tf.wd * (vv * (-(1.f - tf.fu) * c00 + (1.f - tf.fu) * c01 - tf.fu * c10 + tf.fu * c11));
+            // ---------------- D1: lane = pair ----------------
+            for (int it = 0; it < niter; ++it) {
+                const int e = it * 32 + lane;
+                const bool act = e < np;
+                const int ent = act ? (int)W.q_ent[e] : (lane << 8);
+                const int pl = ent >> 8;
+                PixelConsts qc;
+                qc.px = __shfl_sync(full, pc.px, pl); qc.py = __shfl_sync(full, pc.py, pl);
+                qc.rn = __shfl_sync(full, pc.rn, pl); qc.vdep = __shfl_sync(full, pc.vdep, pl);
+                qc.eps = __shfl_sync(full, pc.eps, pl);
+                const float vi0 = __shfl_sync(full, me.vi0, pl), vi1 = __shfl_sync(full, me.vi1, pl), vi2 = __shfl_sync(full, me.vi2, pl);
+                const float vn0 = __shfl_sync(full, me.vn0, pl), vn1 = __shfl_sync(full, me.vn1, pl), vn2 = __shfl_sync(full, me.vn2, pl);
+                const float vt0 = __shfl_sync(full, me.vt0, pl), vt1 = __shfl_sync(full, me.vt1, pl), vt2 = __shfl_sync(full, me.vt2, pl);
+                const float Sf0 = __shfl_sync(full, me.Sf0, pl), Sf1 = __shfl_sync(full, me.Sf1, pl), Sf2 = __shfl_sync(full, me.Sf2, pl);
+                const float v_reg = __shfl_sync(full, me.v_reg, pl);
+                const int ppix = C3 ? 0 : __shfl_sync(full, me.pix, pl);
+                if (act) {
+                    const int j = ent & 0xff;
+                    const int sw = j & 7;
+                    const float4 *__restrict__ R = W.rec + (j << 3);
+                    const float4 q0 = R[sw], q1 = R[1 ^ sw], q2 = R[2 ^ sw], q3 = R[3 ^ sw];
+                    const float4 q4 = R[4 ^ sw], q5 = R[5 ^ sw], q6 = R[6 ^ sw], q7 = R[7 ^ sw];
+                    PairEval pe;
+                    eval_pair<BLUR>(q0, q1, q2, q3, qc, p.mean2d, pe);
+                    float v_vis = q6.x * vi0 + q6.y * vi1 + q6.z * vi2 + q7.x * vn0 + q7.y * vn1 + q7.z * vn2;
+                    // texture fetch (reference texture.cu:594-642, texture_helpers.cuh:252-300)
+                    const float nu = fmaf(q4.x, pe.ex, fmaf(q4.y, pe.ey, q4.z));
+                    const float nv = fmaf(q5.x, pe.ex, fmaf(q5.y, pe.ey, q5.z));
+                    const float u = clamp01(fmaf(nu, pe.rD, q4.w)), v = clamp01(fmaf(nv, pe.rD, q5.w));
+                    TexFetch tf;
+                    texel_setup(__float_as_int(q3.z), __float_as_int(q3.w), __float_as_int(q6.w), u, v, bilinear, tf);
+                    float gu = 0.f, gv = 0.f;
+                    const bool want_uv = bilinear && prop_uv;
+                    if (C3) {
+                        const float4 t0 = __ldg(p.tex4 + tf.idx[0]), t1 = __ldg(p.tex4 + tf.idx[1]);
+                        const float4 t2 = __ldg(p.tex4 + tf.idx[2]), t3 = __ldg(p.tex4 + tf.idx[3]);
+                        const float val0 = tf.w[0] * t0.x + tf.w[1] * t1.x + tf.w[2] * t2.x + tf.w[3] * t3.x;
+                        const float val1 = tf.w[0] * t0.y + tf.w[1] * t1.y + tf.w[2] * t2.y + tf.w[3] * t3.y;
+                        const float val2 = tf.w[0] * t0.z + tf.w[1] * t1.z + tf.w[2] * t2.z + tf.w[3] * t3.z;
+                        v_vis += val0 * vt0 + val1 * vt1 + val2 * vt2;
+                        if (want_uv) {
+                            const float ofu = 1.f - tf.fu, ofv = 1.f - tf.fv;
+                            const float gu0 = -ofv * t0.x - tf.fv * t1.x + ofv * t2.x + tf.fv * t3.x;
+                            const float gu1 = -ofv * t0.y - tf.fv * t1.y + ofv * t2.y + tf.fv * t3.y;
+                            const float gu2 = -ofv * t0.z - tf.fv * t1.z + ofv * t2.z + tf.fv * t3.z;
+                            const float gv0 = -ofu * t0.x + ofu * t1.x - tf.fu * t2.x + tf.fu * t3.x;
+                            const float gv1 = -ofu * t0.y + ofu * t1.y - tf.fu * t2.y + tf.fu * t3.y;
+                            const float gv2 = -ofu * t0.z + ofu * t1.z - tf.fu * t2.z + tf.fu * t3.z;
+                            gu = (float)tf.h * (vt0 * gu0 + vt1 * gu1 + vt2 * gu2);
+                            gv = (float)tf.wd * (vt0 * gv0 + vt1 * gv1 + vt2 * gv2);
+                        }
+                    } else {
+                        const float *__restrict__ tx = p.tex;
+                        const float *__restrict__ vtp = in.v_tex + (size_t)C * ppix;
+                        for (int c = 0; c < C; ++c) {
+                            const float c00 = __ldg(tx + (size_t)tf.idx[0] * C + c), c01 = __ldg(tx + (size_t)tf.idx[1] * C + c);
+                            const float c10 = __ldg(tx + (size_t)tf.idx[2] * C + c), c11 = __ldg(tx + (size_t)tf.idx[3] * C + c);
+                            const float vtc = vtp[c];
+                            v_vis += (tf.w[0] * c00 + tf.w[1] * c01 + tf.w[2] * c10 + tf.w[3] * c11) * vtc;
+                            if (want_uv) {
+                                gu += (float)tf.h * (vtc * (-(1.f - tf.fv) * c00 - tf.fv * c01 + (1.f - tf.fv) * c10 + tf.fv * c11));
+                                gv += (float)tf.wd * (vtc * (-(1.f - tf.fu) * c00 + (1.f - tf.fu) * c01 - tf.fu * c10 + tf.fu * c11));
+                            }
                         }
                     }
-                }
-
-                // alpha / transmittance recurrences and distortion (reference texture.cu:650-670)
-                float v_alpha = T * v_vis - T * v_T_run;
-                float v_T_cur = alpha * v_vis + (1.f - alpha) * v_T_run;
-                const float t_view = pe.t * pc.vdep;
-                const float t_ndc = (T_FAR * t_view - T_FAR * T_NEAR) / ((T_FAR - T_NEAR) * t_view);
-                const float tv = use_ndc ? t_ndc : pe.t;
-                const float v_tv = 2.f * (vis * tv * Sf0 - vis * Sf1) * v_reg;  // FINAL sums, helpers.cuh:266-269
-                const float v_w = (tv * tv * Sf0 - 2.f * tv * Sf1 + Sf2) * v_reg;
-                v_alpha += v_w * T;
-                v_T_cur += v_w * alpha;
-                v_T_run = v_T_cur;
-                float v_t = use_ndc ? 0.f : v_tv;
-                float v_tview = (idx == dfinal && dfinal != -1) ? v_dep : 0.f;  // texture.cu:678-680
-                if (use_ndc) v_tview += (T_FAR * T_NEAR) / ((T_FAR - T_NEAR) * t_view * t_view) * v_tv;
-                v_t += pc.vdep * v_tview;
-                const float v_s = v_t * pc.rn;
-
-                // alpha = min(.99, opac * f): the cap is not masked (reference texture.cu:672, :707)
-                a[A_OPAC] = pe.f * v_alpha;
-                const float v_q = pe.blur ? 0.f : -LN2_F * q0.w * pe.e * v_alpha;
-                const float v_l1 = 2.f * pe.l1 * v_q, v_l2 = 2.f * pe.l2 * v_q;
-                const float gN1 = v_l1 * pe.rD, gN2 = v_l2 * pe.rD, gNu = v_u * pe.rD, gNv = v_v * pe.rD;
-                const float gD = -(v_l1 * pe.l1 + v_l2 * pe.l2 + v_s * pe.s + v_u * du + v_v * dv) * pe.rD;
-                a[A_G1X] = gN1 * pe.ex; a[A_G1Y] = gN1 * pe.ey; a[A_G1C] = gN1;
-                a[A_C0] = v_s * pe.rD;
-                a[A_G2X] = gN2 * pe.ex; a[A_G2Y] = gN2 * pe.ey; a[A_G2C] = gN2;
-                a[A_G3X] = gD * pe.ex; a[A_G3Y] = gD * pe.ey; a[A_G3C] = gD;
-                a[A_GUX] = gNu * pe.ex; a[A_GUY] = gNu * pe.ey; a[A_GUC] = gNu;
-                a[A_U0] = v_u;
-                a[A_GVX] = gNv * pe.ex; a[A_GVY] = gNv * pe.ey; a[A_GVC] = gNv;
-                a[A_V0] = v_v;
-                if (BLUR) {
-                    if (pe.blur) {  // reference texture.cu:683-692
-                        const float v_sb = -q0.w * pe.f * v_alpha;
-                        a[A_MX] = 2.0f * v_sb * pe.bx;
-                        a[A_MY] = 2.0f * v_sb * pe.by;
-                    }
+                    // distortion: d(reg)/d(weight) with the FINAL sums (helpers.cuh:266-269)
+                    const float t_view = pe.t * qc.vdep;
+                    const float tv = use_ndc ? (T_FAR * t_view - T_FAR * T_NEAR) / ((T_FAR - T_NEAR) * t_view) : pe.t;
+                    const float v_w = (tv * tv * Sf0 - 2.f * tv * Sf1 + Sf2) * v_reg;
+                    W.e_a[e] = pe.alpha;
+                    W.e_y[e] = v_vis + v_w;
+                    W.e_gu[e] = gu;
+                    W.e_gv[e] = gv;
                 }
             }
-            const float4 tot = warp_reduce_slots(a, lane);
-            if ((lane & 3) == 0 && (BLUR || lane < 28)) {
-                const int g = __float_as_int(q2.w);
-                atomicAdd(o.acc + (size_t)g * 8 + (lane >> 2), tot);
+            __syncwarp();
+
+            // ---------------- scan: lane = pixel, its pairs in list order (back to front) ----------------
+            {
+                int off = 0;
+                for (int s = si0; s > si; --s) {
+                    const unsigned m = W.sv_mask[s];
+                    if ((m >> lane) & 1u) {
+                        const int e = off + __popc(m & lt);
+                        const float alpha = W.e_a[e], y = W.e_y[e];
+                        T *= 1.f / (1.f - alpha);  // transmittance in front of the entry (reference texture.cu:579-580)
+                        W.e_a[e] = alpha * T;
+                        W.e_y[e] = T * (y - v_T_run);                       // v_alpha (texture.cu:650, :667)
+                        v_T_run = alpha * y + (1.f - alpha) * v_T_run;      // texture.cu:651, :668-670
+                    }
+                    off += __popc(m);
+                }
+            }
+            __syncwarp();
+
+            // ---------------- D2: lane = pair ----------------
+            for (int it = 0; it < niter; ++it) {
+                const int e = it * 32 + lane;
+                const bool act = e < np;
+                const int ent = act ? (int)W.q_ent[e] : (lane << 8);
+                const int pl = ent >> 8;
+                PixelConsts qc;
+                qc.px = __shfl_sync(full, pc.px, pl); qc.py = __shfl_sync(full, pc.py, pl);
+                qc.rn = __shfl_sync(full, pc.rn, pl); qc.vdep = __shfl_sync(full, pc.vdep, pl);
+                qc.eps = __shfl_sync(full, pc.eps, pl);
+                const float vi0 = __shfl_sync(full, me.vi0, pl), vi1 = __shfl_sync(full, me.vi1, pl), vi2 = __shfl_sync(full, me.vi2, pl);
+                const float vn0 = __shfl_sync(full, me.vn0, pl), vn1 = __shfl_sync(full, me.vn1, pl), vn2 = __shfl_sync(full, me.vn2, pl);
+                const float vt0 = __shfl_sync(full, me.vt0, pl), vt1 = __shfl_sync(full, me.vt1, pl), vt2 = __shfl_sync(full, me.vt2, pl);
+                const float Sf0 = __shfl_sync(full, me.Sf0, pl), Sf1 = __shfl_sync(full, me.Sf1, pl);
+                const float v_reg = __shfl_sync(full, me.v_reg, pl), v_dep = __shfl_sync(full, me.v_dep, pl);
+                const int dfinal = __shfl_sync(full, me.dfinal, pl);
+                const int ppix = C3 ? 0 : __shfl_sync(full, me.pix, pl);
+                const int jloc = act ? (ent & 0xff) : -1 - lane;
+                int gid = 0;
+                if (act) {
+                    const int sw = jloc & 7;
+                    const float4 *__restrict__ R = W.rec + (jloc << 3);
+                    const float4 q0 = R[sw], q1 = R[1 ^ sw], q2 = R[2 ^ sw], q3 = R[3 ^ sw];
+                    const float4 q4 = R[4 ^ sw], q5 = R[5 ^ sw], q6 = R[6 ^ sw];
+                    gid = __float_as_int(q2.w);
+                    PairEval pe;
+                    eval_pair<BLUR>(q0, q1, q2, q3, qc, p.mean2d, pe);
+                    const float vis = W.e_a[e], v_alpha = W.e_y[e];
+                    const float v_u = vis * W.e_gu[e], v_v = vis * W.e_gv[e];
+                    const float nu = fmaf(q4.x, pe.ex, fmaf(q4.y, pe.ey, q4.z));
+                    const float nv = fmaf(q5.x, pe.ex, fmaf(q5.y, pe.ey, q5.z));
+                    const float du = nu * pe.rD, dv = nv * pe.rD;
+                    // texel gradients: one vector reduction per bilinear corner (texture_helpers.cuh:257-260)
+                    {
+                        const float u = clamp01(fmaf(nu, pe.rD, q4.w)), v = clamp01(fmaf(nv, pe.rD, q5.w));
+                        TexFetch tf;
+                        texel_setup(__float_as_int(q3.z), __float_as_int(q3.w), __float_as_int(q6.w), u, v, bilinear, tf);
+                        if (C3) {
+                            const float vv0 = vis * vt0, vv1 = vis * vt1, vv2 = vis * vt2;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                if (tf.w[k] != 0.f)
+                                    atomicAdd(o.vtex4 + tf.idx[k], make_float4(tf.w[k] * vv0, tf.w[k] * vv1, tf.w[k] * vv2, 0.f));
+                        } else {
+                            const float *__restrict__ vtp = in.v_tex + (size_t)C * ppix;
+                            for (int c = 0; c < C; ++c) {
+                                const float vv = vis * vtp[c];
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    if (tf.w[k] != 0.f) atomicAdd(o.vtex + (size_t)tf.idx[k] * C + c, tf.w[k] * vv);
+                            }
+                        }
+                    }
+                    // depth / distortion terms through t (reference texture.cu:655-682)
+                    const float t_view = pe.t * qc.vdep;
+                    const float tv = use_ndc ? (T_FAR * t_view - T_FAR * T_NEAR) / ((T_FAR - T_NEAR) * t_view) : pe.t;
+                    const float v_tv = 2.f * (vis * tv * Sf0 - vis * Sf1) * v_reg;
+                    float v_t = use_ndc ? 0.f : v_tv;
+                    const int idx = first + (int)W.sv_r[si0 - jloc];
+                    float v_tview = (idx == dfinal && dfinal != -1) ? v_dep : 0.f;  // texture.cu:678-680
+                    if (use_ndc) v_tview += (T_FAR * T_NEAR) / ((T_FAR - T_NEAR) * t_view * t_view) * v_tv;
+                    v_t += qc.vdep * v_tview;
+                    const float v_s = v_t * qc.rn;
+                    // alpha = min(.99, opac * f): the cap is not masked (reference texture.cu:672, :707)
+                    const float v_q = pe.blur ? 0.f : -LN2_F * q0.w * pe.e * v_alpha;
+                    const float v_l1 = 2.f * pe.l1 * v_q, v_l2 = 2.f * pe.l2 * v_q;
+                    const float gN1 = v_l1 * pe.rD, gN2 = v_l2 * pe.rD, gNu = v_u * pe.rD, gNv = v_v * pe.rD;
+                    const float gD = -(v_l1 * pe.l1 + v_l2 * pe.l2 + v_s * pe.s + v_u * du + v_v * dv) * pe.rD;
+                    float4 *__restrict__ rowp = reinterpret_cast<float4 *>(W.rows + lane * PITCH);  // AccSlot order
+                    rowp[0] = make_float4(gN1 * pe.ex, gN1 * pe.ey, gN1, v_s * pe.rD);
+                    rowp[1] = make_float4(gN2 * pe.ex, gN2 * pe.ey, gN2, pe.f * v_alpha);
+                    rowp[2] = make_float4(gD * pe.ex, gD * pe.ey, gD, 0.f);
+                    rowp[3] = make_float4(gNu * pe.ex, gNu * pe.ey, gNu, v_u);
+                    rowp[4] = make_float4(gNv * pe.ex, gNv * pe.ey, gNv, v_v);
+                    rowp[5] = make_float4(vis * vi0, vis * vi1, vis * vi2, 0.f);
+                    rowp[6] = make_float4(vis * vn0, vis * vn1, vis * vn2, 0.f);
+                    if (BLUR) {
+                        float mx = 0.f, my = 0.f;
+                        if (pe.blur) {  // reference texture.cu:683-692
+                            const float v_sb = -q0.w * pe.f * v_alpha;
+                            mx = 2.0f * v_sb * pe.bx;
+                            my = 2.0f * v_sb * pe.by;
+                        }
+                        rowp[7] = make_float4(mx, my, 0.f, 0.f);
+                    }
+                    W.row_gid[lane] = gid;
+                }
+                // rows of one Gaussian are contiguous: segment starts where the chunk-local entry changes
+                const int jprev = __shfl_up_sync(full, jloc, 1);
+                const unsigned bnd = __ballot_sync(full, lane == 0 || jloc != jprev);
+                __syncwarp();
+                const int nact = min(32, np - it * 32);
+                if (lane < 2 * NCOL2) {  // 2 x NCOL2 lanes: column pair (lane % NCOL2), rows [16 half, 16 half + 16)
+                    const int half = lane >= NCOL2 ? 1 : 0, cp = lane - half * NCOL2;
+                    const int r0 = half << 4;
+                    const float *__restrict__ colp = W.rows + 2 * cp;
+                    float2 acc2 = make_float2(0.f, 0.f);
+                    for (int t = 0; t < 16; ++t) {
+                        const int r = r0 + t;
+                        if (r < nact) {
+                            if (t > 0 && ((bnd >> r) & 1u)) {
+                                atomicAdd(reinterpret_cast<float2 *>(o.acc) + (size_t)W.row_gid[r - 1] * 16 + cp, acc2);
+                                acc2 = make_float2(0.f, 0.f);
+                            }
+                            const float2 v2 = *reinterpret_cast<const float2 *>(colp + r * PITCH);
+                            acc2.x += v2.x;
+                            acc2.y += v2.y;
+                        }
+                    }
+                    const int rl = min(nact, r0 + 16) - 1;
+                    if (rl >= r0) atomicAdd(reinterpret_cast<float2 *>(o.acc) + (size_t)W.row_gid[rl] * 16 + cp, acc2);
+                }
+                __syncwarp();
             }
         }
-        __syncthreads();
     }
+}
+
+static int set_bwd_smem(const void *fn, size_t BWD_SMEM_BYTES) {
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (e != cudaSuccess) {
+        set_error("cudaFuncSetAttribute(raster_backward_kernel, %zu bytes) failed: %s", BWD_SMEM_BYTES, cudaGetErrorString(e));
+        return GSTEX_E_CUDA;
+    }
+    return GSTEX_OK;
+}
+
+template <bool C3, bool BLUR>
+static int launch_bwd_variant(const dim3 grid, const RasterCommon &p, const BackwardIn &in, const BackwardOut &o,
+                              cudaStream_t s) {
+    const size_t smem = sizeof(BwdWarpSmem<BLUR>) * BWD_WARPS;
+    int rc = set_bwd_smem((const void *)raster_backward_kernel<C3, BLUR>, smem);
+    if (rc != GSTEX_OK) return rc;
+    raster_backward_kernel<C3, BLUR><<<grid, p.nthreads, smem, s>>>(p, in, o);
+    return GSTEX_OK;
 }
 
 int launch_raster_backward(const RasterCommon &p, const BackwardIn &in, const BackwardOut &o, cudaStream_t s) {
     const dim3 grid(p.tiles_x, ceil_div(p.img_h, p.bw));
     const bool blur = (p.settings & GSTEX_SET_BLUR) != 0;
-    if (p.channels == 3) {
-        if (blur) raster_backward_kernel<true, true><<<grid, p.nthreads, 0, s>>>(p, in, o);
-        else raster_backward_kernel<true, false><<<grid, p.nthreads, 0, s>>>(p, in, o);
-    } else {
-        if (blur) raster_backward_kernel<false, true><<<grid, p.nthreads, 0, s>>>(p, in, o);
-        else raster_backward_kernel<false, false><<<grid, p.nthreads, 0, s>>>(p, in, o);
-    }
+    int rc;
+    if (p.channels == 3) rc = blur ? launch_bwd_variant<true, true>(grid, p, in, o, s) : launch_bwd_variant<true, false>(grid, p, in, o, s);
+    else rc = blur ? launch_bwd_variant<false, true>(grid, p, in, o, s) : launch_bwd_variant<false, false>(grid, p, in, o, s);
+    if (rc != GSTEX_OK) return rc;
     GSTEX_LAUNCH_OK("raster_backward_kernel");
     return GSTEX_OK;
 }
@@ -292,7 +422,7 @@ extern "C" size_t gstex_texture_backward_temp_bytes(int n, int64_t num_texels, i
 }
 
 extern "C" int gstex_texture_backward(
-    int img_height, int img_width, int block_width, int n, int64_t num_texels, int channels,
+    int img_height, int img_width, int block_width, int n, int64_t num_texels, int channels, int64_t num_intersects,
     const int32_t *texture_dims, const int32_t *gaussian_ids_sorted, const int32_t *tile_bins, const float *colors,
     const float *opacities, const float *means, const float *scales, float glob_scale, const float *quats,
     const float *uv0, const float *umap, const float *vmap, const float *texture, const float *viewmat,
@@ -302,11 +432,13 @@ extern "C" int gstex_texture_backward(
     const float *v_out_texture, const float *v_out_normal, float *v_colors, float *v_opacity, float *v_means,
     float *v_scales, float *v_quats, float *v_uv0, float *v_umap, float *v_vmap, float *v_texture, int accumulate,
     const void *fwd_temp, void *temp, size_t temp_bytes, gstex_stream_t stream) {
+    GSTEX_REQUIRE(num_intersects >= 0 && num_intersects < ((int64_t)1 << 31), GSTEX_E_INVALID,
+                  "texture_backward: num_intersects = %lld", (long long)num_intersects);
     (void)texture_dims; (void)colors; (void)opacities; (void)uv0;
     int rc = check_raster_args("texture_backward", img_height, img_width, block_width, n, num_texels, channels, settings);
     if (rc != GSTEX_OK) return rc;
     GSTEX_REQUIRE(fwd_temp != nullptr, GSTEX_E_INVALID, "texture_backward: fwd_temp (forward scratch) is NULL");
-    const FwdLayout FL = forward_layout(n, num_texels, channels);
+    const FwdLayout FL = forward_layout(n, num_texels, channels, num_intersects);
     const BwdLayout L = backward_layout(n, num_texels, channels);
     GSTEX_REQUIRE(temp && temp_bytes >= L.total, GSTEX_E_WORKSPACE, "texture_backward: temp too small (%zu < %zu)",
                   temp_bytes, L.total);
@@ -325,7 +457,8 @@ extern "C" int gstex_texture_backward(
     const RasterCommon p = make_raster_common(
         img_height, img_width, block_width, channels, settings, gaussian_ids_sorted, tile_bins,
         (const float4 *)(fbase + FL.recs_off), (const float2 *)(fbase + FL.mean2d_off),
-        (const float4 *)(fbase + FL.tex4_off), texture, viewmat, c2w, background, fx, fy, cx, cy);
+        (const float4 *)(fbase + FL.tex4_off), texture, viewmat, c2w, background, fx, fy, cx, cy,
+        (uint32_t *)const_cast<char *>(fbase + FL.masks_off));
     BackwardIn in{final_Ts, final_s, final_idx, depth_idx, v_out_img, v_out_depth, v_out_reg, v_out_alpha, v_out_texture,
                   v_out_normal};
     BackwardOut o{acc, vtex4, v_texture};

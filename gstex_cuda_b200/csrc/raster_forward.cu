@@ -18,7 +18,7 @@ namespace gstex {
 // C3 = true : 3-channel texture read through the padded float4 copy, accumulators in registers.
 // C3 = false: runtime channel count (<= 64) read from the caller's (X,C) array (slow generic path).
 template <bool C3, bool BLUR>
-__global__ void __launch_bounds__(RASTER_MAX_THREADS) raster_forward_kernel(const RasterCommon p, const ForwardOut o) {
+__global__ void __launch_bounds__(RASTER_MAX_THREADS, 4) raster_forward_kernel(const RasterCommon p, const ForwardOut o) {
     __shared__ float4 stage[2][RASTER_BATCH * 8];
     __shared__ uint8_t survivors[RASTER_MAX_THREADS / 32][RASTER_BATCH];
 
@@ -80,6 +80,14 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS) raster_forward_kernel(cons
                     break;
                 }
                 if (pair_skipped(pe)) continue;
+
+                // Record which pixels of this warp blend entry first+i (read by the backward pass).  The lanes on this
+                // path are normally converged, so one lane ORs the whole group's mask; the OR keeps the word correct
+                // even if the hardware runs the group in several pieces.
+                if (p.masks) {
+                    const unsigned grp = __activemask();
+                    if (lane == __ffs(grp) - 1) atomicOr(p.masks + (size_t)(first + i) * MASK_WARPS + (tr >> 5), grp);
+                }
 
                 const float4 q4 = R[4 ^ sw], q5 = R[5 ^ sw], q6 = R[6 ^ sw], q7 = R[7 ^ sw];
                 const float vis = pe.alpha * T;
@@ -160,7 +168,7 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS) raster_forward_kernel(cons
 RasterCommon make_raster_common(int img_height, int img_width, int block_width, int channels, int settings,
                                 const int32_t *ids, const int32_t *tile_bins, const float4 *recs, const float2 *mean2d,
                                 const float4 *tex4, const float *tex, const float *viewmat, const float *c2w,
-                                const float *background, float fx, float fy, float cx, float cy) {
+                                const float *background, float fx, float fy, float cx, float cy, uint32_t *masks) {
     RasterCommon p;
     p.img_w = img_width;
     p.img_h = img_height;
@@ -179,10 +187,26 @@ RasterCommon make_raster_common(int img_height, int img_width, int block_width, 
     p.c2w = c2w;
     p.background = background;
     p.fx = fx; p.fy = fy; p.cx = cx; p.cy = cy;
+    p.masks = masks;
     return p;
 }
 
-int launch_raster_forward(const RasterCommon &p, const ForwardOut &o, cudaStream_t s) {
+// grid-stride zero fill of the live part of the mask array (the live length may only be known on the device)
+__global__ void __launch_bounds__(256) zero_masks_kernel(uint4 *__restrict__ masks, int64_t entries,
+                                                         const int32_t *__restrict__ d_count) {
+    const int64_t live = d_count ? min((int64_t)max(*d_count, 0), entries) : entries;
+    const int64_t quads = live * (MASK_WARPS / 4);
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += (int64_t)gridDim.x * blockDim.x)
+        masks[q] = make_uint4(0u, 0u, 0u, 0u);
+}
+
+int launch_raster_forward(const RasterCommon &p, const ForwardOut &o, int64_t mask_entries, const int32_t *d_count,
+                          cudaStream_t s) {
+    if (p.masks && mask_entries > 0) {
+        const int blocks = (int)min((int64_t)148 * 8, ceil_div64(mask_entries * (MASK_WARPS / 4), 256));
+        zero_masks_kernel<<<blocks, 256, 0, s>>>((uint4 *)p.masks, mask_entries, d_count);
+        GSTEX_LAUNCH_OK("zero_masks_kernel");
+    }
     const dim3 grid(p.tiles_x, ceil_div(p.img_h, p.bw));
     const bool blur = (p.settings & GSTEX_SET_BLUR) != 0;
     if (p.channels == 3) {
@@ -196,7 +220,7 @@ int launch_raster_forward(const RasterCommon &p, const ForwardOut &o, cudaStream
     return GSTEX_OK;
 }
 
-FwdLayout forward_layout(int n, int64_t num_texels, int channels) {
+FwdLayout forward_layout(int n, int64_t num_texels, int channels, int64_t num_intersects) {
     FwdLayout L;
     size_t off = 0;
     L.recs_off = off;
@@ -205,6 +229,8 @@ FwdLayout forward_layout(int n, int64_t num_texels, int channels) {
     off = align_up(off + sizeof(float2) * (size_t)(n > 0 ? n : 1), 256);
     L.tex4_off = off;
     if (channels == 3) off = align_up(off + sizeof(float4) * (size_t)(num_texels > 0 ? num_texels : 1), 256);
+    L.masks_off = off;
+    off = align_up(off + sizeof(uint32_t) * MASK_WARPS * (size_t)(num_intersects > 0 ? num_intersects : 1), 256);
     L.total = off;
     return L;
 }
@@ -228,52 +254,25 @@ int check_raster_args(const char *who, int img_height, int img_width, int block_
 
 using namespace gstex;
 
-extern "C" size_t gstex_texture_forward_temp_bytes(int n, int64_t num_texels, int channels) {
-    return forward_layout(n, num_texels, channels).total;
-}
-
-// fills the forward scratch: packed per-view records, projected means, padded texture
-static int texture_pack(int n, int64_t num_texels, int channels, const int32_t *texture_dims, const float *colors,
-                        const float *opacities, const float *means, const float *scales, float glob_scale,
-                        const float *quats, const float *uv0, const float *umap, const float *vmap,
-                        const float *texture, const float *viewmat, const float *c2w, float fx, float fy, float cx,
-                        float cy, void *temp, size_t temp_bytes, cudaStream_t s) {
-    const FwdLayout L = forward_layout(n, num_texels, channels);
-    GSTEX_REQUIRE(temp && temp_bytes >= L.total, GSTEX_E_WORKSPACE, "texture_pack: temp too small (%zu < %zu)",
-                  temp_bytes, L.total);
-    char *base = (char *)temp;
-    int rc = launch_pack(n, means, scales, glob_scale, quats, opacities, colors, uv0, umap, vmap, texture_dims, viewmat,
-                         c2w, fx, fy, cx, cy, (float4 *)(base + L.recs_off), (float2 *)(base + L.mean2d_off), s);
-    if (rc != GSTEX_OK) return rc;
-    if (channels == 3) return launch_pad_texture(num_texels, texture, (float4 *)(base + L.tex4_off), s);
-    return GSTEX_OK;
-}
-
-extern "C" int gstex_texture_pack(int n, int64_t num_texels, int channels, const int32_t *texture_dims,
-                                  const float *colors, const float *opacities, const float *means,
-                                  const float *scales, float glob_scale, const float *quats, const float *uv0,
-                                  const float *umap, const float *vmap, const float *texture, const float *viewmat,
-                                  const float *c2w, float fx, float fy, float cx, float cy, void *temp,
-                                  size_t temp_bytes, gstex_stream_t stream) {
-    GSTEX_REQUIRE(n >= 0 && num_texels >= 0 && channels >= 1 && channels <= RASTER_MAX_C, GSTEX_E_INVALID,
-                  "texture_pack: n = %d, texels = %lld, channels = %d", n, (long long)num_texels, channels);
-    return texture_pack(n, num_texels, channels, texture_dims, colors, opacities, means, scales, glob_scale, quats, uv0,
-                        umap, vmap, texture, viewmat, c2w, fx, fy, cx, cy, temp, temp_bytes, as_stream(stream));
+extern "C" size_t gstex_texture_forward_temp_bytes(int n, int64_t num_texels, int channels, int64_t num_intersects) {
+    return forward_layout(n, num_texels, channels, num_intersects).total;
 }
 
 extern "C" int gstex_texture_forward(int img_height, int img_width, int block_width, int n, int64_t num_texels,
-                                     int channels, const int32_t *texture_dims, const int32_t *gaussian_ids_sorted,
-                                     const int32_t *tile_bins, const float *colors, const float *opacities,
-                                     const float *means, const float *scales, float glob_scale, const float *quats,
-                                     const float *uv0, const float *umap, const float *vmap, const float *texture,
-                                     const float *viewmat, const float *c2w, float fx, float fy, float cx, float cy,
-                                     int settings, const float *background, float *out_img, float *out_depth,
-                                     float *out_reg, float *out_texture, float *out_normal, float *final_Ts,
-                                     int32_t *final_idx, int32_t *depth_idx, float *out_reg_s, void *temp,
-                                     size_t temp_bytes, gstex_stream_t stream) {
+                                     int channels, int64_t num_intersects, const int32_t *texture_dims,
+                                     const int32_t *gaussian_ids_sorted, const int32_t *tile_bins, const float *colors,
+                                     const float *opacities, const float *means, const float *scales, float glob_scale,
+                                     const float *quats, const float *uv0, const float *umap, const float *vmap,
+                                     const float *texture, const float *viewmat, const float *c2w, float fx, float fy,
+                                     float cx, float cy, int settings, const float *background, float *out_img,
+                                     float *out_depth, float *out_reg, float *out_texture, float *out_normal,
+                                     float *final_Ts, int32_t *final_idx, int32_t *depth_idx, float *out_reg_s,
+                                     void *temp, size_t temp_bytes, gstex_stream_t stream) {
     int rc = check_raster_args("texture_forward", img_height, img_width, block_width, n, num_texels, channels, settings);
     if (rc != GSTEX_OK) return rc;
-    const FwdLayout L = forward_layout(n, num_texels, channels);
+    GSTEX_REQUIRE(num_intersects >= 0 && num_intersects < ((int64_t)1 << 31), GSTEX_E_INVALID,
+                  "texture_forward: num_intersects = %lld", (long long)num_intersects);
+    const FwdLayout L = forward_layout(n, num_texels, channels, num_intersects);
     GSTEX_REQUIRE(temp && temp_bytes >= L.total, GSTEX_E_WORKSPACE, "texture_forward: temp too small (%zu < %zu)",
                   temp_bytes, L.total);
     cudaStream_t s = as_stream(stream);
@@ -281,12 +280,17 @@ extern "C" int gstex_texture_forward(int img_height, int img_width, int block_wi
     float4 *recs = (float4 *)(base + L.recs_off);
     float2 *mean2d = (float2 *)(base + L.mean2d_off);
     float4 *tex4 = (float4 *)(base + L.tex4_off);
-    rc = texture_pack(n, num_texels, channels, texture_dims, colors, opacities, means, scales, glob_scale, quats, uv0,
-                      umap, vmap, texture, viewmat, c2w, fx, fy, cx, cy, temp, temp_bytes, s);
+    uint32_t *masks = (uint32_t *)(base + L.masks_off);
+    rc = launch_pack(n, means, scales, glob_scale, quats, opacities, colors, uv0, umap, vmap, texture_dims, viewmat, c2w,
+                     fx, fy, cx, cy, recs, mean2d, s);
     if (rc != GSTEX_OK) return rc;
+    if (channels == 3) {
+        rc = launch_pad_texture(num_texels, texture, tex4, s);
+        if (rc != GSTEX_OK) return rc;
+    }
     const RasterCommon p = make_raster_common(img_height, img_width, block_width, channels, settings,
                                               gaussian_ids_sorted, tile_bins, recs, mean2d, tex4, texture, viewmat,
-                                              c2w, background, fx, fy, cx, cy);
+                                              c2w, background, fx, fy, cx, cy, masks);
     ForwardOut o{out_img, out_depth, out_reg, out_texture, out_normal, final_Ts, out_reg_s, final_idx, depth_idx};
-    return launch_raster_forward(p, o, s);
+    return launch_raster_forward(p, o, num_intersects, nullptr, s);
 }

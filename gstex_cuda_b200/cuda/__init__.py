@@ -139,15 +139,15 @@ def _check_raster_inputs(texture_dims, gaussian_ids_sorted, tile_bins, colors, o
         raise RuntimeError("background must hold at least 3 floats")
 
 
-def _forward_scratch(n, num_texels, channels, dev) -> torch.Tensor:
-    nbytes = _lib.load().gstex_texture_forward_temp_bytes(n, num_texels, channels)
+def _forward_scratch(n, num_texels, channels, num_intersects, dev) -> torch.Tensor:
+    nbytes = _lib.load().gstex_texture_forward_temp_bytes(n, num_texels, channels, num_intersects)
     return torch.empty((nbytes,), dtype=torch.uint8, device=dev)
 
 
 def texture_forward_ex(tile_bounds, block, img_size, texture_info, texture_dims, gaussian_ids_sorted, tile_bins,
                        colors, opacities, means, scales, glob_scale, quats, uv0, umap, vmap, texture, viewmat, c2w, fx,
                        fy, cx, cy, settings, background):
-    """texture_forward plus the forward scratch (packed records / padded texture) the backward can reuse."""
+    """texture_forward plus the forward scratch (packed records, padded texture, blend masks) the backward needs."""
     _check_raster_inputs(texture_dims, gaussian_ids_sorted, tile_bins, colors, opacities, means, scales, quats, uv0,
                          umap, vmap, texture, viewmat, c2w, background)
     dev = means.device
@@ -162,10 +162,11 @@ def texture_forward_ex(tile_bounds, block, img_size, texture_info, texture_dims,
     out_texture, out_normal = torch.empty((H, W, C), **f32), torch.empty((H, W, 3), **f32)
     final_Ts, final_idx, depth_idx = torch.empty((H, W), **f32), torch.empty((H, W), **i32), torch.empty((H, W), **i32)
     out_reg_s = torch.empty((H, W, 3), **f32)
-    scratch = _forward_scratch(n, X, C, dev)
+    M = gaussian_ids_sorted.shape[0]
+    scratch = _forward_scratch(n, X, C, M, dev)
     with torch.cuda.device(dev):
         rc = _lib.load().gstex_texture_forward(
-            H, W, bw, n, X, C, _p(texture_dims), _p(gaussian_ids_sorted), _p(tile_bins), _p(colors), _p(opacities),
+            H, W, bw, n, X, C, M, _p(texture_dims), _p(gaussian_ids_sorted), _p(tile_bins), _p(colors), _p(opacities),
             _p(means), _p(scales), float(glob_scale), _p(quats), _p(uv0), _p(umap), _p(vmap), _p(texture), _p(viewmat),
             _p(c2w), float(fx), float(fy), float(cx), float(cy), int(settings), _p(background), _p(out_img),
             _p(out_depth), _p(out_reg), _p(out_texture), _p(out_normal), _p(final_Ts), _p(final_idx), _p(depth_idx),
@@ -186,7 +187,7 @@ def texture_backward(img_height, img_width, block_width, texture_info, texture_d
     """texture_backward_tensor, texture.cu:915-1053: returns the same 9-tuple of gradients.
 
     ``_fwd_scratch`` (keyword, optional, not in the reference signature) is the scratch tensor returned by
-    ``texture_forward_ex`` for the same inputs; without it the records are packed again first.
+    ``texture_forward_ex`` for the same inputs; without it the forward pass is run again first.
     """
     _check_raster_inputs(texture_dims, gaussian_ids_sorted, tile_bins, colors, opacities, means, scales, quats, uv0,
                          umap, vmap, texture, viewmat, c2w, background)
@@ -208,15 +209,15 @@ def texture_backward(img_height, img_width, block_width, texture_info, texture_d
     lib = _lib.load()
     with torch.cuda.device(dev):
         if _fwd_scratch is None:
-            _fwd_scratch = _forward_scratch(n, X, C, dev)
-            rc = lib.gstex_texture_pack(n, X, C, _p(texture_dims), _p(colors), _p(opacities), _p(means), _p(scales),
-                                        float(glob_scale), _p(quats), _p(uv0), _p(umap), _p(vmap), _p(texture),
-                                        _p(viewmat), _p(c2w), float(fx), float(fy), float(cx), float(cy),
-                                        _p(_fwd_scratch), _fwd_scratch.numel(), _stream(dev))
-            _lib.check(rc, "texture_pack")
+            # the reference's backward is a pure function of its arguments; ours differentiates the pairs recorded by
+            # the forward pass, so a caller that kept no scratch pays for one more forward here
+            _, _fwd_scratch = texture_forward_ex(
+                ((W + bw - 1) // bw, (H + bw - 1) // bw, 1), (bw, bw, 1), (W, H, 1), texture_info, texture_dims,
+                gaussian_ids_sorted, tile_bins, colors, opacities, means, scales, glob_scale, quats, uv0, umap, vmap,
+                texture, viewmat, c2w, fx, fy, cx, cy, settings, background)
         temp = torch.empty((lib.gstex_texture_backward_temp_bytes(n, X, C),), dtype=torch.uint8, device=dev)
         rc = lib.gstex_texture_backward(
-            H, W, bw, n, X, C, _p(texture_dims), _p(gaussian_ids_sorted), _p(tile_bins), _p(colors), _p(opacities),
+            H, W, bw, n, X, C, gaussian_ids_sorted.shape[0], _p(texture_dims), _p(gaussian_ids_sorted), _p(tile_bins), _p(colors), _p(opacities),
             _p(means), _p(scales), float(glob_scale), _p(quats), _p(uv0), _p(umap), _p(vmap), _p(texture), _p(viewmat),
             _p(c2w), float(fx), float(fy), float(cx), float(cy), int(settings), _p(background), _p(final_Ts),
             _p(final_idx), _p(depth_idx), _p(final_s), _p(v_output), _p(v_output_depth), _p(v_output_reg),

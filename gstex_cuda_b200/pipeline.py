@@ -85,6 +85,7 @@ class FusedTrainStep:
         self.nth = torch.empty((n,), **i32)
         self.ids_sorted = torch.empty((self.cap,), **i32)
         self.num_isect = torch.zeros((1,), **i32)
+        self.masks = torch.empty((self.cap, 8), **i32)  # blend masks: forward -> backward (csrc/raster.cuh)
         self.bin_temp = torch.empty((self.lib.gstex_bin_tiles_temp_bytes(self.num_tiles, self.cap),), dtype=torch.uint8, device=dev)
         self.tile_bins = torch.empty((self.num_tiles, 2), **i32)
         self.recs, self.mean2d, self.acc = torch.empty((n, 32), **f32), torch.empty((n, 2), **f32), torch.empty((n, 32), **f32)
@@ -169,8 +170,9 @@ class FusedTrainStep:
                                               P(self.recs), P(self.mean2d), P(tex), P(viewmat), P(c2w), fx, fy, cx, cy,
                                               P(self.background), P(o["out_img"]), P(o["out_depth"]), P(o["out_reg"]),
                                               P(o["out_texture"]), P(o["out_normal"]), P(o["final_Ts"]),
-                                              P(o["final_idx"]), P(o["depth_idx"]), P(o["out_reg_s"]), s), "raster_forward")
-        self.launches += 1 + 1 + self._bin_launches + 1 + 1  # sh, project, binning, pack, raster
+                                              P(o["final_idx"]), P(o["depth_idx"]), P(o["out_reg_s"]), P(self.masks), self.cap,
+                                              P(self.num_isect), s), "raster_forward")
+        self.launches += 1 + 1 + self._bin_launches + 1 + 2  # sh, project, binning, pack, mask zero-fill + raster
         return o
 
     def view_loss(self, target: torch.Tensor) -> None:
@@ -203,7 +205,7 @@ class FusedTrainStep:
                                                P(self.background), P(o["final_Ts"]), P(o["final_idx"]),
                                                P(o["depth_idx"]), P(o["out_reg_s"]), P(v["v_out_img"]),
                                                P(v["v_out_depth"]), P(v["v_out_reg"]), P(v["v_out_alpha"]),
-                                               P(v["v_out_texture"]), P(v["v_out_normal"]), P(self.acc), P(vtex), s),
+                                               P(v["v_out_texture"]), P(v["v_out_normal"]), P(self.masks), P(self.acc), P(vtex), s),
                      "raster_backward")
         self.launches += 3  # raster backward, epilogue, SH backward
         self._ck(lib.gstex_raster_epilogue(n, P(p["means"]), P(p["scales"]), self.glob_scale, P(p["quats"]), P(p["umap"]),

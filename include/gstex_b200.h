@@ -124,42 +124,37 @@ int gstex_bin_tiles(int n, const float *centers, const float *extents, const flo
  * (3) rasterise forward / (4) rasterise backward
  * ======================================================================================== */
 
-/* Scratch needed by gstex_texture_forward / gstex_texture_backward for n Gaussians, x texels with
- * c channels.  The forward scratch must stay alive and untouched until the matching backward ran
- * (it holds the per-view packed Gaussian records and the padded texture). */
-size_t gstex_texture_forward_temp_bytes(int n, int64_t num_texels, int channels);
+/* Scratch needed by gstex_texture_forward / gstex_texture_backward for n Gaussians, x texels with c channels and
+ * num_intersects sorted-list entries (the length of gaussian_ids_sorted).  The forward scratch must stay alive and
+ * untouched until the matching backward ran: it holds the per-view packed Gaussian records, the float4-padded
+ * texture and the forward pass's blend masks (one 32-bit word per list entry and warp: which pixels composited
+ * the entry), which is what the backward pass differentiates. */
+size_t gstex_texture_forward_temp_bytes(int n, int64_t num_texels, int channels, int64_t num_intersects);
 size_t gstex_texture_backward_temp_bytes(int n, int64_t num_texels, int channels);
-
-/* Fills the forward scratch (per-view packed records + padded texture) without rasterising.  The
- * reference's texture_backward is a pure function of its arguments (texture.cuh:120-168); a caller that
- * invokes the backward without having run gstex_texture_forward for the same inputs packs first. */
-int gstex_texture_pack(int n, int64_t num_texels, int channels, const int32_t *texture_dims, const float *colors,
-                       const float *opacities, const float *means, const float *scales, float glob_scale,
-                       const float *quats, const float *uv0, const float *umap, const float *vmap,
-                       const float *texture, const float *viewmat, const float *c2w, float fx, float fy, float cx,
-                       float cy, void *temp, size_t temp_bytes, gstex_stream_t stream);
 
 /* replaces texture_forward_tensor, texture.cu:766-901 (kernel :11-329).
  * Outputs (all fully written): out_img (H,W,3), out_depth (H,W), out_reg (H,W), out_texture (H,W,C),
  * out_normal (H,W,3), final_Ts (H,W), final_idx (H,W) int32, depth_idx (H,W) int32, out_reg_s (H,W,3).
  * background: 3 floats on the device. */
 int gstex_texture_forward(int img_height, int img_width, int block_width, int n, int64_t num_texels,
-                          int channels, const int32_t *texture_dims, const int32_t *gaussian_ids_sorted,
-                          const int32_t *tile_bins, const float *colors, const float *opacities,
-                          const float *means, const float *scales, float glob_scale, const float *quats,
-                          const float *uv0, const float *umap, const float *vmap, const float *texture,
-                          const float *viewmat, const float *c2w, float fx, float fy, float cx, float cy,
-                          int settings, const float *background, float *out_img, float *out_depth,
+                          int channels, int64_t num_intersects, const int32_t *texture_dims,
+                          const int32_t *gaussian_ids_sorted, const int32_t *tile_bins, const float *colors,
+                          const float *opacities, const float *means, const float *scales, float glob_scale,
+                          const float *quats, const float *uv0, const float *umap, const float *vmap,
+                          const float *texture, const float *viewmat, const float *c2w, float fx, float fy, float cx,
+                          float cy, int settings, const float *background, float *out_img, float *out_depth,
                           float *out_reg, float *out_texture, float *out_normal, float *final_Ts,
                           int32_t *final_idx, int32_t *depth_idx, float *out_reg_s, void *temp,
                           size_t temp_bytes, gstex_stream_t stream);
 
 /* replaces texture_backward_tensor, texture.cu:915-1053 (kernel :331-760).
- * fwd_temp: the scratch the matching forward call filled.  Gradients (n,3) (n,1) (n,3) (n,3) (n,4) (n,1,2)
+ * fwd_temp: the scratch the matching gstex_texture_forward call (same inputs) filled; the reference's backward is a
+ * pure function of its arguments (texture.cuh:120-168), so a caller without that scratch runs the forward again
+ * first (gstex_cuda_b200/cuda/__init__.py does).  Gradients (n,3) (n,1) (n,3) (n,3) (n,4) (n,1,2)
  * (n,1,3) (n,1,3) (X,C): if accumulate == 0 they are overwritten (no zero-fill needed), otherwise the
  * view's gradient is added to what they hold (multi-view accumulation). */
 int gstex_texture_backward(int img_height, int img_width, int block_width, int n, int64_t num_texels,
-                           int channels, const int32_t *texture_dims, const int32_t *gaussian_ids_sorted,
+                           int channels, int64_t num_intersects, const int32_t *texture_dims, const int32_t *gaussian_ids_sorted,
                            const int32_t *tile_bins, const float *colors, const float *opacities,
                            const float *means, const float *scales, float glob_scale, const float *quats,
                            const float *uv0, const float *umap, const float *vmap, const float *texture,
@@ -209,6 +204,8 @@ int gstex_image_loss(int img_height, int img_width, const float *out_texture, co
  * The stages gstex_texture_forward / gstex_texture_backward run internally, exposed so that a multi-view step
  * pads the texture once, packs records per view and accumulates all views into one gradient arena.
  * recs: n x 32 floats, mean2d: n x 2 floats, acc: n x 32 floats (zero-filled by the caller per view),
+ * masks: mask_entries x 8 uint32 blend masks written by gstex_raster_forward (which first zeroes the words of the first
+ * min(*d_num_intersects, mask_entries) entries; d_num_intersects NULL = all) and read by gstex_raster_backward,
  * tex / vtex: (X,4) padded when channels == 3, else the caller's (X,C) layout; vtex is accumulated into. */
 int gstex_pad_texture(int64_t num_texels, const float *texture, float *tex4, gstex_stream_t stream);
 int gstex_unpad_texture_grad(int64_t num_texels, const float *g4, float *v_texture, int accumulate,
@@ -223,7 +220,8 @@ int gstex_raster_forward(int img_height, int img_width, int block_width, int cha
                          const float *mean2d, const float *tex, const float *viewmat, const float *c2w, float fx,
                          float fy, float cx, float cy, const float *background, float *out_img, float *out_depth,
                          float *out_reg, float *out_texture, float *out_normal, float *final_Ts,
-                         int32_t *final_idx, int32_t *depth_idx, float *out_reg_s, gstex_stream_t stream);
+                         int32_t *final_idx, int32_t *depth_idx, float *out_reg_s, uint32_t *masks,
+                         int64_t mask_entries, const int32_t *d_num_intersects, gstex_stream_t stream);
 int gstex_raster_backward(int img_height, int img_width, int block_width, int channels, int settings,
                           const int32_t *gaussian_ids_sorted, const int32_t *tile_bins, const float *recs,
                           const float *mean2d, const float *tex, const float *viewmat, const float *c2w, float fx,
@@ -231,7 +229,7 @@ int gstex_raster_backward(int img_height, int img_width, int block_width, int ch
                           const int32_t *final_idx, const int32_t *depth_idx, const float *final_s,
                           const float *v_out_img, const float *v_out_depth, const float *v_out_reg,
                           const float *v_out_alpha, const float *v_out_texture, const float *v_out_normal,
-                          float *acc, float *vtex, gstex_stream_t stream);
+                          const uint32_t *masks, float *acc, float *vtex, gstex_stream_t stream);
 int gstex_raster_epilogue(int n, const float *means, const float *scales, float glob_scale, const float *quats,
                           const float *umap, const float *vmap, const float *viewmat, const float *c2w, float fx,
                           float fy, float cx, float cy, const float *acc, float *v_colors, float *v_opacity,

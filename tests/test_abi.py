@@ -34,9 +34,10 @@ def test_host_only_entry_points():
     assert lib.gstex_scan_temp_bytes(1 << 20) >= 4 * ((1 << 20) // 2048)
     assert lib.gstex_sort_temp_bytes(1 << 20) >= 12 * (1 << 20)
     n, x = 1000, 16000
-    assert lib.gstex_texture_forward_temp_bytes(n, x, 3) >= 128 * n + 16 * x
-    assert lib.gstex_texture_forward_temp_bytes(n, x, 5) >= 128 * n
+    assert lib.gstex_texture_forward_temp_bytes(n, x, 3, 5 * n) >= 128 * n + 16 * x + 32 * 5 * n
+    assert lib.gstex_texture_forward_temp_bytes(n, x, 5, 0) >= 128 * n
     assert lib.gstex_texture_backward_temp_bytes(n, x, 3) >= 128 * n + 16 * x
+    assert lib.gstex_bin_tiles_temp_bytes(8160, 4 * n) >= 8 * 4 * n + 12 * 8160
     # argument validation happens on the host before any CUDA call: error code + message, no exception
     rc = lib.gstex_sh_forward(10, 7, 0, None, None, None, None)
     assert rc == -1 and "degree" in _lib.last_error()
