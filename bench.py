@@ -12,8 +12,9 @@ A "step" is one training step of the hot path over one batch of synthetic views:
   rasterise forward -> image loss (example.py:189-209) -> rasterise backward -> per-Gaussian epilogue ->
   SH backward [-> NCCL all-reduce of the gradient arena when N > 1].
 N = 1 : BASELINE config 4 - one 1920x1080 view per step (the front camera of SURVEY 8d C4).
-N > 1 : BASELINE config 5 - 64 orbit views per step, sharded round-robin over the ranks, replicated
-        parameters, one all-reduce of the 0.43 GB fp32 gradient arena per step  (strong scaling).
+N > 1 : BASELINE config 5 - 64 views per step (an arc of +-30 degrees around the C4 camera, so that a view costs about
+        what the C4 view costs), sharded round-robin over the ranks, replicated parameters, one all-reduce of the
+        0.46 GB fp32 gradient arena per step  (strong scaling of the 64-view batch).
 `value` = pixels rendered (forward+backward) by all ranks / device time (max over ranks), inputs resident in HBM.
 `e2e`   = the same metric through the reference-shaped public API (project_points, get_aabb_2d,
           get_num_tiles_hit_2d, texture_gaussians, autograd) with the step's inputs (camera matrices and target
@@ -189,11 +190,13 @@ def main():
         run_reference(args, rank)
         return
 
+    # rank 0 prints exactly one JSON line on stdout: keep NCCL's banner out of it (GSTEX_NCCL_DEBUG=INFO to see NCCL logs)
+    os.environ["NCCL_DEBUG"] = os.environ.get("GSTEX_NCCL_DEBUG", "WARN")
     import torch
     import torch.distributed as dist
 
     from gstex_cuda_b200.pipeline import FusedTrainStep, DataParallelTrainStep
-    from gstex_cuda_b200.scenes import synthetic_scene, circle_cameras
+    from gstex_cuda_b200.scenes import synthetic_scene, arc_cameras
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (the product has no CPU path)"
     torch.cuda.set_device(local_rank)
@@ -210,8 +213,9 @@ def main():
         cams = [(scene["viewmat"], scene["c2w"])]
         workload = "C4: 1 view/step, front camera"
     else:
-        cams = [(a.to(dev), b.to(dev)) for a, b in circle_cameras(views)]
-        workload = f"C5: {views} orbit views/step sharded over {world} GPU(s), NCCL all-reduce of the gradient arena"
+        cams = [(a.to(dev), b.to(dev)) for a, b in arc_cameras(views)]
+        workload = (f"C5: {views} views/step on a +-30 degree arc around the C4 camera, sharded over {world} GPU(s), "
+                    f"one NCCL all-reduce of the gradient arena per step")
     mine = DataParallelTrainStep.shard(views, rank, world)
     gen = torch.Generator().manual_seed(99)
     targets_host = {}

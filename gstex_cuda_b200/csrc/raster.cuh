@@ -243,6 +243,17 @@ __device__ __forceinline__ int build_survivors(const float4 *__restrict__ S, int
     return n;
 }
 
+// Pull the first lines of a Gaussian's texture block towards the SM before the compositing loop needs them: the
+// texel fetch is the one long-latency load of a blended pair (4 x 16 B inside a block of h*w*16 B; 256 B for the
+// 4x4 textures of the C4 scene).
+__device__ __forceinline__ void prefetch_texture_block(const float4 *__restrict__ tex4, int tex0, int h, int w) {
+    const char *base = reinterpret_cast<const char *>(tex4 + tex0);
+    const int bytes = h * w * 16;
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(base));
+    if (bytes > 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(base + 128));
+    if (bytes > 256) asm volatile("prefetch.global.L1 [%0];" ::"l"(base + bytes - 16));
+}
+
 struct RasterCommon {
     int img_w, img_h, tiles_x, bw, nthreads, settings, channels;
     const int32_t *ids;        // gaussian_ids_sorted

@@ -64,6 +64,10 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, 4) raster_forward_kernel(c
         // stage b is visible to the whole CTA after this barrier; leave if every pixel is finished
         if (__syncthreads_count(done) >= p.nthreads) break;
         const float4 *__restrict__ S = stage[b & 1];
+        if (C3 && tr < cnt) {  // one thread per staged record: start fetching its texture block
+            const float4 q3 = S[quad_slot(tr, 3)], q6 = S[quad_slot(tr, 6)];
+            prefetch_texture_block(p.tex4, __float_as_int(q6.w), __float_as_int(q3.z), __float_as_int(q3.w));
+        }
         // warp-level culling: the warp walks only the records that can reach alpha >= 1/255 on its patch
         const int nsurv = __all_sync(0xffffffffu, done) ? 0 : build_survivors<BLUR>(S, 0, cnt, wr, p.mean2d, my_list, lane);
         if (!done) {

@@ -131,6 +131,15 @@ class FusedTrainStep:
 
         return _T()
 
+    def _cam(self, m: torch.Tensor, name: str) -> torch.Tensor:
+        """Camera matrices are read through raw pointers as row-major 4x4 float32: reject anything else loudly
+        (torch.linalg.inv, for one, returns column-major strides)."""
+        if not (isinstance(m, torch.Tensor) and m.is_cuda and m.dtype == torch.float32 and tuple(m.shape) == (4, 4)):
+            raise RuntimeError(f"{name} must be a float32 CUDA tensor of shape (4, 4)")
+        if not m.is_contiguous():
+            raise RuntimeError(f"{name} must be contiguous (row-major); call .contiguous() on it")
+        return m
+
     def begin_step(self) -> None:
         """Once per optimiser step: pad the texture, clear the texel-gradient buffer and the loss."""
         lib, s = self.lib, self._s()
@@ -149,6 +158,7 @@ class FusedTrainStep:
         n, H, W, bw = self.n, self.H, self.W, self.bw
         fx, fy, cx, cy = self.intr
         P = lambda t: t.data_ptr()  # noqa: E731
+        viewmat, c2w = self._cam(viewmat, "viewmat"), self._cam(c2w, "c2w")
         self._ck(lib.gstex_sh_colors_forward(n, self.sh_degree, self.sh_degree, P(p["means"]), P(c2w), P(p["sh_coeffs"]),
                                              P(self.colors), P(self.mask), s), "sh_colors_forward")
         self._ck(lib.gstex_project_aabb_count(n, P(p["means"]), P(p["scales"]), self.glob_scale, P(p["quats"]), P(viewmat),
@@ -192,6 +202,7 @@ class FusedTrainStep:
         fx, fy, cx, cy = self.intr
         P = lambda t: t.data_ptr()  # noqa: E731
         v = vout if vout is not None else self.vout
+        viewmat, c2w = self._cam(viewmat, "viewmat"), self._cam(c2w, "c2w")
         o, g = self.out, self.grads
         acc_flag = 0 if self._first_view else 1
         self.acc.zero_()

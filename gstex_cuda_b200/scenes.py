@@ -27,7 +27,8 @@ def look_at_camera(eye, target=(0.0, 0.0, 0.0), up=(0.0, 1.0, 0.0)) -> Tuple[tor
     viewmat[:3, :3] = R
     viewmat[:3, 3] = -R @ eye
     c2w = torch.linalg.inv(viewmat)
-    return viewmat.float(), c2w.float()
+    # torch.linalg.inv returns a column-major tensor: make both row-major (the kernels read raw pointers)
+    return viewmat.float().contiguous(), c2w.float().contiguous()
 
 
 def uniform_quats(n: int, gen: torch.Generator) -> torch.Tensor:
@@ -97,6 +98,17 @@ def circle_cameras(num_views: int, radius: float = 8.0, height: float = 0.0) -> 
         a = 2.0 * math.pi * i / num_views
         eye = (radius * math.sin(a), height, -radius * math.cos(a))
         cams.append(look_at_camera(eye))
+    return cams
+
+
+def arc_cameras(num_views: int, radius: float = 8.0, half_angle_deg: float = 30.0) -> List[Tuple[torch.Tensor, torch.Tensor]]:
+    """Config C5 as benchmarked: cameras on an arc of +-half_angle around the C4 front camera (same distance, all
+    looking at the origin), so that every view sees the scene face-on and costs about what the C4 view costs -
+    which is what makes the 1 -> 8 GPU throughput numbers comparable.  View num_views // 2 is (nearly) the front view."""
+    cams = []
+    for i in range(num_views):
+        a = math.radians(half_angle_deg) * (2.0 * i / max(1, num_views - 1) - 1.0) if num_views > 1 else 0.0
+        cams.append(look_at_camera((radius * math.sin(a), 0.0, -radius * math.cos(a))))
     return cams
 
 

@@ -7,7 +7,7 @@ import torch
 import oracle
 from gstex_cuda_b200 import sh as SH
 from gstex_cuda_b200.pipeline import FusedTrainStep, DataParallelTrainStep
-from gstex_cuda_b200.scenes import synthetic_scene, circle_cameras
+from gstex_cuda_b200.scenes import synthetic_scene, arc_cameras
 from gstex_cuda_b200.texture import texture_gaussians
 from gstex_cuda_b200.get_aabb_2d import get_aabb_2d, get_num_tiles_hit_2d, project_points
 from gpu_util import DEV, to_np, assert_close_frac
@@ -47,7 +47,7 @@ def _api_step(s, cams, targets):
 @pytest.mark.parametrize("nviews", [1, 3])
 def test_fused_step_matches_api_path(nviews):
     s = synthetic_scene(30000, 320, 192, seed=7, device=DEV)
-    cams = [(s["viewmat"], s["c2w"])] + [(a.to(DEV), b.to(DEV)) for a, b in circle_cameras(8)[1:nviews]]
+    cams = [(s["viewmat"], s["c2w"])] + [(a.to(DEV), b.to(DEV)) for a, b in arc_cameras(5)[: nviews - 1]]
     g = torch.Generator().manual_seed(1)
     targets = [torch.rand(s["H"], s["W"], 3, generator=g).to(DEV) for _ in range(nviews)]
     fused = FusedTrainStep({k: s[k] for k in PARAMS}, s["texture_dims"], s["H"], s["W"], intrins=s["intrins"],
@@ -55,6 +55,9 @@ def test_fused_step_matches_api_path(nviews):
     loss = fused.step(cams, targets)
     m = fused.check_overflow()
     assert m > 0
+    assert float((1 - fused.out["final_Ts"]).mean()) > 0.03  # the last (rotated) view really rendered the scene
+    with pytest.raises(RuntimeError):  # column-major camera matrices (torch.linalg.inv) are rejected, not misread
+        fused.view_forward(cams[0][0], torch.linalg.inv(cams[0][0]))
     loss_api, grads = _api_step(s, cams, targets)
     assert abs(float(loss) - loss_api) <= 1e-4 * abs(loss_api) + 1e-6
     names = dict(means="v_means", scales="v_scales", quats="v_quats", opacities="v_opacity", sh_coeffs="v_sh_coeffs",

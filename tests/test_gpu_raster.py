@@ -164,3 +164,39 @@ def test_unsupported_settings_fail_loudly():
     b = bin_cuda(s)
     with pytest.raises(RuntimeError, match="settings"):
         forward_cuda(s, b["gaussian_ids_sorted"], b["tile_bins"], settings=(1 << 8) | (1 << 16))
+
+
+# ---- general cameras: every fixture above looks down +z with an identity rotation (as example.py does) -----------
+def _rotated_scene(n, W, H, seed, yaw_deg, pitch_deg, roll_deg, channels=3):
+    import math
+    from gstex_cuda_b200.scenes import look_at_camera
+    s = random_small_scene(n, W, H, seed=seed, channels=channels, device=DEV)
+    y, p_ = math.radians(yaw_deg), math.radians(pitch_deg)
+    eye = (8 * math.sin(y) * math.cos(p_), 8 * math.sin(p_), -8 * math.cos(y) * math.cos(p_))
+    vm, _ = look_at_camera(eye)
+    r = math.radians(roll_deg)
+    roll = torch.tensor([[math.cos(r), -math.sin(r), 0, 0], [math.sin(r), math.cos(r), 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]],
+                        dtype=torch.float32)
+    vm = (roll @ vm).contiguous()
+    s["viewmat"], s["c2w"] = vm.to(DEV), torch.linalg.inv(vm).contiguous().to(DEV)
+    return s
+
+
+@pytest.mark.parametrize("yaw,pitch,roll,settings", [(0, 0, 180, 1 << 8), (25, 0, 0, 1 << 8), (-20, 15, 40, 1 << 8),
+                                                     (30, -10, 75, (1 << 8) | (1 << 9) | (1 << 10))])
+def test_rotated_camera_vs_oracle(yaw, pitch, roll, settings):
+    s = _rotated_scene(300, 96, 80, 11, yaw, pitch, roll)
+    s["settings"] = settings
+    b = bin_cuda(s)
+    ids, bins = b["gaussian_ids_sorted"], b["tile_bins"]
+    bo = oracle.bin_view(to_np(s["means"]), to_np(s["scales"]), 1.0, to_np(s["quats"]), to_np(s["viewmat"]), s["intrins"],
+                         s["H"], s["W"], 16)
+    assert abs(len(bo["gaussian_ids_sorted"]) - b["num_intersects"]) <= 2
+    f_c, scratch = forward_cuda(s, ids, bins)
+    f_o = forward_oracle(s, to_np(ids), to_np(bins))
+    assert float((1 - f_o["final_Ts"]).mean()) > 0.02  # the scene is in view
+    compare_forward(f_c, f_o, max_bad_frac=FLIP, int_bad_frac=FLIP)
+    vout = random_vout(s, 5)
+    g_c = backward_cuda(s, ids, bins, f_c, vout, scratch=scratch)
+    g_o = backward_oracle(s, to_np(ids), to_np(bins), f_c, vout)
+    compare_backward(g_c, g_o, max_bad_frac=FLIP)

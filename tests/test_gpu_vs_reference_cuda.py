@@ -175,3 +175,23 @@ def test_sample_and_sh_vs_reference_cuda(ref):
     b = ref.texture_sample_forward((50, 1, 7), qd, uvs, s["texture"])
     torch.cuda.synchronize()
     torch.testing.assert_close(a, b, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("yaw,pitch,roll", [(0, 0, 180), (25, 10, -30)])
+def test_rotated_camera_vs_reference_cuda(ref, yaw, pitch, roll):
+    """The reference's own fixtures never rotate the camera; this pins oracle and kernels for general cameras."""
+    from test_gpu_raster import _rotated_scene
+    s = _rotated_scene(400, 96, 96, 21, yaw, pitch, roll)
+    b = bin_cuda(s)
+    ids, bins = b["gaussian_ids_sorted"], b["tile_bins"]
+    f_m, scratch = forward_cuda(s, ids, bins)
+    f_r = ref_forward(ref, s, ids, bins, 16, 1 << 8)
+    f_r_np = {k: to_np(v) for k, v in f_r.items()}
+    assert float((1 - f_r_np["final_Ts"]).mean()) > 0.02
+    compare_forward(f_m, f_r_np, max_bad_frac=2e-3, int_bad_frac=2e-3)
+    compare_forward(forward_oracle(s, to_np(ids), to_np(bins)), f_r_np, max_bad_frac=2e-3, int_bad_frac=2e-3)
+    vout = random_vout(s, 2)
+    g_r = {k: to_np(v) for k, v in ref_backward(ref, s, ids, bins, 16, 1 << 8, f_r, vout).items()}
+    g_m = backward_cuda(s, ids, bins, f_m, vout, scratch=scratch)
+    compare_backward(g_m, g_r, max_bad_frac=2e-3)
+    compare_backward(backward_oracle(s, to_np(ids), to_np(bins), f_r, vout), g_r, max_bad_frac=2e-3)
