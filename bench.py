@@ -42,8 +42,8 @@ UNIT = "Mpixel/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--points", type=int, default=1_000_000)
     ap.add_argument("--width", type=int, default=1920)
@@ -87,12 +87,19 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
-    def stop(self):
+    def mark(self):
+        """Index of the next sample: call at the start of the loaded region."""
+        return len(self.rows)
+
+    def stop(self, since: int = 0):
+        """Summary of the samples taken since `since` (they cover warm-up + timed steps: all of it is load)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)  # let the last sample of the loaded region arrive
         self.proc.terminate()
+        rows = self.rows[since:] or self.rows[-1:]
         sm, smax, reasons = [], None, set()
-        for r in self.rows:
+        for r in rows:
             c = [x.strip() for x in r.split(",")]
             if len(c) < 6:
                 continue
@@ -199,6 +206,8 @@ def main():
     from gstex_cuda_b200.scenes import synthetic_scene, arc_cameras
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (the product has no CPU path)"
+    sampler = ClockSampler(local_rank)
+    sampler.start()  # nvidia-smi takes a while to deliver its first sample: start it long before the timed region
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -235,6 +244,8 @@ def main():
         torch.cuda.synchronize()
 
     # ---- warm-up --------------------------------------------------------------------------------
+    barrier()
+    load_start = sampler.mark()
     for _ in range(args.warmup):
         dp.step(cams, targets)
     barrier()
@@ -244,8 +255,6 @@ def main():
     fused.time_kernels = True
     fused.kernel_events = []
     launches0 = fused.launches
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -253,7 +262,7 @@ def main():
         loss = dp.step(cams, targets)
     e1.record()
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop(load_start)
     elapsed_ms = e0.elapsed_time(e1)
     launches = fused.launches - launches0
     fused.time_kernels = False

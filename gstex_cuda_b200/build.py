@@ -23,6 +23,10 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-Xptxas", "-v", "--expt-relaxed-constexpr"]
 
 
+# experiments: extra flags (e.g. -DGSTEX_EXP_...) through the environment, never set in production
+NVCC_FLAGS += os.environ.get("GSTEX_NVCC_EXTRA", "").split()
+
+
 def _nvcc() -> str:
     for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", shutil.which("nvcc")):
         if cand and os.path.exists(cand):

@@ -39,6 +39,10 @@ constexpr int BWD_WARPS = RASTER_MAX_THREADS / 32;
 constexpr int BWD_QCAP = 128;          // pairs per chunk (4 dense iterations)
 constexpr int BWD_ECAP = 16;           // list entries (Gaussians) per chunk: their records are staged per warp
 constexpr int BWD_BATCH = 64;          // list entries whose mask words a warp fetches at a time
+#ifndef GSTEX_BWD_FULL
+#define GSTEX_BWD_FULL 20
+#endif
+constexpr int BWD_FULL = GSTEX_BWD_FULL;  // entries covering at least this many of the 32 pixels run lane = pixel
 
 template <bool BLUR>
 struct BwdWarpSmem {
@@ -52,6 +56,7 @@ struct BwdWarpSmem {
     uint32_t sv_mask[BWD_BATCH];       // blend mask of each non-empty entry of the batch
     int32_t sv_gid[BWD_BATCH];         // its Gaussian id
     uint16_t q_ent[BWD_QCAP];          // pair -> (chunk-local entry | pixel lane << 8)
+    uint16_t ch_off[BWD_ECAP];         // first queue slot of each chunk entry
     uint8_t sv_r[BWD_BATCH];           // its position inside the batch
 };
 
@@ -59,6 +64,176 @@ struct PixelShare {  // per-pixel values a pair lane fetches from the pixel's la
     float vi0, vi1, vi2, vn0, vn1, vn2, vt0, vt1, vt2, Sf0, Sf1, Sf2, v_reg, v_dep;
     int dfinal, pix;
 };
+
+struct PairFlags {
+    bool use_ndc, bilinear, want_uv;
+    int C;
+};
+
+// First half of a pair's gradient: everything that does not need the pair's transmittance.
+//   y      = dL/d(vis-weighted value) = colour, normal and texture terms + the distortion weight term
+//            (reference texture.cu:583-589, :612-634, :661-668 with the FINAL sums, helpers.cuh:266-269)
+//   gu, gv = d(texture term)/du, /dv per unit vis (texture_helpers.cuh:252-300)
+template <bool C3>
+__device__ __forceinline__ void pair_terms(const RasterCommon &p, const BackwardIn &in, const PairFlags &fl,
+                                           const float4 q3, const float4 q4, const float4 q5, const float4 q6,
+                                           const float4 q7, const PairEval &pe, const PixelConsts &qc,
+                                           const PixelShare &px, float &y, float &gu, float &gv) {
+    float v_vis = q6.x * px.vi0 + q6.y * px.vi1 + q6.z * px.vi2 + q7.x * px.vn0 + q7.y * px.vn1 + q7.z * px.vn2;
+    const float nu = fmaf(q4.x, pe.ex, fmaf(q4.y, pe.ey, q4.z));
+    const float nv = fmaf(q5.x, pe.ex, fmaf(q5.y, pe.ey, q5.z));
+    const float u = clamp01(fmaf(nu, pe.rD, q4.w)), v = clamp01(fmaf(nv, pe.rD, q5.w));
+    TexFetch tf;
+    texel_setup(__float_as_int(q3.z), __float_as_int(q3.w), __float_as_int(q6.w), u, v, fl.bilinear, tf);
+    gu = 0.f;
+    gv = 0.f;
+    if (C3) {
+        const float4 t0 = __ldg(p.tex4 + tf.idx[0]), t1 = __ldg(p.tex4 + tf.idx[1]);
+        const float4 t2 = __ldg(p.tex4 + tf.idx[2]), t3 = __ldg(p.tex4 + tf.idx[3]);
+        const float val0 = tf.w[0] * t0.x + tf.w[1] * t1.x + tf.w[2] * t2.x + tf.w[3] * t3.x;
+        const float val1 = tf.w[0] * t0.y + tf.w[1] * t1.y + tf.w[2] * t2.y + tf.w[3] * t3.y;
+        const float val2 = tf.w[0] * t0.z + tf.w[1] * t1.z + tf.w[2] * t2.z + tf.w[3] * t3.z;
+        v_vis += val0 * px.vt0 + val1 * px.vt1 + val2 * px.vt2;
+        if (fl.want_uv) {
+            const float ofu = 1.f - tf.fu, ofv = 1.f - tf.fv;
+            const float gu0 = -ofv * t0.x - tf.fv * t1.x + ofv * t2.x + tf.fv * t3.x;
+            const float gu1 = -ofv * t0.y - tf.fv * t1.y + ofv * t2.y + tf.fv * t3.y;
+            const float gu2 = -ofv * t0.z - tf.fv * t1.z + ofv * t2.z + tf.fv * t3.z;
+            const float gv0 = -ofu * t0.x + ofu * t1.x - tf.fu * t2.x + tf.fu * t3.x;
+            const float gv1 = -ofu * t0.y + ofu * t1.y - tf.fu * t2.y + tf.fu * t3.y;
+            const float gv2 = -ofu * t0.z + ofu * t1.z - tf.fu * t2.z + tf.fu * t3.z;
+            gu = (float)tf.h * (px.vt0 * gu0 + px.vt1 * gu1 + px.vt2 * gu2);
+            gv = (float)tf.wd * (px.vt0 * gv0 + px.vt1 * gv1 + px.vt2 * gv2);
+        }
+    } else {
+        const float *__restrict__ tx = p.tex;
+        const float *__restrict__ vtp = in.v_tex + (size_t)fl.C * px.pix;
+        for (int c = 0; c < fl.C; ++c) {
+            const float c00 = __ldg(tx + (size_t)tf.idx[0] * fl.C + c), c01 = __ldg(tx + (size_t)tf.idx[1] * fl.C + c);
+            const float c10 = __ldg(tx + (size_t)tf.idx[2] * fl.C + c), c11 = __ldg(tx + (size_t)tf.idx[3] * fl.C + c);
+            const float vtc = vtp[c];
+            v_vis += (tf.w[0] * c00 + tf.w[1] * c01 + tf.w[2] * c10 + tf.w[3] * c11) * vtc;
+            if (fl.want_uv) {
+                gu += (float)tf.h * (vtc * (-(1.f - tf.fv) * c00 - tf.fv * c01 + (1.f - tf.fv) * c10 + tf.fv * c11));
+                gv += (float)tf.wd * (vtc * (-(1.f - tf.fu) * c00 + (1.f - tf.fu) * c01 - tf.fu * c10 + tf.fu * c11));
+            }
+        }
+    }
+    const float t_view = pe.t * qc.vdep;
+    const float tv = fl.use_ndc ? (T_FAR * t_view - T_FAR * T_NEAR) / ((T_FAR - T_NEAR) * t_view) : pe.t;
+    y = v_vis + (tv * tv * px.Sf0 - 2.f * tv * px.Sf1 + px.Sf2) * px.v_reg;
+}
+
+// Second half: given vis = alpha T_k and v_alpha, the texel-gradient reductions and the moment row (AccSlot order,
+// quad by quad; r[7] only with BLUR).
+template <bool C3, bool BLUR>
+__device__ __forceinline__ void pair_rows(const RasterCommon &p, const BackwardIn &in, const BackwardOut &o,
+                                          const PairFlags &fl, const float4 q0, const float4 q3, const float4 q4,
+                                          const float4 q5, const float4 q6, const PairEval &pe, const PixelConsts &qc,
+                                          const PixelShare &px, float vis, float v_alpha, float gu, float gv,
+                                          bool is_median, float4 (&r)[8]) {
+    const float v_u = vis * gu, v_v = vis * gv;
+    const float nu = fmaf(q4.x, pe.ex, fmaf(q4.y, pe.ey, q4.z));
+    const float nv = fmaf(q5.x, pe.ex, fmaf(q5.y, pe.ey, q5.z));
+    const float du = nu * pe.rD, dv = nv * pe.rD;
+    {  // texel gradients: one vector reduction per bilinear corner (texture_helpers.cuh:257-260)
+        const float u = clamp01(fmaf(nu, pe.rD, q4.w)), v = clamp01(fmaf(nv, pe.rD, q5.w));
+        TexFetch tf;
+        texel_setup(__float_as_int(q3.z), __float_as_int(q3.w), __float_as_int(q6.w), u, v, fl.bilinear, tf);
+        if (C3) {
+            const float vv0 = vis * px.vt0, vv1 = vis * px.vt1, vv2 = vis * px.vt2;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#ifdef GSTEX_EXP_NO_TEXRED
+                if (tf.w[k] == 12345.f)
+#else
+                if (tf.w[k] != 0.f)
+#endif
+                    atomicAdd(o.vtex4 + tf.idx[k], make_float4(tf.w[k] * vv0, tf.w[k] * vv1, tf.w[k] * vv2, 0.f));
+        } else {
+            const float *__restrict__ vtp = in.v_tex + (size_t)fl.C * px.pix;
+            for (int c = 0; c < fl.C; ++c) {
+                const float vv = vis * vtp[c];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (tf.w[k] != 0.f) atomicAdd(o.vtex + (size_t)tf.idx[k] * fl.C + c, tf.w[k] * vv);
+            }
+        }
+    }
+    // depth / distortion terms through t (reference texture.cu:655-682)
+    const float t_view = pe.t * qc.vdep;
+    const float tv = fl.use_ndc ? (T_FAR * t_view - T_FAR * T_NEAR) / ((T_FAR - T_NEAR) * t_view) : pe.t;
+    const float v_tv = 2.f * (vis * tv * px.Sf0 - vis * px.Sf1) * px.v_reg;
+    float v_t = fl.use_ndc ? 0.f : v_tv;
+    float v_tview = is_median ? px.v_dep : 0.f;  // texture.cu:678-680
+    if (fl.use_ndc) v_tview += (T_FAR * T_NEAR) / ((T_FAR - T_NEAR) * t_view * t_view) * v_tv;
+    v_t += qc.vdep * v_tview;
+    const float v_s = v_t * qc.rn;
+    // alpha = min(.99, opac * f): the cap is not masked (reference texture.cu:672, :707)
+    const float v_q = pe.blur ? 0.f : -LN2_F * q0.w * pe.e * v_alpha;
+    const float v_l1 = 2.f * pe.l1 * v_q, v_l2 = 2.f * pe.l2 * v_q;
+    const float gN1 = v_l1 * pe.rD, gN2 = v_l2 * pe.rD, gNu = v_u * pe.rD, gNv = v_v * pe.rD;
+    const float gD = -(v_l1 * pe.l1 + v_l2 * pe.l2 + v_s * pe.s + v_u * du + v_v * dv) * pe.rD;
+    r[0] = make_float4(gN1 * pe.ex, gN1 * pe.ey, gN1, v_s * pe.rD);
+    r[1] = make_float4(gN2 * pe.ex, gN2 * pe.ey, gN2, pe.f * v_alpha);
+    r[2] = make_float4(gD * pe.ex, gD * pe.ey, gD, 0.f);
+    r[3] = make_float4(gNu * pe.ex, gNu * pe.ey, gNu, v_u);
+    r[4] = make_float4(gNv * pe.ex, gNv * pe.ey, gNv, v_v);
+    r[5] = make_float4(vis * px.vi0, vis * px.vi1, vis * px.vi2, 0.f);
+    r[6] = make_float4(vis * px.vn0, vis * px.vn1, vis * px.vn2, 0.f);
+    r[7] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (BLUR) {
+        if (pe.blur) {  // reference texture.cu:683-692
+            const float v_sb = -q0.w * pe.f * v_alpha;
+            r[7].x = 2.0f * v_sb * pe.bx;
+            r[7].y = 2.0f * v_sb * pe.by;
+        }
+    }
+}
+
+// Sum 8 float4 quads held per lane over the warp: recursive halving, 36 shuffles; every lane returns the total of
+// quad (lane >> 2).
+__device__ __forceinline__ float4 warp_reduce_quads(const float4 (&r)[8], int lane) {
+    const unsigned full = 0xffffffffu;
+    float a[32];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        a[4 * k] = r[k].x; a[4 * k + 1] = r[k].y; a[4 * k + 2] = r[k].z; a[4 * k + 3] = r[k].w;
+    }
+    {
+        const bool hi = (lane & 16) != 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float send = hi ? a[i] : a[i + 16];
+            const float keep = hi ? a[i + 16] : a[i];
+            a[i] = keep + __shfl_xor_sync(full, send, 16);
+        }
+    }
+    {
+        const bool hi = (lane & 8) != 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float send = hi ? a[i] : a[i + 8];
+            const float keep = hi ? a[i + 8] : a[i];
+            a[i] = keep + __shfl_xor_sync(full, send, 8);
+        }
+    }
+    {
+        const bool hi = (lane & 4) != 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float send = hi ? a[i] : a[i + 4];
+            const float keep = hi ? a[i + 4] : a[i];
+            a[i] = keep + __shfl_xor_sync(full, send, 4);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        a[i] += __shfl_xor_sync(full, a[i], 2);
+        a[i] += __shfl_xor_sync(full, a[i], 1);
+    }
+    return make_float4(a[0], a[1], a[2], a[3]);
+}
 
 template <bool C3, bool BLUR>
 __global__ void __launch_bounds__(RASTER_MAX_THREADS, 3) raster_backward_kernel(const RasterCommon p, const BackwardIn in,
@@ -77,10 +252,11 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, 3) raster_backward_kernel(
     const int col = blockIdx.x * p.bw + lx, row = blockIdx.y * p.bw + ly;
     const bool inside = (tr < p.bw * p.bw) && col < p.img_w && row < p.img_h;
     const PixelConsts pc = make_pixel(col, row, p.c2w, p.viewmat, p.fx, p.fy, p.cx, p.cy);
-    const bool use_ndc = (p.settings & GSTEX_SET_NDC) != 0;
-    const bool bilinear = !(p.settings & GSTEX_SET_NEAREST);
-    const bool prop_uv = (p.settings & GSTEX_SET_PROPAGATE_UV) != 0;
-    const int C = C3 ? 3 : p.channels;
+    PairFlags fl;
+    fl.use_ndc = (p.settings & GSTEX_SET_NDC) != 0;
+    fl.bilinear = !(p.settings & GSTEX_SET_NEAREST);
+    fl.want_uv = fl.bilinear && (p.settings & GSTEX_SET_PROPAGATE_UV) != 0;
+    fl.C = C3 ? 3 : p.channels;
     constexpr int NCOL2 = BLUR ? 15 : 14;  // float2 column pairs of a moment row
 
     PixelShare me;
@@ -106,6 +282,20 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, 3) raster_backward_kernel(
     }
     float v_T_run = p.background[0] * me.vi0 + p.background[1] * me.vi1 + p.background[2] * me.vi2 - in.v_alpha[me.pix];
 
+    // values of pixel lane `pl`, fetched by a pair lane (all 32 lanes must call this together)
+    auto fetch_pixel = [&](int pl, PixelConsts &qc, PixelShare &px) {
+        qc.px = __shfl_sync(full, pc.px, pl); qc.py = __shfl_sync(full, pc.py, pl);
+        qc.rn = __shfl_sync(full, pc.rn, pl); qc.vdep = __shfl_sync(full, pc.vdep, pl);
+        qc.eps = __shfl_sync(full, pc.eps, pl);
+        px.vi0 = __shfl_sync(full, me.vi0, pl); px.vi1 = __shfl_sync(full, me.vi1, pl); px.vi2 = __shfl_sync(full, me.vi2, pl);
+        px.vn0 = __shfl_sync(full, me.vn0, pl); px.vn1 = __shfl_sync(full, me.vn1, pl); px.vn2 = __shfl_sync(full, me.vn2, pl);
+        px.vt0 = __shfl_sync(full, me.vt0, pl); px.vt1 = __shfl_sync(full, me.vt1, pl); px.vt2 = __shfl_sync(full, me.vt2, pl);
+        px.Sf0 = __shfl_sync(full, me.Sf0, pl); px.Sf1 = __shfl_sync(full, me.Sf1, pl); px.Sf2 = __shfl_sync(full, me.Sf2, pl);
+        px.v_reg = __shfl_sync(full, me.v_reg, pl); px.v_dep = __shfl_sync(full, me.v_dep, pl);
+        px.dfinal = __shfl_sync(full, me.dfinal, pl);
+        px.pix = C3 ? 0 : __shfl_sync(full, me.pix, pl);
+    };
+
     for (int b = 0; b < nbatch; ++b) {
         // batch b covers [first, first + cnt) counted from the back of [range.x, hi)
         const int first = max(range.x, hi - (b + 1) * BWD_BATCH), cnt = (hi - b * BWD_BATCH) - first;
@@ -128,22 +318,41 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, 3) raster_backward_kernel(
 
         int si = nsurv - 1;
         while (si >= 0) {
-            // ---------------- build one chunk of pairs: entries si0, si0-1, ... while they fit ----------------
+            // ---------------- build one chunk: entries si0, si0-1, ... while they fit ----------------
+            // lane j looks at entry si0 - j.  Entries that cover >= BWD_FULL pixels of the patch are handled
+            // lane = pixel inside the scan below; the pairs of the sparser ones are queued for the dense stages.
+            // (A pixel takes part in an entry iff its bit is set in the forward pass's mask.)
             const int si0 = si;
-            int np = 0;
-            while (si >= 0 && si0 - si < BWD_ECAP) {
-                const bool mine = ((W.sv_mask[si] >> lane) & 1u) && (first + (int)W.sv_r[si]) <= bfinal;
-                const unsigned m = __ballot_sync(full, mine);
+            int ne, np;
+            {
+                const bool cand = lane < BWD_ECAP && si0 - lane >= 0;
+                const unsigned m = cand ? W.sv_mask[si0 - lane] : 0u;
                 const int c = __popc(m);
-                if (np + c > BWD_QCAP) break;
-                if (mine) W.q_ent[np + __popc(m & lt)] = (uint16_t)((si0 - si) | (lane << 8));
-                if (lane == 0) W.sv_mask[si] = m;  // from here on: the pixels that really take part
-                np += c;
-                --si;
+                const bool sparse = c < BWD_FULL;
+                const int cs = sparse ? c : 0;
+                int incl = cs;  // inclusive prefix sum of the queued pairs over the entries
+#pragma unroll
+                for (int o = 1; o < BWD_ECAP; o <<= 1) {
+                    const int t = __shfl_up_sync(full, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                ne = __popc(__ballot_sync(full, cand && incl <= BWD_QCAP));  // a prefix: incl is non-decreasing
+                np = __shfl_sync(full, incl, ne - 1);
+                const int off = incl - cs;
+                if (lane < ne) W.ch_off[lane] = (uint16_t)off;
+                unsigned mm = (lane < ne && sparse) ? m : 0u;
+                int slot = off;
+                while (__any_sync(full, mm != 0u)) {
+                    if (mm) {
+                        const int l = __ffs(mm) - 1;
+                        mm &= mm - 1;
+                        W.q_ent[slot++] = (uint16_t)(lane | (l << 8));
+                    }
+                }
+                si = si0 - ne;
             }
             // stage the records of the chunk's entries: 8 lanes fetch one 128-byte record
             {
-                const int ne = si0 - si;
                 for (int t = lane; t < ne * 8; t += 32) {
                     const int j = t >> 3, q = t & 7;
                     __pipeline_memcpy_async(W.rec + quad_slot(j, q), p.recs + (size_t)W.sv_gid[si0 - j] * 8 + q, 16);
@@ -159,17 +368,9 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, 3) raster_backward_kernel(
                 const int e = it * 32 + lane;
                 const bool act = e < np;
                 const int ent = act ? (int)W.q_ent[e] : (lane << 8);
-                const int pl = ent >> 8;
                 PixelConsts qc;
-                qc.px = __shfl_sync(full, pc.px, pl); qc.py = __shfl_sync(full, pc.py, pl);
-                qc.rn = __shfl_sync(full, pc.rn, pl); qc.vdep = __shfl_sync(full, pc.vdep, pl);
-                qc.eps = __shfl_sync(full, pc.eps, pl);
-                const float vi0 = __shfl_sync(full, me.vi0, pl), vi1 = __shfl_sync(full, me.vi1, pl), vi2 = __shfl_sync(full, me.vi2, pl);
-                const float vn0 = __shfl_sync(full, me.vn0, pl), vn1 = __shfl_sync(full, me.vn1, pl), vn2 = __shfl_sync(full, me.vn2, pl);
-                const float vt0 = __shfl_sync(full, me.vt0, pl), vt1 = __shfl_sync(full, me.vt1, pl), vt2 = __shfl_sync(full, me.vt2, pl);
-                const float Sf0 = __shfl_sync(full, me.Sf0, pl), Sf1 = __shfl_sync(full, me.Sf1, pl), Sf2 = __shfl_sync(full, me.Sf2, pl);
-                const float v_reg = __shfl_sync(full, me.v_reg, pl);
-                const int ppix = C3 ? 0 : __shfl_sync(full, me.pix, pl);
+                PixelShare px;
+                fetch_pixel(ent >> 8, qc, px);
                 if (act) {
                     const int j = ent & 0xff;
                     const int sw = j & 7;
@@ -178,73 +379,60 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, 3) raster_backward_kernel(
                     const float4 q4 = R[4 ^ sw], q5 = R[5 ^ sw], q6 = R[6 ^ sw], q7 = R[7 ^ sw];
                     PairEval pe;
                     eval_pair<BLUR>(q0, q1, q2, q3, qc, p.mean2d, pe);
-                    float v_vis = q6.x * vi0 + q6.y * vi1 + q6.z * vi2 + q7.x * vn0 + q7.y * vn1 + q7.z * vn2;
-                    // texture fetch (reference texture.cu:594-642, texture_helpers.cuh:252-300)
-                    const float nu = fmaf(q4.x, pe.ex, fmaf(q4.y, pe.ey, q4.z));
-                    const float nv = fmaf(q5.x, pe.ex, fmaf(q5.y, pe.ey, q5.z));
-                    const float u = clamp01(fmaf(nu, pe.rD, q4.w)), v = clamp01(fmaf(nv, pe.rD, q5.w));
-                    TexFetch tf;
-                    texel_setup(__float_as_int(q3.z), __float_as_int(q3.w), __float_as_int(q6.w), u, v, bilinear, tf);
-                    float gu = 0.f, gv = 0.f;
-                    const bool want_uv = bilinear && prop_uv;
-                    if (C3) {
-                        const float4 t0 = __ldg(p.tex4 + tf.idx[0]), t1 = __ldg(p.tex4 + tf.idx[1]);
-                        const float4 t2 = __ldg(p.tex4 + tf.idx[2]), t3 = __ldg(p.tex4 + tf.idx[3]);
-                        const float val0 = tf.w[0] * t0.x + tf.w[1] * t1.x + tf.w[2] * t2.x + tf.w[3] * t3.x;
-                        const float val1 = tf.w[0] * t0.y + tf.w[1] * t1.y + tf.w[2] * t2.y + tf.w[3] * t3.y;
-                        const float val2 = tf.w[0] * t0.z + tf.w[1] * t1.z + tf.w[2] * t2.z + tf.w[3] * t3.z;
-                        v_vis += val0 * vt0 + val1 * vt1 + val2 * vt2;
-                        if (want_uv) {
-                            const float ofu = 1.f - tf.fu, ofv = 1.f - tf.fv;
-                            const float gu0 = -ofv * t0.x - tf.fv * t1.x + ofv * t2.x + tf.fv * t3.x;
-                            const float gu1 = -ofv * t0.y - tf.fv * t1.y + ofv * t2.y + tf.fv * t3.y;
-                            const float gu2 = -ofv * t0.z - tf.fv * t1.z + ofv * t2.z + tf.fv * t3.z;
-                            const float gv0 = -ofu * t0.x + ofu * t1.x - tf.fu * t2.x + tf.fu * t3.x;
-                            const float gv1 = -ofu * t0.y + ofu * t1.y - tf.fu * t2.y + tf.fu * t3.y;
-                            const float gv2 = -ofu * t0.z + ofu * t1.z - tf.fu * t2.z + tf.fu * t3.z;
-                            gu = (float)tf.h * (vt0 * gu0 + vt1 * gu1 + vt2 * gu2);
-                            gv = (float)tf.wd * (vt0 * gv0 + vt1 * gv1 + vt2 * gv2);
-                        }
-                    } else {
-                        const float *__restrict__ tx = p.tex;
-                        const float *__restrict__ vtp = in.v_tex + (size_t)C * ppix;
-                        for (int c = 0; c < C; ++c) {
-                            const float c00 = __ldg(tx + (size_t)tf.idx[0] * C + c), c01 = __ldg(tx + (size_t)tf.idx[1] * C + c);
-                            const float c10 = __ldg(tx + (size_t)tf.idx[2] * C + c), c11 = __ldg(tx + (size_t)tf.idx[3] * C + c);
-                            const float vtc = vtp[c];
-                            v_vis += (tf.w[0] * c00 + tf.w[1] * c01 + tf.w[2] * c10 + tf.w[3] * c11) * vtc;
-                            if (want_uv) {
-                                gu += (float)tf.h * (vtc * (-(1.f - tf.fv) * c00 - tf.fv * c01 + (1.f - tf.fv) * c10 + tf.fv * c11));
-                                gv += (float)tf.wd * (vtc * (-(1.f - tf.fu) * c00 + (1.f - tf.fu) * c01 - tf.fu * c10 + tf.fu * c11));
-                            }
-                        }
-                    }
-                    // distortion: d(reg)/d(weight) with the FINAL sums (helpers.cuh:266-269)
-                    const float t_view = pe.t * qc.vdep;
-                    const float tv = use_ndc ? (T_FAR * t_view - T_FAR * T_NEAR) / ((T_FAR - T_NEAR) * t_view) : pe.t;
-                    const float v_w = (tv * tv * Sf0 - 2.f * tv * Sf1 + Sf2) * v_reg;
+                    float y, gu, gv;
+                    pair_terms<C3>(p, in, fl, q3, q4, q5, q6, q7, pe, qc, px, y, gu, gv);
                     W.e_a[e] = pe.alpha;
-                    W.e_y[e] = v_vis + v_w;
+                    W.e_y[e] = y;
                     W.e_gu[e] = gu;
                     W.e_gv[e] = gv;
                 }
             }
             __syncwarp();
 
-            // ---------------- scan: lane = pixel, its pairs in list order (back to front) ----------------
+            // ---------------- scan: lane = pixel, entries in list order (back to front) ----------------
             {
-                int off = 0;
-                for (int s = si0; s > si; --s) {
+                for (int jj = 0; jj < ne; ++jj) {
+                    const int s = si0 - jj;
                     const unsigned m = W.sv_mask[s];
-                    if ((m >> lane) & 1u) {
-                        const int e = off + __popc(m & lt);
-                        const float alpha = W.e_a[e], y = W.e_y[e];
-                        T *= 1.f / (1.f - alpha);  // transmittance in front of the entry (reference texture.cu:579-580)
-                        W.e_a[e] = alpha * T;
-                        W.e_y[e] = T * (y - v_T_run);                       // v_alpha (texture.cu:650, :667)
-                        v_T_run = alpha * y + (1.f - alpha) * v_T_run;      // texture.cu:651, :668-670
+                    const int c = __popc(m);
+                    const bool mine = (m >> lane) & 1u;
+                    if (c >= BWD_FULL) {
+                        // a Gaussian that covers most of the patch: the whole gradient path right here, lane = pixel,
+                        // record read by broadcast, moments reduced with the shuffle butterfly
+                        const int sw = jj & 7;
+                        const float4 *__restrict__ R = W.rec + (jj << 3);
+                        const float4 q0 = R[sw], q1 = R[1 ^ sw], q2 = R[2 ^ sw], q3 = R[3 ^ sw];
+                        float4 r[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) r[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (mine) {
+                            const float4 q4 = R[4 ^ sw], q5 = R[5 ^ sw], q6 = R[6 ^ sw], q7 = R[7 ^ sw];
+                            PairEval pe;
+                            eval_pair<BLUR>(q0, q1, q2, q3, pc, p.mean2d, pe);
+                            float y, gu, gv;
+                            pair_terms<C3>(p, in, fl, q3, q4, q5, q6, q7, pe, pc, me, y, gu, gv);
+                            const float alpha = pe.alpha;
+                            T *= fast_rcp(1.f - alpha);
+                            const float d = y - v_T_run;
+                            const float v_alpha = T * d;
+                            v_T_run = fmaf(alpha, d, v_T_run);
+                            const int idx = first + (int)W.sv_r[s];
+                            pair_rows<C3, BLUR>(p, in, o, fl, q0, q3, q4, q5, q6, pe, pc, me, alpha * T, v_alpha, gu, gv,
+                                                idx == me.dfinal && me.dfinal != -1, r);
+                        }
+                        const float4 tot = warp_reduce_quads(r, lane);
+                        if ((lane & 3) == 0 && (BLUR || lane < 28))
+                            atomicAdd(o.acc + (size_t)__float_as_int(q2.w) * 8 + (lane >> 2), tot);
+                    } else {
+                        if (mine) {
+                            const int e = (int)W.ch_off[jj] + __popc(m & lt);
+                            const float alpha = W.e_a[e], d = W.e_y[e] - v_T_run;
+                            T *= fast_rcp(1.f - alpha);  // transmittance in front of the entry (texture.cu:579-580)
+                            W.e_a[e] = alpha * T;
+                            W.e_y[e] = T * d;                        // v_alpha (texture.cu:650, :667)
+                            v_T_run = fmaf(alpha, d, v_T_run);       // alpha y + (1 - alpha) R  (texture.cu:651, :668-670)
+                        }
                     }
-                    off += __popc(m);
                 }
             }
             __syncwarp();
@@ -254,87 +442,25 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, 3) raster_backward_kernel(
                 const int e = it * 32 + lane;
                 const bool act = e < np;
                 const int ent = act ? (int)W.q_ent[e] : (lane << 8);
-                const int pl = ent >> 8;
                 PixelConsts qc;
-                qc.px = __shfl_sync(full, pc.px, pl); qc.py = __shfl_sync(full, pc.py, pl);
-                qc.rn = __shfl_sync(full, pc.rn, pl); qc.vdep = __shfl_sync(full, pc.vdep, pl);
-                qc.eps = __shfl_sync(full, pc.eps, pl);
-                const float vi0 = __shfl_sync(full, me.vi0, pl), vi1 = __shfl_sync(full, me.vi1, pl), vi2 = __shfl_sync(full, me.vi2, pl);
-                const float vn0 = __shfl_sync(full, me.vn0, pl), vn1 = __shfl_sync(full, me.vn1, pl), vn2 = __shfl_sync(full, me.vn2, pl);
-                const float vt0 = __shfl_sync(full, me.vt0, pl), vt1 = __shfl_sync(full, me.vt1, pl), vt2 = __shfl_sync(full, me.vt2, pl);
-                const float Sf0 = __shfl_sync(full, me.Sf0, pl), Sf1 = __shfl_sync(full, me.Sf1, pl);
-                const float v_reg = __shfl_sync(full, me.v_reg, pl), v_dep = __shfl_sync(full, me.v_dep, pl);
-                const int dfinal = __shfl_sync(full, me.dfinal, pl);
-                const int ppix = C3 ? 0 : __shfl_sync(full, me.pix, pl);
+                PixelShare px;
+                fetch_pixel(ent >> 8, qc, px);
                 const int jloc = act ? (ent & 0xff) : -1 - lane;
-                int gid = 0;
                 if (act) {
                     const int sw = jloc & 7;
                     const float4 *__restrict__ R = W.rec + (jloc << 3);
                     const float4 q0 = R[sw], q1 = R[1 ^ sw], q2 = R[2 ^ sw], q3 = R[3 ^ sw];
                     const float4 q4 = R[4 ^ sw], q5 = R[5 ^ sw], q6 = R[6 ^ sw];
-                    gid = __float_as_int(q2.w);
                     PairEval pe;
                     eval_pair<BLUR>(q0, q1, q2, q3, qc, p.mean2d, pe);
-                    const float vis = W.e_a[e], v_alpha = W.e_y[e];
-                    const float v_u = vis * W.e_gu[e], v_v = vis * W.e_gv[e];
-                    const float nu = fmaf(q4.x, pe.ex, fmaf(q4.y, pe.ey, q4.z));
-                    const float nv = fmaf(q5.x, pe.ex, fmaf(q5.y, pe.ey, q5.z));
-                    const float du = nu * pe.rD, dv = nv * pe.rD;
-                    // texel gradients: one vector reduction per bilinear corner (texture_helpers.cuh:257-260)
-                    {
-                        const float u = clamp01(fmaf(nu, pe.rD, q4.w)), v = clamp01(fmaf(nv, pe.rD, q5.w));
-                        TexFetch tf;
-                        texel_setup(__float_as_int(q3.z), __float_as_int(q3.w), __float_as_int(q6.w), u, v, bilinear, tf);
-                        if (C3) {
-                            const float vv0 = vis * vt0, vv1 = vis * vt1, vv2 = vis * vt2;
-#pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                if (tf.w[k] != 0.f)
-                                    atomicAdd(o.vtex4 + tf.idx[k], make_float4(tf.w[k] * vv0, tf.w[k] * vv1, tf.w[k] * vv2, 0.f));
-                        } else {
-                            const float *__restrict__ vtp = in.v_tex + (size_t)C * ppix;
-                            for (int c = 0; c < C; ++c) {
-                                const float vv = vis * vtp[c];
-#pragma unroll
-                                for (int k = 0; k < 4; ++k)
-                                    if (tf.w[k] != 0.f) atomicAdd(o.vtex + (size_t)tf.idx[k] * C + c, tf.w[k] * vv);
-                            }
-                        }
-                    }
-                    // depth / distortion terms through t (reference texture.cu:655-682)
-                    const float t_view = pe.t * qc.vdep;
-                    const float tv = use_ndc ? (T_FAR * t_view - T_FAR * T_NEAR) / ((T_FAR - T_NEAR) * t_view) : pe.t;
-                    const float v_tv = 2.f * (vis * tv * Sf0 - vis * Sf1) * v_reg;
-                    float v_t = use_ndc ? 0.f : v_tv;
                     const int idx = first + (int)W.sv_r[si0 - jloc];
-                    float v_tview = (idx == dfinal && dfinal != -1) ? v_dep : 0.f;  // texture.cu:678-680
-                    if (use_ndc) v_tview += (T_FAR * T_NEAR) / ((T_FAR - T_NEAR) * t_view * t_view) * v_tv;
-                    v_t += qc.vdep * v_tview;
-                    const float v_s = v_t * qc.rn;
-                    // alpha = min(.99, opac * f): the cap is not masked (reference texture.cu:672, :707)
-                    const float v_q = pe.blur ? 0.f : -LN2_F * q0.w * pe.e * v_alpha;
-                    const float v_l1 = 2.f * pe.l1 * v_q, v_l2 = 2.f * pe.l2 * v_q;
-                    const float gN1 = v_l1 * pe.rD, gN2 = v_l2 * pe.rD, gNu = v_u * pe.rD, gNv = v_v * pe.rD;
-                    const float gD = -(v_l1 * pe.l1 + v_l2 * pe.l2 + v_s * pe.s + v_u * du + v_v * dv) * pe.rD;
-                    float4 *__restrict__ rowp = reinterpret_cast<float4 *>(W.rows + lane * PITCH);  // AccSlot order
-                    rowp[0] = make_float4(gN1 * pe.ex, gN1 * pe.ey, gN1, v_s * pe.rD);
-                    rowp[1] = make_float4(gN2 * pe.ex, gN2 * pe.ey, gN2, pe.f * v_alpha);
-                    rowp[2] = make_float4(gD * pe.ex, gD * pe.ey, gD, 0.f);
-                    rowp[3] = make_float4(gNu * pe.ex, gNu * pe.ey, gNu, v_u);
-                    rowp[4] = make_float4(gNv * pe.ex, gNv * pe.ey, gNv, v_v);
-                    rowp[5] = make_float4(vis * vi0, vis * vi1, vis * vi2, 0.f);
-                    rowp[6] = make_float4(vis * vn0, vis * vn1, vis * vn2, 0.f);
-                    if (BLUR) {
-                        float mx = 0.f, my = 0.f;
-                        if (pe.blur) {  // reference texture.cu:683-692
-                            const float v_sb = -q0.w * pe.f * v_alpha;
-                            mx = 2.0f * v_sb * pe.bx;
-                            my = 2.0f * v_sb * pe.by;
-                        }
-                        rowp[7] = make_float4(mx, my, 0.f, 0.f);
-                    }
-                    W.row_gid[lane] = gid;
+                    float4 r[8];
+                    pair_rows<C3, BLUR>(p, in, o, fl, q0, q3, q4, q5, q6, pe, qc, px, W.e_a[e], W.e_y[e], W.e_gu[e],
+                                        W.e_gv[e], idx == px.dfinal && px.dfinal != -1, r);
+                    float4 *__restrict__ rowp = reinterpret_cast<float4 *>(W.rows + lane * PITCH);
+#pragma unroll
+                    for (int k = 0; k < (BLUR ? 8 : 7); ++k) rowp[k] = r[k];
+                    W.row_gid[lane] = __float_as_int(q2.w);
                 }
                 // rows of one Gaussian are contiguous: segment starts where the chunk-local entry changes
                 const int jprev = __shfl_up_sync(full, jloc, 1);
