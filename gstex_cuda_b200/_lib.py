@@ -43,6 +43,9 @@ _PROTOS = {
                               + [c_i] + [c_fp] * 10 + [c_fp, c_sz, c_fp]),
     "gstex_texture_backward": (c_i, [c_i, c_i, c_i, c_i, c_i64, c_i, c_i64] + [c_fp] * 7 + [c_f] + [c_fp] * 7 + [c_f] * 4
                                + [c_i] + [c_fp] * 11 + [c_fp] * 9 + [c_i, c_fp, c_fp, c_sz, c_fp]),
+    "gstex_texture_edit_temp_bytes": (c_sz, [c_i]),
+    "gstex_texture_edit": (c_i, [c_i, c_i, c_i, c_i, c_i64, c_i] + [c_fp] * 10 + [c_f] + [c_fp] * 6 + [c_f] * 4 + [c_i]
+                           + [c_fp, c_fp, c_sz, c_fp]),
     "gstex_sh_forward": (c_i, [c_i, c_i, c_i, c_fp, c_fp, c_fp, c_fp]),
     "gstex_sh_backward": (c_i, [c_i, c_i, c_i, c_fp, c_fp, c_fp, c_i, c_fp]),
     "gstex_texture_sample_forward": (c_i, [c_i, c_i, c_fp, c_fp, c_fp, c_fp, c_fp]),
@@ -56,6 +59,11 @@ _PROTOS = {
     "gstex_raster_epilogue": (c_i, [c_i, c_fp, c_fp, c_f] + [c_fp] * 5 + [c_f] * 4 + [c_fp] * 9 + [c_i, c_fp]),
     "gstex_sh_colors_forward": (c_i, [c_i, c_i, c_i] + [c_fp] * 5 + [c_fp]),
     "gstex_sh_colors_backward": (c_i, [c_i, c_i, c_i] + [c_fp] * 5 + [c_i, c_fp]),
+    "gstex_preprocess_forward": (c_i, [c_i] + [c_fp] * 12 + [c_fp]),
+    "gstex_preprocess_backward": (c_i, [c_i] + [c_fp] * 17 + [c_fp]),
+    "gstex_sigmoid_pad_texture": (c_i, [c_i64, c_fp, c_fp, c_fp]),
+    "gstex_unpad_texture_grad_sigmoid": (c_i, [c_i64, c_fp, c_fp, c_fp, c_i, c_fp]),
+    "gstex_adam_step": (c_i, [c_i64, c_fp, c_fp, c_fp, c_fp] + [C.c_double] * 4 + [c_i, c_f, c_fp]),
 }
 
 # entry points that may be absent from an older build of the library (checked lazily)

@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(CSRC, "_build")
 LIB = os.path.join(HERE, "libgstex_b200.so")
 SOURCES = ["util.cu", "project.cu", "binning.cu", "binning_tiles.cu", "pack.cu", "raster_forward.cu", "raster_backward.cu", "sh.cu",
-           "texture_sample.cu", "loss.cu", "pipeline.cu"]
+           "texture_sample.cu", "texture_edit.cu", "train_ops.cu", "loss.cu", "pipeline.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xptxas", "-v", "--expt-relaxed-constexpr"]
 

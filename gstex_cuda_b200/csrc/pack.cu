@@ -97,7 +97,9 @@ __global__ void __launch_bounds__(256) pack_kernel(int n, const float *__restric
                        __int_as_float(texture_dims[3 * g + 1]));
     r[4] = make_float4(hu.x * ifx, hu.y * ify, cu, t0.x);
     r[5] = make_float4(hv.x * ifx, hv.y * ify, cv, t0.y);
-    r[6] = make_float4(colors[3 * g], colors[3 * g + 1], colors[3 * g + 2], __int_as_float(texture_dims[3 * g + 2]));
+    // colours are optional: texture_edit walks the same records without them
+    const Vec3 col = colors ? ld3(colors + 3 * g) : mk3(0.f, 0.f, 0.f);
+    r[6] = make_float4(col.x, col.y, col.z, __int_as_float(texture_dims[3 * g + 2]));
     r[7] = make_float4(f.a3.x, f.a3.y, f.a3.z, 0.f);
     mean2d[g] = pinhole(fx, fy, cx, cy, xform_point(cam.vm, mean));
 }

@@ -255,5 +255,35 @@ def texture_sample_backward(texture_info, texture_dims, uvs, texture, v_output):
     return v_texture
 
 
-def texture_edit(*args, **kwargs):
-    raise NotImplementedError("texture_edit is an editing tool outside the training hot path (SURVEY 2.1 #7, 8f rank 2)")
+def texture_edit(tile_bounds, block, img_size, texture_info, texture_total_size, texture_dims, updated_img,
+                 updated_alpha, depth_lower, depth_upper, gaussian_ids_sorted, tile_bins, opacities, means, scales,
+                 glob_scale, quats, uv0, umap, vmap, viewmat, c2w, fx, fy, cx, cy, settings, background):
+    """texture_edit_tensor, texture_edit.cu:238-354: returns updated_texture (texture_total_size, texture_info[2]),
+    zero-initialised, channels 0-4 = (r*a, g*a, b*a, a, weight) splatted with the bilinear texel weights.
+    ``settings``: bit 0 = blur, bit 1 = ndc (texture_edit.cu:46-47).  ``background`` is unused, as upstream."""
+    _chk("texture_dims", texture_dims, torch.int32)
+    _chk("gaussian_ids_sorted", gaussian_ids_sorted, torch.int32), _chk("tile_bins", tile_bins, torch.int32)
+    for n_, t in (("updated_img", updated_img), ("updated_alpha", updated_alpha), ("depth_lower", depth_lower),
+                  ("depth_upper", depth_upper), ("opacities", opacities), ("means", means), ("scales", scales),
+                  ("quats", quats), ("uv0", uv0), ("umap", umap), ("vmap", vmap), ("viewmat", viewmat), ("c2w", c2w)):
+        _chk(n_, t, torch.float32)
+    if background is not None:
+        _chk("background", background)
+    dev = means.device
+    W, H, bw = int(img_size[0]), int(img_size[1]), int(block[0])
+    if updated_img.numel() != H * W * 3 or updated_alpha.numel() != H * W:
+        raise RuntimeError("updated_img must be (H, W, 3) and updated_alpha (H, W, 1)")
+    if depth_lower.numel() != H * W or depth_upper.numel() != H * W:
+        raise RuntimeError("depth_lower / depth_upper must be (H, W)")
+    n, X, C = means.shape[0], int(texture_total_size), int(texture_info[2])
+    out = torch.empty((X, C), dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    temp = torch.empty((lib.gstex_texture_edit_temp_bytes(n),), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.gstex_texture_edit(
+            H, W, bw, n, X, C, _p(texture_dims), _p(updated_img), _p(updated_alpha), _p(depth_lower), _p(depth_upper),
+            _p(gaussian_ids_sorted), _p(tile_bins), _p(opacities), _p(means), _p(scales), float(glob_scale), _p(quats),
+            _p(uv0), _p(umap), _p(vmap), _p(viewmat), _p(c2w), float(fx), float(fy), float(cx), float(cy),
+            int(settings), _p(out), _p(temp), temp.numel(), _stream(dev))
+    _lib.check(rc, "texture_edit")
+    return out

@@ -34,14 +34,24 @@ class FusedTrainStep:
     def __init__(self, params: Dict[str, torch.Tensor], texture_dims: torch.Tensor, img_height: int, img_width: int,
                  *, intrins: Tuple[float, float, float, float], sh_degree: int = 3, block_width: int = 16,
                  settings: int = 1 << 8, glob_scale: float = 1.0, background: Optional[torch.Tensor] = None,
-                 max_intersects: Optional[int] = None):
+                 max_intersects: Optional[int] = None, grad_views: Optional[Dict[str, torch.Tensor]] = None,
+                 texture_is_raw: bool = False):
+        """``params`` holds the ACTIVATED parameters the rasteriser consumes.  Colours come from ``sh_coeffs``
+        (N,K,3) through clamp(SH + 0.5, 0, 1) or, when ``params`` has ``colors`` (N,3) instead,
+        are used as given (example.py:162).  ``grad_views`` places named gradients (e.g. ``v_means``,
+        ``v_sh_coeffs``, ``v_texture``) in caller-owned tensors instead of this object's arena (trainer.py keeps
+        them in its raw-parameter gradient arena).  ``texture_is_raw``: ``params["texture"]`` holds pre-sigmoid
+        texels; the sigmoid and its VJP are fused into the padding / un-padding passes (example.py:171)."""
         self.lib = _lib.load()
         self.p = params
         dev = params["means"].device
         if dev.type != "cuda":
             raise RuntimeError("FusedTrainStep needs CUDA tensors (there is no CPU path)")
         self.dev = dev
-        for k in ("means", "scales", "quats", "opacities", "sh_coeffs", "uv0", "umap", "vmap", "texture"):
+        self.use_sh = "sh_coeffs" in params
+        self.texture_is_raw = bool(texture_is_raw)
+        for k in ("means", "scales", "quats", "opacities", "sh_coeffs" if self.use_sh else "colors", "uv0", "umap",
+                  "vmap", "texture"):
             t = params[k]
             if not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32):
                 raise RuntimeError(f"{k} must be a contiguous float32 CUDA tensor")
@@ -52,7 +62,12 @@ class FusedTrainStep:
         self.intr = tuple(float(v) for v in intrins)
         self.sh_degree = int(sh_degree)
         self.K = (self.sh_degree + 1) ** 2
-        assert params["sh_coeffs"].shape == (self.n, self.K, 3)
+        if self.use_sh:
+            assert params["sh_coeffs"].shape == (self.n, self.K, 3)
+        else:
+            assert params["colors"].shape == (self.n, 3)
+        if self.texture_is_raw and self.C != 3:
+            raise RuntimeError("texture_is_raw needs a 3-channel texture (the sigmoid is fused into the float4 padding)")
         self.settings, self.glob_scale = int(settings), float(glob_scale)
         self.tiles_x, self.tiles_y = -(-self.W // self.bw), -(-self.H // self.bw)
         self.num_tiles = self.tiles_x * self.tiles_y
@@ -64,23 +79,35 @@ class FusedTrainStep:
         self.background = (background if background is not None else torch.zeros(3, **f32)).contiguous()
 
         # ---- gradient arena: [means 3 | scales 3 | quats 4 | opacity 1 | uv0 2 | umap 3 | vmap 3 | sh 3K | texture C*X/n]
-        sizes = [n * w for _, w in _GRAD_FIELDS] + [n * self.K * 3, X * C]
-        self.grad_arena = torch.zeros(sum(sizes), **f32)
+        gv = dict(grad_views or {})
+        col_name, col_shape = ("v_sh_coeffs", (n, self.K, 3)) if self.use_sh else ("v_colors", (n, 3))
+        shapes = [(name, (n, w)) for name, w in _GRAD_FIELDS] + [(col_name, col_shape), ("v_texture", (X, C))]
+        own = [(name, shp) for name, shp in shapes if name not in gv]
+        # every field starts on a 256-byte boundary: the kernels use 8- and 16-byte vector accesses on some of them
+        pad = lambda sz: -(-sz // 64) * 64  # noqa: E731
+        self.grad_arena = torch.zeros(sum(pad(math.prod(shp)) for _, shp in own), **f32)
         self.grads: Dict[str, torch.Tensor] = {}
         off = 0
-        for (name, w), sz in zip(_GRAD_FIELDS, sizes):
-            self.grads[name] = self.grad_arena[off:off + sz].view(n, w)
-            off += sz
-        self.grads["v_sh_coeffs"] = self.grad_arena[off:off + n * self.K * 3].view(n, self.K, 3)
-        off += n * self.K * 3
-        self.grads["v_texture"] = self.grad_arena[off:off + X * C].view(X, C)
+        for name, shp in own:
+            sz = math.prod(shp)
+            self.grads[name] = self.grad_arena[off:off + sz].view(*shp)
+            off += pad(sz)
+        for name, shp in shapes:
+            if name in gv:
+                t = gv[name]
+                if not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32 and t.numel() == math.prod(shp)):
+                    raise RuntimeError(f"grad_views[{name!r}] must be a contiguous float32 CUDA tensor of {shp}")
+                self.grads[name] = t.view(*shp)
 
         # ---- per-step buffers
         self.tex4 = torch.empty((X, 4), **f32) if C == 3 else None
         self.vtex4 = torch.empty((X, 4), **f32) if C == 3 else None
         self.loss = torch.zeros(1, **f32)
         # ---- per-view buffers
-        self.colors, self.mask, self.v_colors = torch.empty((n, 3), **f32), torch.empty((n,), dtype=torch.uint8, device=dev), torch.empty((n, 3), **f32)
+        if self.use_sh:  # per-view colours and their gradient (they feed this view's SH backward)
+            self.colors, self.mask, self.v_colors = torch.empty((n, 3), **f32), torch.empty((n,), dtype=torch.uint8, device=dev), torch.empty((n, 3), **f32)
+        else:
+            self.colors, self.mask, self.v_colors = params["colors"], None, self.grads["v_colors"]
         self.centers, self.extents, self.depths = torch.empty((n, 2), **f32), torch.empty((n, 2), **f32), torch.empty((n,), **f32)
         self.nth = torch.empty((n,), **i32)
         self.ids_sorted = torch.empty((self.cap,), **i32)
@@ -144,7 +171,8 @@ class FusedTrainStep:
         """Once per optimiser step: pad the texture, clear the texel-gradient buffer and the loss."""
         lib, s = self.lib, self._s()
         if self.C == 3:
-            self._ck(lib.gstex_pad_texture(self.X, self.p["texture"].data_ptr(), self.tex4.data_ptr(), s), "pad_texture")
+            pad = lib.gstex_sigmoid_pad_texture if self.texture_is_raw else lib.gstex_pad_texture
+            self._ck(pad(self.X, self.p["texture"].data_ptr(), self.tex4.data_ptr(), s), "pad_texture")
             self.launches += 1
             self.vtex4.zero_()
         else:
@@ -159,8 +187,9 @@ class FusedTrainStep:
         fx, fy, cx, cy = self.intr
         P = lambda t: t.data_ptr()  # noqa: E731
         viewmat, c2w = self._cam(viewmat, "viewmat"), self._cam(c2w, "c2w")
-        self._ck(lib.gstex_sh_colors_forward(n, self.sh_degree, self.sh_degree, P(p["means"]), P(c2w), P(p["sh_coeffs"]),
-                                             P(self.colors), P(self.mask), s), "sh_colors_forward")
+        if self.use_sh:
+            self._ck(lib.gstex_sh_colors_forward(n, self.sh_degree, self.sh_degree, P(p["means"]), P(c2w),
+                                                 P(p["sh_coeffs"]), P(self.colors), P(self.mask), s), "sh_colors_forward")
         self._ck(lib.gstex_project_aabb_count(n, P(p["means"]), P(p["scales"]), self.glob_scale, P(p["quats"]), P(viewmat),
                                               fx, fy, cx, cy, H, W, bw, P(self.centers), P(self.extents), P(self.depths),
                                               P(self.nth), s), "project_aabb_count")
@@ -182,7 +211,7 @@ class FusedTrainStep:
                                               P(o["out_texture"]), P(o["out_normal"]), P(o["final_Ts"]),
                                               P(o["final_idx"]), P(o["depth_idx"]), P(o["out_reg_s"]), P(self.masks), self.cap,
                                               P(self.num_isect), s), "raster_forward")
-        self.launches += 1 + 1 + self._bin_launches + 1 + 2  # sh, project, binning, pack, mask zero-fill + raster
+        self.launches += int(self.use_sh) + 1 + self._bin_launches + 1 + 2  # sh, project, binning, pack, mask zero-fill + raster
         return o
 
     def view_loss(self, target: torch.Tensor) -> None:
@@ -206,8 +235,8 @@ class FusedTrainStep:
         o, g = self.out, self.grads
         acc_flag = 0 if self._first_view else 1
         self.acc.zero_()
-        if acc_flag:
-            self.v_colors.zero_()  # colours are per view (they feed this view's SH backward), never accumulated
+        if acc_flag and self.use_sh:
+            self.v_colors.zero_()  # SH colours are per view (they feed this view's SH backward), never accumulated
         tex = self.tex4 if self.C == 3 else p["texture"]
         vtex = self.vtex4 if self.C == 3 else g["v_texture"]
         with self._timed("raster_backward"):
@@ -218,20 +247,28 @@ class FusedTrainStep:
                                                P(v["v_out_depth"]), P(v["v_out_reg"]), P(v["v_out_alpha"]),
                                                P(v["v_out_texture"]), P(v["v_out_normal"]), P(self.masks), P(self.acc), P(vtex), s),
                      "raster_backward")
-        self.launches += 3  # raster backward, epilogue, SH backward
+        self.launches += 2 + int(self.use_sh)  # raster backward, epilogue, SH backward
         self._ck(lib.gstex_raster_epilogue(n, P(p["means"]), P(p["scales"]), self.glob_scale, P(p["quats"]), P(p["umap"]),
                                            P(p["vmap"]), P(viewmat), P(c2w), fx, fy, cx, cy, P(self.acc), P(self.v_colors),
                                            P(g["v_opacity"]), P(g["v_means"]), P(g["v_scales"]), P(g["v_quats"]),
                                            P(g["v_uv0"]), P(g["v_umap"]), P(g["v_vmap"]), acc_flag, s), "raster_epilogue")
-        self._ck(lib.gstex_sh_colors_backward(n, self.sh_degree, self.sh_degree, P(p["means"]), P(c2w), P(self.v_colors),
-                                              P(self.mask), P(g["v_sh_coeffs"]), acc_flag, s), "sh_colors_backward")
+        if self.use_sh:
+            self._ck(lib.gstex_sh_colors_backward(n, self.sh_degree, self.sh_degree, P(p["means"]), P(c2w),
+                                                  P(self.v_colors), P(self.mask), P(g["v_sh_coeffs"]), acc_flag, s),
+                     "sh_colors_backward")
         self._first_view = False
 
     def end_step(self) -> None:
         """Once per step: un-pad the texel gradients into the arena."""
         if self.C == 3:
-            self._ck(self.lib.gstex_unpad_texture_grad(self.X, self.vtex4.data_ptr(), self.grads["v_texture"].data_ptr(), 0,
-                                                       self._s()), "unpad_texture_grad")
+            if self.texture_is_raw:  # gradient w.r.t. the pre-sigmoid texels: g * t (1 - t), fused into the un-padding
+                self._ck(self.lib.gstex_unpad_texture_grad_sigmoid(self.X, self.vtex4.data_ptr(), self.tex4.data_ptr(),
+                                                                   self.grads["v_texture"].data_ptr(), 0, self._s()),
+                         "unpad_texture_grad_sigmoid")
+            else:
+                self._ck(self.lib.gstex_unpad_texture_grad(self.X, self.vtex4.data_ptr(),
+                                                           self.grads["v_texture"].data_ptr(), 0, self._s()),
+                         "unpad_texture_grad")
             self.launches += 1
 
     def step(self, cameras: Sequence[Tuple[torch.Tensor, torch.Tensor]], targets: Sequence[torch.Tensor]) -> torch.Tensor:

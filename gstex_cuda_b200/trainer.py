@@ -1,0 +1,149 @@
+"""One GStex optimiser step from RAW parameters, fused.
+
+The reference trainer (example.py:121-225, :278) goes, every iteration, through ~25 small torch kernels of
+"preprocess" (exp / normalise / quat->R / uv maps / sigmoids), the rasteriser, the same number of autograd kernels
+on the way back, and a 7-tensor ``torch.optim.Adam`` step.  Here the whole iteration is
+
+    preprocess_forward (1 launch) -> FusedTrainStep over this rank's views (pipeline.py; the texel sigmoid and its
+    VJP ride on the float4 padding passes) -> preprocess_backward (1 launch) -> [one NCCL all-reduce of the raw
+    gradient arena] -> adam_step (1 launch over the whole parameter arena)
+
+with no host synchronisation.  Raw parameters, their gradients and both Adam moments live in four contiguous
+fp32 arenas with the same field layout, so the collective and the optimiser each touch one buffer.
+
+Parameter names follow example.py:69-119: ``means``, ``scales`` (log), ``quats`` (un-normalised), ``opacities``
+(pre-sigmoid), ``mapping`` (N,1,4) = (u0, v0, log uv-scale, theta), ``texture`` (pre-sigmoid, (X,3)), and for the
+colours either ``rgbs`` (pre-sigmoid, example.py:162) or ``sh_coeffs`` (N,K,3) with colours = clamp(SH + 0.5, 0, 1)
+(SURVEY 8d C4).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from .pipeline import DataParallelTrainStep, FusedTrainStep
+
+
+class GStexTrainStep:
+    def __init__(self, raw: Dict[str, torch.Tensor], texture_dims: torch.Tensor, img_height: int, img_width: int, *,
+                 intrins: Tuple[float, float, float, float], sh_degree: int = 3, lr: float = 0.01,
+                 betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8, grad_scale: float = 1.0,
+                 train_mapping: bool = False, rank: int = 0, world_size: int = 1, group=None, **fused_kwargs):
+        """``raw``: the leaf parameters (copied into this object's arena; ``self.raw`` are views of it).
+        ``train_mapping``: example.py:118 freezes the uv mapping (its gradient is computed, the update skipped)."""
+        self.lib = _lib.load()
+        dev = raw["means"].device
+        if dev.type != "cuda":
+            raise RuntimeError("GStexTrainStep needs CUDA tensors (there is no CPU path)")
+        self.dev = dev
+        self.use_sh = "sh_coeffs" in raw
+        n = raw["means"].shape[0]
+        X, C = raw["texture"].shape
+        if C != 3:
+            raise RuntimeError("GStexTrainStep trains 3-channel textures (example.py:95)")
+        K = (int(sh_degree) + 1) ** 2
+        col = ("sh_coeffs", (n, K, 3)) if self.use_sh else ("rgbs", (n, 3))
+        # the mapping sits last so that a frozen mapping is simply left out of the Adam range
+        self.fields: List[Tuple[str, Tuple[int, ...]]] = [
+            ("means", (n, 3)), ("scales", (n, 3)), ("quats", (n, 4)), ("opacities", (n, 1)), col, ("texture", (X, 3)),
+            ("mapping", (n, 1, 4))]
+        pad = lambda sz: -(-sz // 64) * 64  # noqa: E731  (fields start on 256-byte boundaries: vector accesses)
+        total = sum(pad(math.prod(shp)) for _, shp in self.fields)
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.param_arena, self.grad_arena = torch.zeros(total, **f32), torch.zeros(total, **f32)
+        self.exp_avg, self.exp_avg_sq = torch.zeros(total, **f32), torch.zeros(total, **f32)
+        self.raw: Dict[str, torch.Tensor] = {}
+        self.raw_grads: Dict[str, torch.Tensor] = {}
+        off = 0
+        for name, shp in self.fields:
+            sz = math.prod(shp)
+            if tuple(raw[name].shape) != shp:
+                raise RuntimeError(f"raw[{name!r}] must have shape {shp}, got {tuple(raw[name].shape)}")
+            self.raw[name] = self.param_arena[off:off + sz].view(*shp)
+            self.raw[name].copy_(raw[name])
+            self.raw_grads[name] = self.grad_arena[off:off + sz].view(*shp)
+            off += pad(sz)
+        self.n_train = total if train_mapping else total - pad(n * 4)
+        self.n, self.X = n, X
+        self.lr, self.betas, self.eps, self.grad_scale = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(grad_scale)
+        self.rank, self.world_size, self.group = int(rank), int(world_size), group
+        self.step_count = 0
+
+        # activated parameters (what the rasteriser consumes) and the gradients w.r.t. them
+        self.act = dict(scales=torch.empty((n, 3), **f32), quats=torch.empty((n, 4), **f32),
+                        opacities=torch.empty((n, 1), **f32), uv0=torch.empty((n, 1, 2), **f32),
+                        umap=torch.empty((n, 1, 3), **f32), vmap=torch.empty((n, 1, 3), **f32))
+        params = dict(self.act, means=self.raw["means"], texture=self.raw["texture"])
+        grad_views = dict(v_means=self.raw_grads["means"], v_texture=self.raw_grads["texture"])
+        if self.use_sh:
+            params["sh_coeffs"] = self.raw["sh_coeffs"]
+            grad_views["v_sh_coeffs"] = self.raw_grads["sh_coeffs"]
+        else:
+            self.act["colors"] = torch.empty((n, 3), **f32)
+            params["colors"] = self.act["colors"]
+        self.fused = FusedTrainStep(params, texture_dims, img_height, img_width, intrins=intrins, sh_degree=sh_degree,
+                                    grad_views=grad_views, texture_is_raw=True, **fused_kwargs)
+        self.launches = 0
+
+    def _s(self) -> int:
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def preprocess(self) -> None:
+        """raw -> activated parameters (example.py:126-143, :162-163); one launch."""
+        P = lambda t: t.data_ptr()  # noqa: E731
+        r, a = self.raw, self.act
+        _lib.check(self.lib.gstex_preprocess_forward(
+            self.n, P(r["scales"]), P(r["quats"]), P(r["mapping"]), 0 if self.use_sh else P(r["rgbs"]), P(r["opacities"]),
+            P(a["scales"]), P(a["quats"]), P(a["uv0"]), P(a["umap"]), P(a["vmap"]), 0 if self.use_sh else P(a["colors"]),
+            P(a["opacities"]), self._s()), "preprocess_forward")
+        self.launches += 1
+
+    def backward_preprocess(self) -> None:
+        """gradients w.r.t. activated parameters (FusedTrainStep arena) -> raw gradient arena; one launch."""
+        P = lambda t: t.data_ptr()  # noqa: E731
+        r, g, rg = self.raw, self.fused.grads, self.raw_grads
+        _lib.check(self.lib.gstex_preprocess_backward(
+            self.n, P(r["scales"]), P(r["quats"]), P(r["mapping"]), 0 if self.use_sh else P(r["rgbs"]), P(r["opacities"]),
+            P(g["v_scales"]), P(g["v_quats"]), P(g["v_uv0"]), P(g["v_umap"]), P(g["v_vmap"]),
+            0 if self.use_sh else P(g["v_colors"]), P(g["v_opacity"]), P(rg["scales"]), P(rg["quats"]), P(rg["mapping"]),
+            0 if self.use_sh else P(rg["rgbs"]), P(rg["opacities"]), self._s()), "preprocess_backward")
+        self.launches += 1
+
+    def forward_backward(self, cameras: Sequence[Tuple[torch.Tensor, torch.Tensor]],
+                         targets: Sequence[torch.Tensor]) -> torch.Tensor:
+        """Loss (summed over this rank's views, device tensor) and raw gradients (``self.raw_grads``, summed over
+        all ranks) of the batch; no parameter update."""
+        mine = DataParallelTrainStep.shard(len(cameras), self.rank, self.world_size)
+        self.preprocess()
+        loss = self.fused.step([cameras[i] for i in mine], [targets[i] for i in mine])
+        if mine:
+            self.backward_preprocess()
+        else:
+            self.grad_arena.zero_()
+        if self.world_size > 1:
+            import torch.distributed as dist
+
+            dist.all_reduce(self.grad_arena, op=dist.ReduceOp.SUM, group=self.group)
+            dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=self.group)
+        return loss
+
+    def optimizer_step(self) -> None:
+        """torch.optim.Adam's update over the parameter arena (example.py:223-225, :278); one launch."""
+        self.step_count += 1
+        P = lambda t: t.data_ptr()  # noqa: E731
+        _lib.check(self.lib.gstex_adam_step(self.n_train, P(self.param_arena), P(self.grad_arena), P(self.exp_avg),
+                                            P(self.exp_avg_sq), self.lr, self.betas[0], self.betas[1], self.eps,
+                                            self.step_count, self.grad_scale, self._s()), "adam_step")
+        self.launches += 1
+
+    def step(self, cameras, targets) -> torch.Tensor:
+        loss = self.forward_backward(cameras, targets)
+        self.optimizer_step()
+        return loss
+
+    @property
+    def total_launches(self) -> int:
+        return self.launches + self.fused.launches

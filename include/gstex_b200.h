@@ -167,6 +167,23 @@ int gstex_texture_backward(int img_height, int img_width, int block_width, int n
                            float *v_uv0, float *v_umap, float *v_vmap, float *v_texture, int accumulate,
                            const void *fwd_temp, void *temp, size_t temp_bytes, gstex_stream_t stream);
 
+/* replaces texture_edit_tensor, texture_edit.cu:238-354 (kernel :11-236): walks every pixel's
+ * depth-sorted list like the forward pass and, for each blended Gaussian whose view depth lies inside the pixel's
+ * [depth_lower, depth_upper] window, adds rgb*alpha, alpha and 1 of the edit canvas with the bilinear weights of the
+ * intersection's texel into updated_texture (num_texels, channels), which the call zero-fills first.
+ * channels = texture_info.z of the reference call (the row pitch of the output), >= 5; channels 5.. stay zero.
+ * updated_img (H,W,3), updated_alpha / depth_lower / depth_upper (H,W).
+ * settings: bit 0 = blur, bit 1 = ndc (read but unused upstream) -- NOT the rasteriser's bit positions
+ * (texture_edit.cu:46-47). */
+size_t gstex_texture_edit_temp_bytes(int n);
+int gstex_texture_edit(int img_height, int img_width, int block_width, int n, int64_t num_texels, int channels,
+                       const int32_t *texture_dims, const float *updated_img, const float *updated_alpha,
+                       const float *depth_lower, const float *depth_upper, const int32_t *gaussian_ids_sorted,
+                       const int32_t *tile_bins, const float *opacities, const float *means, const float *scales,
+                       float glob_scale, const float *quats, const float *uv0, const float *umap, const float *vmap,
+                       const float *viewmat, const float *c2w, float fx, float fy, float cx, float cy, int settings,
+                       float *updated_texture, void *temp, size_t temp_bytes, gstex_stream_t stream);
+
 /* ======================================================================================== *
  * spherical harmonics, texture sampling
  * ======================================================================================== */
@@ -243,6 +260,43 @@ int gstex_sh_colors_forward(int n, int degree, int degrees_to_use, const float *
 int gstex_sh_colors_backward(int n, int degree, int degrees_to_use, const float *means, const float *c2w,
                              const float *v_colors, const uint8_t *mask, float *v_coeffs, int accumulate,
                              gstex_stream_t stream);
+
+/* ======================================================================================== *
+ * training-step glue around the rasteriser
+ * ======================================================================================== */
+
+/* replaces the ~25 torch ops of example.py:126-143 + the sigmoids of :162-163 (one launch):
+ *   scales = (exp(raw.x), exp(raw.y), 1e-5 * mean of the two), quats = raw / |raw|,
+ *   uv0 = mapping[:, :2], umap = e^m2 (a1 cos m3 + a2 sin m3), vmap = e^m2 (-a1 sin m3 + a2 cos m3) with a1, a2 the
+ *   first two columns of R(quats), colors = sigmoid(raw_rgbs) (skipped when raw_rgbs == colors == NULL, e.g. when
+ *   colours come from spherical harmonics), opacities = sigmoid(raw_opacities).
+ * raw_scales (n,3), raw_quats (n,4), mapping (n,1,4) = (u0, v0, log uv-scale, theta), raw_rgbs (n,3), raw_opacities (n,1). */
+int gstex_preprocess_forward(int n, const float *raw_scales, const float *raw_quats, const float *mapping,
+                             const float *raw_rgbs, const float *raw_opacities, float *scales, float *quats,
+                             float *uv0, float *umap, float *vmap, float *colors, float *opacities,
+                             gstex_stream_t stream);
+
+/* the VJP of gstex_preprocess_forward (what torch autograd does for example.py:126-143): gradients w.r.t. the
+ * activated parameters in, gradients w.r.t. the raw parameters out (overwritten).  v_raw_scales[:, 2] = 0: the
+ * thickness is detached upstream (example.py:128). */
+int gstex_preprocess_backward(int n, const float *raw_scales, const float *raw_quats, const float *mapping,
+                              const float *raw_rgbs, const float *raw_opacities, const float *v_scales,
+                              const float *v_quats, const float *v_uv0, const float *v_umap, const float *v_vmap,
+                              const float *v_colors, const float *v_opacity, float *v_raw_scales, float *v_raw_quats,
+                              float *v_mapping, float *v_raw_rgbs, float *v_raw_opacities, gstex_stream_t stream);
+
+/* torch.sigmoid(texture) (example.py:171) fused into the float4 padding pass, and its VJP fused into the un-padding
+ * pass: v_raw (+)= g4 * t * (1 - t) with t read from tex4.  3-channel textures. */
+int gstex_sigmoid_pad_texture(int64_t num_texels, const float *raw_texture, float *tex4, gstex_stream_t stream);
+int gstex_unpad_texture_grad_sigmoid(int64_t num_texels, const float *g4, const float *tex4, float *v_raw_texture,
+                                     int accumulate, gstex_stream_t stream);
+
+/* torch.optim.Adam's update (example.py:223-225, :278; betas / eps as given, no weight decay, no amsgrad) over a
+ * contiguous fp32 range: one launch for a whole parameter arena.  step is 1-based; grads are multiplied by
+ * grad_scale first (1/world_size or 1/views for a mean).  lr / betas / eps are doubles because torch forms
+ * 1 - beta, the bias corrections and lr / bc1 in Python doubles before rounding to fp32. */
+int gstex_adam_step(int64_t count, float *params, const float *grads, float *exp_avg, float *exp_avg_sq, double lr,
+                    double beta1, double beta2, double eps, int step, float grad_scale, gstex_stream_t stream);
 
 #ifdef __cplusplus
 }

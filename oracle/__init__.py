@@ -219,6 +219,71 @@ def texture_backward(img_height, img_width, block_width, texture_dims, gaussian_
     return o
 
 
+def texture_edit(img_height, img_width, block_width, channels, num_texels, texture_dims, updated_img, updated_alpha,
+                 depth_lower, depth_upper, gaussian_ids_sorted, tile_bins, opacities, means, scales, glob_scale, quats,
+                 uv0, umap, vmap, viewmat, c2w, fx, fy, cx, cy, settings) -> np.ndarray:
+    """texture_edit_tensor, texture_edit.cu:238-354: (num_texels, channels) zero-initialised, 5 channels splatted."""
+    H, W = int(img_height), int(img_width)
+    assert channels >= 5
+    out = np.zeros((int(num_texels), int(channels)), np.float32)
+    a = [_i(texture_dims), _f(updated_img), _f(updated_alpha), _f(depth_lower), _f(depth_upper),
+         _i(gaussian_ids_sorted), _i(tile_bins), _f(opacities), _f(means), _f(scales)]
+    b = [_f(quats), _f(uv0), _f(umap), _f(vmap), _f(viewmat), _f(c2w)]
+    lib().orc_texture_edit(
+        C.c_int(W), C.c_int(H), C.c_int(block_width), C.c_int(channels), *[_p(x) for x in a], C.c_float(glob_scale),
+        *[_p(x) for x in b], C.c_float(fx), C.c_float(fy), C.c_float(cx), C.c_float(cy), C.c_int(settings), _p(out))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# training-step glue (SURVEY 8f ranks 1 and 3)
+PRE_KEYS = ("scales", "quats", "uv0", "umap", "vmap", "colors", "opacities")
+PRE_GRAD_KEYS = ("v_raw_scales", "v_raw_quats", "v_mapping", "v_raw_rgbs", "v_raw_opacities")
+
+
+def preprocess_forward(raw_scales, raw_quats, mapping, raw_rgbs, raw_opacities) -> Dict[str, np.ndarray]:
+    """example.py:126-143 + :162-163; raw_rgbs may be None (colours from SH)."""
+    raw_scales, raw_quats, mapping, raw_opacities = _f(raw_scales), _f(raw_quats), _f(mapping), _f(raw_opacities)
+    n = raw_scales.shape[0]
+    o = dict(scales=np.zeros((n, 3), np.float32), quats=np.zeros((n, 4), np.float32), uv0=np.zeros((n, 1, 2), np.float32),
+             umap=np.zeros((n, 1, 3), np.float32), vmap=np.zeros((n, 1, 3), np.float32),
+             colors=None if raw_rgbs is None else np.zeros((n, 3), np.float32), opacities=np.zeros((n, 1), np.float32))
+    rgb = None if raw_rgbs is None else _f(raw_rgbs)
+    lib().orc_preprocess_forward(C.c_int(n), _p(raw_scales), _p(raw_quats), _p(mapping),
+                                 None if rgb is None else _p(rgb), _p(raw_opacities), _p(o["scales"]), _p(o["quats"]),
+                                 _p(o["uv0"]), _p(o["umap"]), _p(o["vmap"]),
+                                 None if rgb is None else _p(o["colors"]), _p(o["opacities"]))
+    return o
+
+
+def preprocess_backward(raw_scales, raw_quats, mapping, raw_rgbs, raw_opacities, v_scales, v_quats, v_uv0, v_umap,
+                        v_vmap, v_colors, v_opacity) -> Dict[str, np.ndarray]:
+    raw_scales, raw_quats, mapping, raw_opacities = _f(raw_scales), _f(raw_quats), _f(mapping), _f(raw_opacities)
+    n = raw_scales.shape[0]
+    rgb = None if raw_rgbs is None else _f(raw_rgbs)
+    vc = None if raw_rgbs is None else _f(v_colors)
+    o = dict(v_raw_scales=np.zeros((n, 3), np.float32), v_raw_quats=np.zeros((n, 4), np.float32),
+             v_mapping=np.zeros((n, 1, 4), np.float32), v_raw_rgbs=None if rgb is None else np.zeros((n, 3), np.float32),
+             v_raw_opacities=np.zeros((n, 1), np.float32))
+    g = [_f(v_scales), _f(v_quats), _f(v_uv0), _f(v_umap), _f(v_vmap)]
+    vo = _f(v_opacity)
+    lib().orc_preprocess_backward(C.c_int(n), _p(raw_scales), _p(raw_quats), _p(mapping),
+                                  None if rgb is None else _p(rgb), _p(raw_opacities), *[_p(x) for x in g],
+                                  None if vc is None else _p(vc), _p(vo), _p(o["v_raw_scales"]), _p(o["v_raw_quats"]),
+                                  _p(o["v_mapping"]), None if rgb is None else _p(o["v_raw_rgbs"]),
+                                  _p(o["v_raw_opacities"]))
+    return o
+
+
+def adam_step(params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, grad_scale=1.0):
+    """torch.optim.Adam update, in place on float32 numpy arrays (step is 1-based)."""
+    for a in (params, exp_avg, exp_avg_sq):
+        assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
+    g = _f(grads)
+    lib().orc_adam_step(C.c_int64(params.size), _p(params), _p(g), _p(exp_avg), _p(exp_avg_sq), C.c_double(lr),
+                        C.c_double(beta1), C.c_double(beta2), C.c_double(eps), C.c_int(step), C.c_float(grad_scale))
+
+
 # ----------------------------------------------------------------------------------------------
 def bin_view(means, scales, glob_scale, quats, viewmat, intrins, img_height, img_width, block_width):
     """project -> aabb -> tile count -> cumsum -> key emit -> sort -> tile ranges, as example.py:146-152

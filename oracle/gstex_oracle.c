@@ -644,6 +644,149 @@ void orc_texture_backward(int img_w, int img_h, int bw, int C, const int32_t *te
     }
 }
 
+/* ------------------------------------------------------------------------------------------
+ * texture_edit: texture_edit.cu:11-236.  Walks every pixel's list exactly like the forward
+ * pass (same alpha, skip and stop rules, :161-186) and, for every blended Gaussian whose view depth lies inside
+ * the pixel's [depth_lower, depth_upper] window (:191), splats five values with the BILINEAR weights of the
+ * intersection's texel coordinate into `updated_texture` (X, C) -- channel 0-2 rgb*alpha of the edit canvas,
+ * 3 its alpha, 4 the constant 1 (:204-227; texture_helpers.cuh:239-250).  The splat is NOT weighted by the blend
+ * weight `vis` (computed at :189 but unused).  C = texture_info.z is the row pitch of the output and must be >= 5.
+ * NB the settings bits differ from the rasteriser's: bit 0 = blur, bit 1 = ndc (unused) (:46-47).
+ * ---------------------------------------------------------------------------------------- */
+void orc_texture_edit(int img_w, int img_h, int bw, int C, const int32_t *texture_dims, const float *updated_img,
+                      const float *updated_alpha, const float *depth_lower, const float *depth_upper,
+                      const int32_t *gaussian_ids_sorted, const int32_t *tile_bins, const float *opacities,
+                      const float *means, const float *scales, float glob_scale, const float *quats,
+                      const float *uv0, const float *umap, const float *vmap, const float *viewmat,
+                      const float *c2w, float fx, float fy, float cx, float cy, int settings,
+                      float *updated_texture) {
+    const int tiles_x = (img_w + bw - 1) / bw;
+    const int use_blur = (settings & 1) != 0;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int pix = 0; pix < img_w * img_h; ++pix) {
+        int row = pix / img_w, col = pix % img_w;
+        int tile = (row / bw) * tiles_x + (col / bw);
+        int lo = tile_bins[2 * tile], hi = tile_bins[2 * tile + 1];
+        pixray r = make_ray(c2w, viewmat, fx, fy, cx, cy, col, row);
+        const float a_upd = updated_alpha[pix];
+        const float vals[5] = {updated_img[3 * pix] * a_upd, updated_img[3 * pix + 1] * a_upd,
+                               updated_img[3 * pix + 2] * a_upd, a_upd, 1.f};
+        const float zlo = depth_lower[pix], zhi = depth_upper[pix];
+        float T = 1.f;
+        for (int idx = lo; idx < hi; ++idx) {
+            int g = gaussian_ids_sorted[idx];
+            pairgeom pg;
+            pair_geometry(&r, means + 3 * g, scales + 3 * g, quats + 4 * g, opacities[g], glob_scale, viewmat,
+                          fx, fy, cx, cy, use_blur, &pg);
+            int skip = (pg.t < T_NEAR || pg.t > T_FAR || pg.alpha < 1.f / 255.f);
+            float next_T = T * (1.f - pg.alpha);
+            if (next_T <= 1e-4f) break; /* texture_edit.cu:180-184 */
+            if (skip) continue;
+            float t_view = pg.t * r.view_depth;
+            if (t_view >= zlo && t_view <= zhi) {
+                float u = clamp01(uv0[2 * g] + v3_dot(v3_load(umap + 3 * g), pg.delta));
+                float v = clamp01(uv0[2 * g + 1] + v3_dot(v3_load(vmap + 3 * g), pg.delta));
+                texfetch f;
+                texel_setup(texture_dims + 3 * g, u, v, 1, C, &f);
+                for (int k = 0; k < 5; ++k)
+                    for (int c4 = 0; c4 < 4; ++c4) atomic_addf(updated_texture + f.idx[c4] + k, f.w[c4] * vals[k]);
+            }
+            T = next_T;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Training-step glue.
+ *
+ * orc_preprocess_forward: example.py:126-143 (+ the sigmoids of :162-163).  raw_rgbs may be NULL.
+ * ---------------------------------------------------------------------------------------- */
+static inline float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+void orc_preprocess_forward(int n, const float *raw_scales, const float *raw_quats, const float *mapping,
+                            const float *raw_rgbs, const float *raw_opac, float *scales, float *quats, float *uv0,
+                            float *umap, float *vmap, float *colors, float *opacities) {
+    for (int g = 0; g < n; ++g) {
+        float s1 = expf(raw_scales[3 * g]), s2 = expf(raw_scales[3 * g + 1]);       /* :126-127 */
+        scales[3 * g] = s1; scales[3 * g + 1] = s2;
+        scales[3 * g + 2] = 1e-5f * (0.5f * (s1 + s2));                              /* :128 */
+        const float *q = raw_quats + 4 * g;
+        float nrm = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);    /* :129 */
+        float qn[4] = {q[0] / nrm, q[1] / nrm, q[2] / nrm, q[3] / nrm};
+        for (int c = 0; c < 4; ++c) quats[4 * g + c] = qn[c];
+        v3 a1, a2, a3;
+        surfel_axes(qn, &a1, &a2, &a3);                                              /* :130, Rs[:, :, 0], Rs[:, :, 1] */
+        const float *m = mapping + 4 * g;
+        float us = expf(m[2]), c = cosf(m[3]), s = sinf(m[3]);                       /* :132-133 */
+        uv0[2 * g] = m[0]; uv0[2 * g + 1] = m[1];                                    /* :131 */
+        umap[3 * g] = us * (a1.x * c + a2.x * s); umap[3 * g + 1] = us * (a1.y * c + a2.y * s);
+        umap[3 * g + 2] = us * (a1.z * c + a2.z * s);                                /* :136 */
+        vmap[3 * g] = us * (-a1.x * s + a2.x * c); vmap[3 * g + 1] = us * (-a1.y * s + a2.y * c);
+        vmap[3 * g + 2] = us * (-a1.z * s + a2.z * c);                               /* :137 */
+        if (raw_rgbs) for (int k = 0; k < 3; ++k) colors[3 * g + k] = sigmoidf_(raw_rgbs[3 * g + k]);
+        opacities[g] = sigmoidf_(raw_opac[g]);
+    }
+}
+
+/* The VJP torch autograd computes for the block above (no reference source: it is autograd's; pinned by the
+ * golden vectors of tests/golden/make_golden_train_ops.py, which run torch autograd over the reference's own
+ * normalized_quat_to_rotmat). */
+void orc_preprocess_backward(int n, const float *raw_scales, const float *raw_quats, const float *mapping,
+                             const float *raw_rgbs, const float *raw_opac, const float *v_scales,
+                             const float *v_quats, const float *v_uv0, const float *v_umap, const float *v_vmap,
+                             const float *v_colors, const float *v_opacity, float *v_raw_scales, float *v_raw_quats,
+                             float *v_mapping, float *v_raw_rgbs, float *v_raw_opac) {
+    for (int g = 0; g < n; ++g) {
+        v_raw_scales[3 * g] = v_scales[3 * g] * expf(raw_scales[3 * g]);
+        v_raw_scales[3 * g + 1] = v_scales[3 * g + 1] * expf(raw_scales[3 * g + 1]);
+        v_raw_scales[3 * g + 2] = 0.f; /* detached thickness, example.py:128 */
+        const float *q = raw_quats + 4 * g;
+        float nrm = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+        float qn[4] = {q[0] / nrm, q[1] / nrm, q[2] / nrm, q[3] / nrm};
+        v3 a1, a2, a3;
+        surfel_axes(qn, &a1, &a2, &a3);
+        const float *m = mapping + 4 * g;
+        float us = expf(m[2]), c = cosf(m[3]), s = sinf(m[3]);
+        v3 um = v3_make(us * (a1.x * c + a2.x * s), us * (a1.y * c + a2.y * s), us * (a1.z * c + a2.z * s));
+        v3 vm = v3_make(us * (-a1.x * s + a2.x * c), us * (-a1.y * s + a2.y * c), us * (-a1.z * s + a2.z * c));
+        v3 gu = v3_load(v_umap + 3 * g), gv = v3_load(v_vmap + 3 * g);
+        v_mapping[4 * g] = v_uv0[2 * g]; v_mapping[4 * g + 1] = v_uv0[2 * g + 1];
+        v_mapping[4 * g + 2] = v3_dot(um, gu) + v3_dot(vm, gv);
+        v_mapping[4 * g + 3] = v3_dot(vm, gu) - v3_dot(um, gv);
+        v3 g1 = v3_make(us * (c * gu.x - s * gv.x), us * (c * gu.y - s * gv.y), us * (c * gu.z - s * gv.z));
+        v3 g2 = v3_make(us * (s * gu.x + c * gv.x), us * (s * gu.y + c * gv.y), us * (s * gu.z + c * gv.z));
+        float va[4];
+        surfel_axes_vjp(qn, g1, g2, v3_make(0.f, 0.f, 0.f), va);
+        float vq[4], d = 0.f;
+        for (int k = 0; k < 4; ++k) { vq[k] = v_quats[4 * g + k] + va[k]; d += qn[k] * vq[k]; }
+        for (int k = 0; k < 4; ++k) v_raw_quats[4 * g + k] = (vq[k] - qn[k] * d) / nrm;
+        if (raw_rgbs)
+            for (int k = 0; k < 3; ++k) {
+                float cv = sigmoidf_(raw_rgbs[3 * g + k]);
+                v_raw_rgbs[3 * g + k] = v_colors[3 * g + k] * cv * (1.f - cv);
+            }
+        float o = sigmoidf_(raw_opac[g]);
+        v_raw_opac[g] = v_opacity[g] * o * (1.f - o);
+    }
+}
+
+/* torch.optim.Adam, single-tensor form (torch/optim/adam.py, pinned version torch 2.11.0; third-party to the
+ * reference, call site example.py:223-225, :278): defaults, no weight decay, no amsgrad.  step is 1-based. */
+void orc_adam_step(int64_t count, float *p, const float *g, float *m, float *v, double lr, double beta1,
+                   double beta2, double eps_d, int step, float grad_scale) {
+    /* torch forms these in Python doubles before the fp32 kernels see them */
+    double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+    float step_size = (float)(lr / bc1), sq2 = (float)sqrt(bc2), eps = (float)eps_d;
+    float omb1 = (float)(1.0 - beta1), omb2 = (float)(1.0 - beta2), b2 = (float)beta2;
+    for (int64_t i = 0; i < count; ++i) {
+        float gi = g[i] * grad_scale;
+        m[i] = m[i] + (gi - m[i]) * omb1;
+        v[i] = b2 * v[i] + omb2 * gi * gi;
+        float denom = sqrtf(v[i]) / sq2 + eps;
+        p[i] = p[i] - step_size * (m[i] / denom);
+    }
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -86,6 +86,20 @@ def make(ref, name, n, W, H, bw, settings, C, seed, opaque=False):
     for k, v in zip(("v_colors", "v_opacity", "v_means", "v_scales", "v_quats", "v_uv0", "v_umap", "v_vmap", "v_texture"),
                     grads):
         d[k] = npy(v)
+    # texture_edit on the same scene (texture_edit.cu:238-354): edit canvas + depth window around the rendered depth
+    ge = torch.Generator().manual_seed(seed + 1000)
+    upd_img = torch.rand(H, W, 3, generator=ge).to(DEV)
+    upd_alpha = (torch.rand(H, W, 1, generator=ge) > 0.3).float().to(DEV) * torch.rand(H, W, 1, generator=ge).to(DEV)
+    dmed = outs[1]
+    zlo, zhi = (dmed - 0.5).contiguous(), (dmed + 0.5).contiguous()
+    X = int(s["texture"].shape[0])
+    edit_settings = (1 if settings & (1 << 9) else 0)  # edit: bit 0 = blur
+    upd = ref.texture_edit(tb, (bw, bw, 1), (W, H, 1), (n, 1, 5), X, s["texture_dims"], upd_img, upd_alpha, zlo, zhi,
+                           gids_s, bins, s["opacities"], s["means"], s["scales"], 1.0, s["quats"], s["uv0"], s["umap"],
+                           s["vmap"], vm, s["c2w"], fx, fy, cx, cy, edit_settings, s["background"])
+    torch.cuda.synchronize()
+    d.update(edit_img=npy(upd_img), edit_alpha=npy(upd_alpha), edit_depth_lower=npy(zlo), edit_depth_upper=npy(zhi),
+             edit_settings=edit_settings, edit_updated_texture=npy(upd))
     os.makedirs(OUT, exist_ok=True)
     np.savez_compressed(os.path.join(OUT, name), **d)
     print(name, "M =", m, "bytes =", os.path.getsize(os.path.join(OUT, name)))

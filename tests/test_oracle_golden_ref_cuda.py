@@ -55,3 +55,22 @@ def test_oracle_matches_reference_cuda(path):
     for k in oracle.BWD_KEYS:
         ref = g[k]
         _close(k, b[k].reshape(ref.shape), ref, 2e-3, 1e-7 + 1e-4 * float(np.abs(ref).max()), 12)
+
+
+@pytest.mark.skipif(not FILES, reason="reference-CUDA golden vectors not generated yet")
+@pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f) for f in FILES])
+def test_oracle_texture_edit_matches_reference_cuda(path):
+    """texture_edit: the oracle against the reference CUDA kernel's splat."""
+    g = dict(np.load(path))
+    if "edit_updated_texture" not in g:
+        pytest.skip("fixture predates the texture_edit vectors")
+    H, W, bw = int(g["H"]), int(g["W"]), int(g["block_width"])
+    fx, fy, cx, cy = (float(v) for v in g["intrins"])
+    want = g["edit_updated_texture"]
+    got = oracle.texture_edit(H, W, bw, want.shape[1], want.shape[0], g["texture_dims"], g["edit_img"], g["edit_alpha"],
+                              g["edit_depth_lower"], g["edit_depth_upper"], g["gaussian_ids_sorted"], g["tile_bins"],
+                              g["opacities"], g["means"], g["scales"], 1.0, g["quats"], g["uv0"], g["umap"], g["vmap"],
+                              g["viewmat"], g["c2w"], fx, fy, cx, cy, int(g["edit_settings"]))
+    assert want[:, 4].sum() > 0, "fixture splats nothing"
+    # a pair at the 1/255 / depth-window threshold may be kept by one side only: a few texels may differ by one splat
+    _close("updated_texture", got, want, 1e-4, 1e-5, 40)
