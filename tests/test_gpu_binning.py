@@ -150,8 +150,8 @@ def test_backend_error_behaviour():
         _C.get_aabb_2d(s["means"].cpu(), s["scales"], 1.0, s["quats"], s["viewmat"], *s["intrins"])
     with pytest.raises(RuntimeError):
         _C.get_aabb_2d(s["means"].T.contiguous().T, s["scales"], 1.0, s["quats"], s["viewmat"], *s["intrins"])
-    with pytest.raises(NotImplementedError):
-        _C.texture_edit()
+    with pytest.raises(RuntimeError):  # dtype is checked where the reference's data_ptr<float>() would throw
+        _C.get_aabb_2d(s["means"].double(), s["scales"], 1.0, s["quats"], s["viewmat"], *s["intrins"])
 
 
 # ---- fused tile binning (csrc/binning_tiles.cu) must reproduce the staged path bit for bit -------------------------
