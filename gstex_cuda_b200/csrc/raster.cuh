@@ -145,10 +145,12 @@ __device__ __forceinline__ void tile_pixel(int bw, int tr, int &lx, int &ly) {
     }
 }
 
-// Shared-memory stage layout: quad k of staged record r lives at float4 slot r*8 + (k ^ (r & 7)).
-// The XOR swizzle keeps the warp-uniform reads of the compositing loop broadcasts (one wavefront) and makes
-// the per-lane reads of the culling pass (lane <-> record, 128-byte stride) bank-conflict free.
-__device__ __forceinline__ int quad_slot(int r, int k) { return (r << 3) + (k ^ (r & 7)); }
+// Shared-memory stage layout: quad k of staged record r lives at float4 slot r*9 + k (records padded from 8 to 9
+// quads).  The odd pitch makes the per-lane reads of the culling pass (lane <-> record) bank-conflict free - lane r
+// reads 16-byte bank group (r + k) mod 8 - while the warp-uniform reads of the compositing loop stay broadcasts, and a
+// record's quads sit at compile-time offsets from one base address (no per-quad address arithmetic).
+constexpr int REC_PITCH = 9;
+__device__ __forceinline__ int quad_slot(int r, int k) { return r * REC_PITCH + k; }
 
 // Stage `cnt` records (ids[first..first+cnt)) into shared memory with 16-byte cp.async copies: eight
 // consecutive threads fetch one 128-byte record (one cache line), so both the global reads and the

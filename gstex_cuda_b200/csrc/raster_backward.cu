@@ -47,7 +47,7 @@ constexpr int BWD_FULL = GSTEX_BWD_FULL;  // entries covering at least this many
 template <bool BLUR>
 struct BwdWarpSmem {
     static constexpr int PITCH = BLUR ? 32 : 28;  // floats per moment row (28 used; 30 with BLUR)
-    float4 rec[BWD_ECAP * 8];          // packed records of the chunk's entries (quad_slot swizzle)
+    float4 rec[BWD_ECAP * REC_PITCH];          // packed records of the chunk's entries (quad_slot layout)
     float rows[32 * PITCH];            // moment rows of one dense iteration (D2)
     float e_a[BWD_QCAP];               // alpha (D1) -> vis = alpha * T_k (scan)
     float e_y[BWD_QCAP];               // y (D1) -> v_alpha (scan)
@@ -373,10 +373,9 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, 3) raster_backward_kernel(
                 fetch_pixel(ent >> 8, qc, px);
                 if (act) {
                     const int j = ent & 0xff;
-                    const int sw = j & 7;
-                    const float4 *__restrict__ R = W.rec + (j << 3);
-                    const float4 q0 = R[sw], q1 = R[1 ^ sw], q2 = R[2 ^ sw], q3 = R[3 ^ sw];
-                    const float4 q4 = R[4 ^ sw], q5 = R[5 ^ sw], q6 = R[6 ^ sw], q7 = R[7 ^ sw];
+                    const float4 *__restrict__ R = W.rec + j * REC_PITCH;
+                    const float4 q0 = R[0], q1 = R[1], q2 = R[2], q3 = R[3];
+                    const float4 q4 = R[4], q5 = R[5], q6 = R[6], q7 = R[7];
                     PairEval pe;
                     eval_pair<BLUR>(q0, q1, q2, q3, qc, p.mean2d, pe);
                     float y, gu, gv;
@@ -399,14 +398,13 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, 3) raster_backward_kernel(
                     if (c >= BWD_FULL) {
                         // a Gaussian that covers most of the patch: the whole gradient path right here, lane = pixel,
                         // record read by broadcast, moments reduced with the shuffle butterfly
-                        const int sw = jj & 7;
-                        const float4 *__restrict__ R = W.rec + (jj << 3);
-                        const float4 q0 = R[sw], q1 = R[1 ^ sw], q2 = R[2 ^ sw], q3 = R[3 ^ sw];
+                        const float4 *__restrict__ R = W.rec + jj * REC_PITCH;
+                        const float4 q0 = R[0], q1 = R[1], q2 = R[2], q3 = R[3];
                         float4 r[8];
 #pragma unroll
                         for (int k = 0; k < 8; ++k) r[k] = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (mine) {
-                            const float4 q4 = R[4 ^ sw], q5 = R[5 ^ sw], q6 = R[6 ^ sw], q7 = R[7 ^ sw];
+                            const float4 q4 = R[4], q5 = R[5], q6 = R[6], q7 = R[7];
                             PairEval pe;
                             eval_pair<BLUR>(q0, q1, q2, q3, pc, p.mean2d, pe);
                             float y, gu, gv;
@@ -447,10 +445,9 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, 3) raster_backward_kernel(
                 fetch_pixel(ent >> 8, qc, px);
                 const int jloc = act ? (ent & 0xff) : -1 - lane;
                 if (act) {
-                    const int sw = jloc & 7;
-                    const float4 *__restrict__ R = W.rec + (jloc << 3);
-                    const float4 q0 = R[sw], q1 = R[1 ^ sw], q2 = R[2 ^ sw], q3 = R[3 ^ sw];
-                    const float4 q4 = R[4 ^ sw], q5 = R[5 ^ sw], q6 = R[6 ^ sw];
+                    const float4 *__restrict__ R = W.rec + jloc * REC_PITCH;
+                    const float4 q0 = R[0], q1 = R[1], q2 = R[2], q3 = R[3];
+                    const float4 q4 = R[4], q5 = R[5], q6 = R[6];
                     PairEval pe;
                     eval_pair<BLUR>(q0, q1, q2, q3, qc, p.mean2d, pe);
                     const int idx = first + (int)W.sv_r[si0 - jloc];

@@ -19,7 +19,7 @@ namespace gstex {
 // C3 = false: runtime channel count (<= 64) read from the caller's (X,C) array (slow generic path).
 template <bool C3, bool BLUR>
 __global__ void __launch_bounds__(RASTER_MAX_THREADS, 4) raster_forward_kernel(const RasterCommon p, const ForwardOut o) {
-    __shared__ float4 stage[2][RASTER_BATCH * 8];
+    __shared__ float4 stage[2][RASTER_BATCH * REC_PITCH];
     __shared__ uint8_t survivors[RASTER_MAX_THREADS / 32][RASTER_BATCH];
 
     const int tr = threadIdx.x, lane = tr & 31;
@@ -70,30 +70,25 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, 4) raster_forward_kernel(c
         }
         // warp-level culling: the warp walks only the records that can reach alpha >= 1/255 on its patch
         const int nsurv = __all_sync(0xffffffffu, done) ? 0 : build_survivors<BLUR>(S, 0, cnt, wr, p.mean2d, my_list, lane);
-        if (!done) {
-            for (int si = 0; si < nsurv; ++si) {
-                const int i = my_list[si];
-                const int sw = i & 7;
-                const float4 *__restrict__ R = S + (i << 3);
-                const float4 q0 = R[sw], q1 = R[1 ^ sw], q2 = R[2 ^ sw], q3 = R[3 ^ sw];
-                PairEval pe;
-                eval_pair<BLUR>(q0, q1, q2, q3, pc, p.mean2d, pe);
-                const float next_T = __fmul_rn(T, __fsub_rn(1.f, pe.alpha));
-                if (next_T <= T_STOP) {  // tested even for skipped Gaussians (reference texture.cu:216-221)
-                    done = true;
-                    break;
-                }
-                if (pair_skipped(pe)) continue;
-
-                // Record which pixels of this warp blend entry first+i (read by the backward pass).  The lanes on this
-                // path are normally converged, so one lane ORs the whole group's mask; the OR keeps the word correct
-                // even if the hardware runs the group in several pieces.
-                if (p.masks) {
-                    const unsigned grp = __activemask();
-                    if (lane == __ffs(grp) - 1) atomicOr(p.masks + (size_t)(first + i) * MASK_WARPS + (tr >> 5), grp);
-                }
-
-                const float4 q4 = R[4 ^ sw], q5 = R[5 ^ sw], q6 = R[6 ^ sw], q7 = R[7 ^ sw];
+        // The survivor walk is warp-uniform: finished pixels stay in the loop (predicated off) so that the blend
+        // decision of all 32 pixels is one ballot - the mask word the backward pass reads - written with one plain
+        // store per (entry, warp) instead of an atomic OR from inside the divergent blend path.
+        for (int si = 0; si < nsurv; ++si) {
+            if (__all_sync(0xffffffffu, done)) break;
+            const int i = my_list[si];
+            const float4 *__restrict__ R = S + i * REC_PITCH;
+            const float4 q0 = R[0], q1 = R[1], q2 = R[2], q3 = R[3];
+            PairEval pe;
+            eval_pair<BLUR>(q0, q1, q2, q3, pc, p.mean2d, pe);
+            const float next_T = __fmul_rn(T, __fsub_rn(1.f, pe.alpha));
+            // the stop rule is tested even for skipped Gaussians (reference texture.cu:216-221)
+            done = done || next_T <= T_STOP;
+            const bool blend = !done && !pair_skipped(pe);
+            const unsigned bm = __ballot_sync(0xffffffffu, blend);
+            if (bm == 0u) continue;
+            if (p.masks && lane == 0) p.masks[(size_t)(first + i) * MASK_WARPS + (tr >> 5)] = bm;
+            if (blend) {
+                const float4 q4 = R[4], q5 = R[5], q6 = R[6], q7 = R[7];
                 const float vis = pe.alpha * T;
                 acc_c0 = fmaf(q6.x, vis, acc_c0);
                 acc_c1 = fmaf(q6.y, vis, acc_c1);

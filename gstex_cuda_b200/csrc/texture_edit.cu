@@ -20,7 +20,7 @@ struct EditIn {
 
 template <bool BLUR>
 __global__ void __launch_bounds__(RASTER_MAX_THREADS, 4) texture_edit_kernel(const RasterCommon p, const EditIn in) {
-    __shared__ float4 stage[2][RASTER_BATCH * 8];
+    __shared__ float4 stage[2][RASTER_BATCH * REC_PITCH];
     __shared__ uint8_t survivors[RASTER_MAX_THREADS / 32][RASTER_BATCH];
 
     const int tr = threadIdx.x, lane = tr & 31;
@@ -61,9 +61,8 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, 4) texture_edit_kernel(con
         if (!done) {
             for (int si = 0; si < nsurv; ++si) {
                 const int i = my_list[si];
-                const int sw = i & 7;
-                const float4 *__restrict__ R = S + (i << 3);
-                const float4 q0 = R[sw], q1 = R[1 ^ sw], q2 = R[2 ^ sw], q3 = R[3 ^ sw];
+                const float4 *__restrict__ R = S + i * REC_PITCH;
+                const float4 q0 = R[0], q1 = R[1], q2 = R[2], q3 = R[3];
                 PairEval pe;
                 eval_pair<BLUR>(q0, q1, q2, q3, pc, p.mean2d, pe);
                 const float next_T = __fmul_rn(T, __fsub_rn(1.f, pe.alpha));
@@ -74,7 +73,7 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, 4) texture_edit_kernel(con
                 if (pair_skipped(pe)) continue;
                 const float t_view = pe.t * pc.vdep;
                 if (t_view >= zlo && t_view <= zhi) {  // texture_edit.cu:191
-                    const float4 q4 = R[4 ^ sw], q5 = R[5 ^ sw], q6 = R[6 ^ sw];
+                    const float4 q4 = R[4], q5 = R[5], q6 = R[6];
                     const float nu = fmaf(q4.x, pe.ex, fmaf(q4.y, pe.ey, q4.z));
                     const float nv = fmaf(q5.x, pe.ex, fmaf(q5.y, pe.ey, q5.z));
                     const float u = clamp01(fmaf(nu, pe.rD, q4.w)), v = clamp01(fmaf(nv, pe.rD, q5.w));
