@@ -36,11 +36,24 @@ namespace gstex {
 // and reach the pair lanes by warp shuffles.  Per pixel the pairs are processed in exactly the reference's order.
 // ------------------------------------------------------------------------------------------
 constexpr int BWD_WARPS = RASTER_MAX_THREADS / 32;
-constexpr int BWD_QCAP = 128;          // pairs per chunk (4 dense iterations)
-constexpr int BWD_ECAP = 16;           // list entries (Gaussians) per chunk: their records are staged per warp
-constexpr int BWD_BATCH = 64;          // list entries whose mask words a warp fetches at a time
+// tuning knobs (overridable with -D for experiments; the defaults are what ships)
+#ifndef GSTEX_BWD_QCAP
+#define GSTEX_BWD_QCAP 128
+#endif
+#ifndef GSTEX_BWD_ECAP
+#define GSTEX_BWD_ECAP 16
+#endif
+#ifndef GSTEX_BWD_BATCH
+#define GSTEX_BWD_BATCH 64
+#endif
+#ifndef GSTEX_BWD_MINB
+#define GSTEX_BWD_MINB 3
+#endif
+constexpr int BWD_QCAP = GSTEX_BWD_QCAP;    // pairs per chunk (4 dense iterations)
+constexpr int BWD_ECAP = GSTEX_BWD_ECAP;    // list entries (Gaussians) per chunk: their records are staged per warp
+constexpr int BWD_BATCH = GSTEX_BWD_BATCH;  // list entries whose mask words a warp fetches at a time
 #ifndef GSTEX_BWD_FULL
-#define GSTEX_BWD_FULL 20
+#define GSTEX_BWD_FULL 14
 #endif
 constexpr int BWD_FULL = GSTEX_BWD_FULL;  // entries covering at least this many of the 32 pixels run lane = pixel
 
@@ -236,7 +249,7 @@ __device__ __forceinline__ float4 warp_reduce_quads(const float4 (&r)[8], int la
 }
 
 template <bool C3, bool BLUR>
-__global__ void __launch_bounds__(RASTER_MAX_THREADS, 3) raster_backward_kernel(const RasterCommon p, const BackwardIn in,
+__global__ void __launch_bounds__(RASTER_MAX_THREADS, GSTEX_BWD_MINB) raster_backward_kernel(const RasterCommon p, const BackwardIn in,
                                                                                const BackwardOut o) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using WS = BwdWarpSmem<BLUR>;
