@@ -32,6 +32,7 @@ _PROTOS = {
     "gstex_scan_temp_bytes": (c_sz, [c_i]),
     "gstex_cumsum_i32": (c_i, [c_i, c_fp, c_fp, c_fp, c_sz, c_fp]),
     "gstex_map_gaussian_to_intersects": (c_i, [c_i, c_i64, c_fp, c_fp, c_fp, c_fp, c_i, c_i, c_i, c_fp, c_fp, c_fp]),
+    "gstex_map_gaussian_to_intersects_wrapped": (c_i, [c_i, c_i64, c_fp, c_fp, c_fp, c_fp, c_i, c_i, c_i, c_fp, c_fp, c_fp]),
     "gstex_sort_temp_bytes": (c_sz, [c_i64]),
     "gstex_sort_pairs": (c_i, [c_i64, c_fp, c_fp, c_fp, c_fp, c_i, c_fp, c_fp, c_sz, c_fp]),
     "gstex_get_tile_bin_edges": (c_i, [c_i64, c_fp, c_fp, c_fp, c_fp]),

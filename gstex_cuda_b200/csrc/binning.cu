@@ -102,8 +102,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(int n, const i
 }
 
 // ------------------------------------------------------------------------------------------
-// key emission: one thread per Gaussian (reference forward.cu:13-71, wrapped = false)
+// key emission: one thread per Gaussian (reference forward.cu:13-71; WRAPPED = the torus mode of forward.cu:34-36, 53-62)
 // ------------------------------------------------------------------------------------------
+template <bool WRAPPED>
 __global__ void __launch_bounds__(256) emit_keys_kernel(int n, const float2 *__restrict__ centers,
                                                         const float2 *__restrict__ extents,
                                                         const float *__restrict__ depths,
@@ -116,12 +117,20 @@ __global__ void __launch_bounds__(256) emit_keys_kernel(int n, const float2 *__r
     const float2 c = centers[i], e = extents[i];
     if (e.x <= 1e-4 && e.y <= 1e-4) return;
     int x0, y0, x1, y1;
-    tile_bbox(c.x, c.y, e.x, e.y, tiles_x, tiles_y, fbw, x0, y0, x1, y1);
+    if (WRAPPED) tile_bbox_wrapped(c.x, c.y, e.x, e.y, fbw, x0, y0, x1, y1);
+    else tile_bbox(c.x, c.y, e.x, e.y, tiles_x, tiles_y, fbw, x0, y0, x1, y1);
     int32_t cur = i == 0 ? 0 : cum_tiles_hit[i - 1];
     const int64_t depth_id = (int64_t)__float_as_int(depths[i]);  // sign-extends like the reference
     for (int ty = y0; ty < y1; ++ty)
         for (int tx = x0; tx < x1; ++tx) {
-            const int64_t tile = (int64_t)ty * tiles_x + tx;
+            int wy = ty, wx = tx;
+            if (WRAPPED) {
+                // The reference takes `ti % tile_bounds.y` with an unsigned (dim3) divisor (forward.cu:56-61): a negative
+                // index is reduced modulo 2^32 first and its sign fix-up never fires.  Reproduced bit for bit.
+                wy = (int)((unsigned)wy % (unsigned)tiles_y);
+                wx = (int)((unsigned)wx % (unsigned)tiles_x);
+            }
+            const int64_t tile = (int64_t)wy * tiles_x + wx;
             if (cur >= 0 && cur < cap) {
                 isect_ids[cur] = (tile << 32) | depth_id;
                 gaussian_ids[cur] = i;
@@ -415,19 +424,42 @@ extern "C" int gstex_cumsum_i32(int n, const int32_t *in, int32_t *out, void *te
     return GSTEX_OK;
 }
 
+static int map_intersects_impl(int n, int64_t num_intersects, const float *centers, const float *extents,
+                               const float *depths, const int32_t *cum_tiles_hit, int tiles_x, int tiles_y,
+                               int block_width, int wrapped, int64_t *isect_ids, int32_t *gaussian_ids,
+                               gstex_stream_t stream) {
+    GSTEX_REQUIRE(n >= 0 && block_width > 0 && tiles_x >= 0 && tiles_y >= 0, GSTEX_E_INVALID,
+                  "map_gaussian_to_intersects: n = %d, bw = %d", n, block_width);
+    GSTEX_REQUIRE(!wrapped || (tiles_x > 0 && tiles_y > 0), GSTEX_E_INVALID,
+                  "map_gaussian_to_intersects: wrapped binning needs a non-empty tile grid (%d x %d)", tiles_x, tiles_y);
+    if (n == 0) return GSTEX_OK;
+    const float2 *c2 = (const float2 *)centers, *e2 = (const float2 *)extents;
+    if (wrapped)
+        emit_keys_kernel<true><<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(
+            n, c2, e2, depths, cum_tiles_hit, tiles_x, tiles_y, (float)block_width, num_intersects, isect_ids, gaussian_ids);
+    else
+        emit_keys_kernel<false><<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(
+            n, c2, e2, depths, cum_tiles_hit, tiles_x, tiles_y, (float)block_width, num_intersects, isect_ids, gaussian_ids);
+    GSTEX_LAUNCH_OK("emit_keys_kernel");
+    return GSTEX_OK;
+}
+
 extern "C" int gstex_map_gaussian_to_intersects(int n, int64_t num_intersects, const float *centers,
                                                 const float *extents, const float *depths,
                                                 const int32_t *cum_tiles_hit, int tiles_x, int tiles_y,
                                                 int block_width, int64_t *isect_ids, int32_t *gaussian_ids,
                                                 gstex_stream_t stream) {
-    GSTEX_REQUIRE(n >= 0 && block_width > 0 && tiles_x >= 0 && tiles_y >= 0, GSTEX_E_INVALID,
-                  "map_gaussian_to_intersects: n = %d, bw = %d", n, block_width);
-    if (n == 0) return GSTEX_OK;
-    emit_keys_kernel<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(
-        n, (const float2 *)centers, (const float2 *)extents, depths, cum_tiles_hit, tiles_x, tiles_y,
-        (float)block_width, num_intersects, isect_ids, gaussian_ids);
-    GSTEX_LAUNCH_OK("emit_keys_kernel");
-    return GSTEX_OK;
+    return map_intersects_impl(n, num_intersects, centers, extents, depths, cum_tiles_hit, tiles_x, tiles_y, block_width,
+                               0, isect_ids, gaussian_ids, stream);
+}
+
+extern "C" int gstex_map_gaussian_to_intersects_wrapped(int n, int64_t num_intersects, const float *centers,
+                                                        const float *extents, const float *depths,
+                                                        const int32_t *cum_tiles_hit, int tiles_x, int tiles_y,
+                                                        int block_width, int64_t *isect_ids, int32_t *gaussian_ids,
+                                                        gstex_stream_t stream) {
+    return map_intersects_impl(n, num_intersects, centers, extents, depths, cum_tiles_hit, tiles_x, tiles_y, block_width,
+                               1, isect_ids, gaussian_ids, stream);
 }
 
 extern "C" size_t gstex_sort_temp_bytes(int64_t m) { return sort_layout(m).total; }

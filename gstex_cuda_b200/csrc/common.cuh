@@ -123,6 +123,19 @@ __device__ __forceinline__ void tile_bbox(float cx, float cy, float ex, float ey
     y1 = min(max(0, (int)(__fadd_rn(__fadd_rn(tcy, tey), 1.f))), tiles_y);
 }
 
+// torus variant (reference helpers.cuh:53-73, 94-111): no clamping, a box that starts at or before tile 0 grows by one
+__device__ __forceinline__ void tile_bbox_wrapped(float cx, float cy, float ex, float ey, float fbw, int &x0, int &y0,
+                                                  int &x1, int &y1) {
+    const float tcx = __fdiv_rn(cx, fbw), tcy = __fdiv_rn(cy, fbw);
+    const float tex = __fdiv_rn(ex, fbw), tey = __fdiv_rn(ey, fbw);
+    x0 = (int)(__fsub_rn(tcx, tex));
+    if (x0 <= 0) x0 -= 1;
+    x1 = (int)(__fadd_rn(__fadd_rn(tcx, tex), 1.f));
+    y0 = (int)(__fsub_rn(tcy, tey));
+    if (y0 <= 0) y0 -= 1;
+    y1 = (int)(__fadd_rn(__fadd_rn(tcy, tey), 1.f));
+}
+
 // ------------------------------------------------------------------------------------------
 // Packed per-view Gaussian record: 32 floats = 128 B = one cache line, eight 16-byte quads.
 // Quads 0-3 feed the alpha test of every (pixel, Gaussian) pair, quads 4-7 only the blend.

@@ -38,7 +38,8 @@ extern "C" int gstex_raster_forward(int img_height, int img_width, int block_wid
                                     float *final_Ts, int32_t *final_idx, int32_t *depth_idx, float *out_reg_s,
                                     uint32_t *masks, int64_t mask_entries, const int32_t *d_num_intersects,
                                     gstex_stream_t stream) {
-    int rc = check_raster_args("raster_forward", img_height, img_width, block_width, 0, 0, channels, settings);
+    int rc = check_raster_args("raster_forward", img_height, img_width, block_width, 0, 0, channels, settings,
+                               GSTEX_SET_SUPPORTED_FORWARD);
     if (rc != GSTEX_OK) return rc;
     const RasterCommon p = make_raster_common(img_height, img_width, block_width, channels, settings,
                                               gaussian_ids_sorted, tile_bins, (const float4 *)recs,

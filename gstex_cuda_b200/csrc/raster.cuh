@@ -223,7 +223,7 @@ __device__ __forceinline__ bool record_culled(const float4 q0, const float4 q1, 
 }
 
 // Builds the warp's survivor list for staged records [lo, hi) of stage S; returns the survivor count.
-template <bool BLUR>
+template <bool BLUR, bool CULL = true>
 __device__ __forceinline__ int build_survivors(const float4 *__restrict__ S, int lo, int hi, const WarpRect &wr,
                                                const float2 *__restrict__ mean2d, uint8_t *__restrict__ list,
                                                int lane) {
@@ -231,8 +231,8 @@ __device__ __forceinline__ int build_survivors(const float4 *__restrict__ S, int
     int n = 0;
     for (int k = lo; k < hi; k += 32) {
         const int r = k + lane;
-        bool keep = false;
-        if (r < hi) {
+        bool keep = !CULL && r < hi;  // CULL = false: the alpha-visualisation mode redefines alpha, keep everything
+        if (CULL && r < hi) {
             const float4 q0 = S[quad_slot(r, 0)], q1 = S[quad_slot(r, 1)], q2 = S[quad_slot(r, 2)],
                          q3 = S[quad_slot(r, 3)];
             keep = !record_culled<BLUR>(q0, q1, q2, q3, wr, mean2d);
@@ -317,6 +317,6 @@ int launch_pad_texture(int64_t num_texels, const float *tex, float4 *tex4, cudaS
 int launch_unpad_texture_grad(int64_t num_texels, const float4 *g4, float *v_texture, int accumulate, cudaStream_t s);
 FwdLayout forward_layout(int n, int64_t num_texels, int channels, int64_t num_intersects);
 int check_raster_args(const char *who, int img_height, int img_width, int block_width, int n, int64_t num_texels,
-                      int channels, int settings);
+                      int channels, int settings, int supported_settings = GSTEX_SET_SUPPORTED);
 
 }  // namespace gstex

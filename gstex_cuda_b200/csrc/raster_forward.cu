@@ -17,7 +17,30 @@ namespace gstex {
 
 // C3 = true : 3-channel texture read through the padded float4 copy, accumulators in registers.
 // C3 = false: runtime channel count (<= 64) read from the caller's (X,C) array (slow generic path).
-template <bool C3, bool BLUR>
+// Visualisation helper (VIS builds only): distance, in pixels, from this pixel to the nearest pixel of its 7x7
+// neighbourhood that lies outside the Gaussian's hard footprint sigma <= sigma_thresh (reference local_outline,
+// texture_helpers.cuh:390-416).  The neighbours' sigma comes from the same affine forms, evaluated at the shifted
+// offset; the plane-denominator clamp uses this pixel's ray norm (the neighbours' differ in the 4th digit of 1e-6).
+__device__ __forceinline__ float outline_distance(const float4 q0, const float4 q1, const float4 q2, const float4 q3,
+                                                  const PixelConsts &pc, float sigma_thresh) {
+    float min_dis = 1000.0f;
+    for (int dx = -3; dx <= 3; ++dx)
+        for (int dy = -3; dy <= 3; ++dy) {
+            const float ex = __fsub_rn(pc.px + (float)dx, q0.x), ey = __fsub_rn(pc.py + (float)dy, q0.y);
+            const float n1 = fmaf(q1.x, ex, fmaf(q1.y, ey, q1.z));
+            const float n2 = fmaf(q2.x, ex, fmaf(q2.y, ey, q2.z));
+            float d = fmaf(q3.x, ex, fmaf(q3.y, ey, q1.w));
+            if (fabsf(d) < pc.eps) d = copysignf(pc.eps, d);
+            const float rd = __fdiv_rn(1.f, d);
+            const float l1 = n1 * rd, l2 = n2 * rd;
+            if (LN2_F * fmaf(l1, l1, l2 * l2) > sigma_thresh) min_dis = fminf(min_dis, sqrtf((float)(dx * dx + dy * dy)));
+        }
+    return min_dis;
+}
+
+// VIS = true: the viewer-only settings bits 15-29 (texture.cu:58-63, :201-241, :269-274) are honoured; that build skips
+// the warp-level culling (its bound assumes alpha = opac * exp(-sigma)) and writes no blend masks (forward only).
+template <bool C3, bool BLUR, bool VIS = false>
 __global__ void __launch_bounds__(RASTER_MAX_THREADS, 4) raster_forward_kernel(const RasterCommon p, const ForwardOut o) {
     __shared__ float4 stage[2][RASTER_BATCH * REC_PITCH];
     __shared__ uint8_t survivors[RASTER_MAX_THREADS / 32][RASTER_BATCH];
@@ -34,6 +57,13 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, 4) raster_forward_kernel(c
     const bool use_ndc = (p.settings & GSTEX_SET_NDC) != 0;
     const bool bilinear = !(p.settings & GSTEX_SET_NEAREST);
     const int C = C3 ? 3 : p.channels;
+    const bool vis_normals = VIS && (p.settings & GSTEX_SET_VIS_NORMALS) != 0;
+    const bool vis_alpha = VIS && (p.settings & GSTEX_SET_VIS_ALPHA) != 0;
+    const bool vis_opac = VIS && (p.settings & GSTEX_SET_VIS_OPACITY_THRESH) != 0;
+    const bool vis_white = VIS && (p.settings & GSTEX_SET_VIS_WHITE_OUTLINE) != 0;
+    const float alpha_bound = (float)((p.settings & GSTEX_SET_VIS_ALPHA_BOUND) >> 17) / 8.0f;
+    const float outline_bound = (float)((p.settings & GSTEX_SET_VIS_OUTLINE_BOUND) >> 26) / 4.0f;
+    const float sigma_thresh = 0.5f * alpha_bound * alpha_bound;
 
     const int2 range = p.bins[tile];
     const int total = range.y - range.x;
@@ -69,7 +99,7 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, 4) raster_forward_kernel(c
             prefetch_texture_block(p.tex4, __float_as_int(q6.w), __float_as_int(q3.z), __float_as_int(q3.w));
         }
         // warp-level culling: the warp walks only the records that can reach alpha >= 1/255 on its patch
-        const int nsurv = __all_sync(0xffffffffu, done) ? 0 : build_survivors<BLUR>(S, 0, cnt, wr, p.mean2d, my_list, lane);
+        const int nsurv = __all_sync(0xffffffffu, done) ? 0 : build_survivors<BLUR, !VIS>(S, 0, cnt, wr, p.mean2d, my_list, lane);
         // The survivor walk is warp-uniform: finished pixels stay in the loop (predicated off) so that the blend
         // decision of all 32 pixels is one ballot - the mask word the backward pass reads - written with one plain
         // store per (entry, warp) instead of an atomic OR from inside the divergent blend path.
@@ -80,22 +110,35 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, 4) raster_forward_kernel(c
             const float4 q0 = R[0], q1 = R[1], q2 = R[2], q3 = R[3];
             PairEval pe;
             eval_pair<BLUR>(q0, q1, q2, q3, pc, p.mean2d, pe);
+            if (VIS && vis_alpha) {  // reference texture.cu:201-211
+                const float sigma = LN2_F * fmaf(pe.l1, pe.l1, pe.l2 * pe.l2);
+                pe.alpha = (sigma > sigma_thresh || (vis_opac && q0.w < 0.5f)) ? 0.f : ALPHA_CAP;
+            }
             const float next_T = __fmul_rn(T, __fsub_rn(1.f, pe.alpha));
             // the stop rule is tested even for skipped Gaussians (reference texture.cu:216-221)
             done = done || next_T <= T_STOP;
             const bool blend = !done && !pair_skipped(pe);
             const unsigned bm = __ballot_sync(0xffffffffu, blend);
             if (bm == 0u) continue;
-            if (p.masks && lane == 0) p.masks[(size_t)(first + i) * MASK_WARPS + (tr >> 5)] = bm;
+            if (!VIS && p.masks && lane == 0) p.masks[(size_t)(first + i) * MASK_WARPS + (tr >> 5)] = bm;
             if (blend) {
                 const float4 q4 = R[4], q5 = R[5], q6 = R[6], q7 = R[7];
                 const float vis = pe.alpha * T;
-                acc_c0 = fmaf(q6.x, vis, acc_c0);
-                acc_c1 = fmaf(q6.y, vis, acc_c1);
-                acc_c2 = fmaf(q6.z, vis, acc_c2);
-                acc_n0 = fmaf(q7.x, vis, acc_n0);
-                acc_n1 = fmaf(q7.y, vis, acc_n1);
-                acc_n2 = fmaf(q7.z, vis, acc_n2);
+                // VIS: outline pixels of the hard footprint carry no colour (or white), texture.cu:226-235, :269-274
+                bool draw = true, white = false;
+                if (VIS && vis_alpha) {
+                    draw = outline_distance(q0, q1, q2, q3, pc, sigma_thresh) > outline_bound;
+                    white = !draw && vis_white;
+                }
+                const float cvis = draw ? vis : 0.f, wvis = white ? vis : 0.f;  // == vis, 0 outside VIS builds
+                acc_c0 = VIS ? fmaf(q6.x, cvis, acc_c0) + wvis : fmaf(q6.x, vis, acc_c0);
+                acc_c1 = VIS ? fmaf(q6.y, cvis, acc_c1) + wvis : fmaf(q6.y, vis, acc_c1);
+                acc_c2 = VIS ? fmaf(q6.z, cvis, acc_c2) + wvis : fmaf(q6.z, vis, acc_c2);
+                // VIS: normals face the camera; D = a3 . R_w(p) has the sign of the reference's dot(ray, ax3) (:236-241)
+                const float nvis = (vis_normals && pe.rD > 0.f) ? -vis : vis;
+                acc_n0 = fmaf(q7.x, nvis, acc_n0);
+                acc_n1 = fmaf(q7.y, nvis, acc_n1);
+                acc_n2 = fmaf(q7.z, nvis, acc_n2);
                 const float nu = fmaf(q4.x, pe.ex, fmaf(q4.y, pe.ey, q4.z));
                 const float nv = fmaf(q5.x, pe.ex, fmaf(q5.y, pe.ey, q5.z));
                 const float u = clamp01(fmaf(nu, pe.rD, q4.w)), v = clamp01(fmaf(nv, pe.rD, q5.w));
@@ -104,10 +147,14 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, 4) raster_forward_kernel(c
                 if (C3) {
                     const float4 t0 = __ldg(p.tex4 + tf.idx[0]), t1 = __ldg(p.tex4 + tf.idx[1]);
                     const float4 t2 = __ldg(p.tex4 + tf.idx[2]), t3 = __ldg(p.tex4 + tf.idx[3]);
-                    const float w0 = tf.w[0] * vis, w1 = tf.w[1] * vis, w2 = tf.w[2] * vis, w3 = tf.w[3] * vis;
+                    const float tvis = VIS ? cvis : vis;
+                    const float w0 = tf.w[0] * tvis, w1 = tf.w[1] * tvis, w2 = tf.w[2] * tvis, w3 = tf.w[3] * tvis;
                     acc_t[0] += w0 * t0.x + w1 * t1.x + w2 * t2.x + w3 * t3.x;
                     acc_t[1] += w0 * t0.y + w1 * t1.y + w2 * t2.y + w3 * t3.y;
                     acc_t[2] += w0 * t0.z + w1 * t1.z + w2 * t2.z + w3 * t3.z;
+                    if (VIS) {
+                        acc_t[0] += wvis; acc_t[1] += wvis; acc_t[2] += wvis;
+                    }
                 } else {
                     const float *__restrict__ tx = p.tex;
                     for (int c = 0; c < C; ++c) {
@@ -115,7 +162,7 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, 4) raster_forward_kernel(c
                                           tf.w[1] * __ldg(tx + (size_t)tf.idx[1] * C + c) +
                                           tf.w[2] * __ldg(tx + (size_t)tf.idx[2] * C + c) +
                                           tf.w[3] * __ldg(tx + (size_t)tf.idx[3] * C + c);
-                        acc_t[c] = fmaf(vis, val, acc_t[c]);
+                        acc_t[c] = VIS ? fmaf(cvis, val, acc_t[c]) + wvis : fmaf(vis, val, acc_t[c]);
                     }
                 }
                 const float t_view = pe.t * pc.vdep;
@@ -208,7 +255,15 @@ int launch_raster_forward(const RasterCommon &p, const ForwardOut &o, int64_t ma
     }
     const dim3 grid(p.tiles_x, ceil_div(p.img_h, p.bw));
     const bool blur = (p.settings & GSTEX_SET_BLUR) != 0;
-    if (p.channels == 3) {
+    if (p.settings & GSTEX_SET_VIS_ALL) {  // viewer-only modes: one generic build per channel layout, forward only
+        if (p.channels == 3) {
+            if (blur) raster_forward_kernel<true, true, true><<<grid, p.nthreads, 0, s>>>(p, o);
+            else raster_forward_kernel<true, false, true><<<grid, p.nthreads, 0, s>>>(p, o);
+        } else {
+            if (blur) raster_forward_kernel<false, true, true><<<grid, p.nthreads, 0, s>>>(p, o);
+            else raster_forward_kernel<false, false, true><<<grid, p.nthreads, 0, s>>>(p, o);
+        }
+    } else if (p.channels == 3) {
         if (blur) raster_forward_kernel<true, true><<<grid, p.nthreads, 0, s>>>(p, o);
         else raster_forward_kernel<true, false><<<grid, p.nthreads, 0, s>>>(p, o);
     } else {
@@ -235,7 +290,7 @@ FwdLayout forward_layout(int n, int64_t num_texels, int channels, int64_t num_in
 }
 
 int check_raster_args(const char *who, int img_height, int img_width, int block_width, int n, int64_t num_texels,
-                      int channels, int settings) {
+                      int channels, int settings, int supported_settings) {
     GSTEX_REQUIRE(img_height > 0 && img_width > 0, GSTEX_E_INVALID, "%s: image %dx%d", who, img_height, img_width);
     GSTEX_REQUIRE(block_width > 1 && block_width <= 16, GSTEX_E_INVALID,
                   "%s: block_width must be between 2 and 16 (got %d)", who, block_width);
@@ -243,9 +298,9 @@ int check_raster_args(const char *who, int img_height, int img_width, int block_
                   "%s: n = %d, texels = %lld", who, n, (long long)num_texels);
     GSTEX_REQUIRE(channels >= 1 && channels <= RASTER_MAX_C, GSTEX_E_INVALID,
                   "%s: texture channels must be in [1, %d] (got %d)", who, RASTER_MAX_C, channels);
-    GSTEX_REQUIRE((settings & ~GSTEX_SET_SUPPORTED) == 0, GSTEX_E_UNSUPPORTED,
-                  "%s: settings 0x%x has bits outside the training path (supported mask 0x%x); the visualisation "
-                  "modes (bits 15-29) are not built", who, settings, GSTEX_SET_SUPPORTED);
+    GSTEX_REQUIRE((settings & ~supported_settings) == 0, GSTEX_E_UNSUPPORTED,
+                  "%s: settings 0x%x has bits this entry point does not implement (supported mask 0x%x); the "
+                  "visualisation bits 15-29 are forward-only", who, settings, supported_settings);
     return GSTEX_OK;
 }
 
@@ -267,7 +322,8 @@ extern "C" int gstex_texture_forward(int img_height, int img_width, int block_wi
                                      float *out_depth, float *out_reg, float *out_texture, float *out_normal,
                                      float *final_Ts, int32_t *final_idx, int32_t *depth_idx, float *out_reg_s,
                                      void *temp, size_t temp_bytes, gstex_stream_t stream) {
-    int rc = check_raster_args("texture_forward", img_height, img_width, block_width, n, num_texels, channels, settings);
+    int rc = check_raster_args("texture_forward", img_height, img_width, block_width, n, num_texels, channels, settings,
+                               GSTEX_SET_SUPPORTED_FORWARD);
     if (rc != GSTEX_OK) return rc;
     GSTEX_REQUIRE(num_intersects >= 0 && num_intersects < ((int64_t)1 << 31), GSTEX_E_INVALID,
                   "texture_forward: num_intersects = %lld", (long long)num_intersects);

@@ -76,17 +76,16 @@ def compute_sh_backward(num_points, degree, degrees_to_use, viewdirs, v_colors):
 
 def map_gaussian_to_intersects(num_points, num_intersects, centers, extents, depths, cum_tiles_hit, tile_bounds,
                                block_width, wrapped=False) -> Tuple[torch.Tensor, torch.Tensor]:
-    """bindings.cu:77-121"""
-    if wrapped:
-        raise NotImplementedError("wrapped (torus) binning is an editing/visualisation mode outside the training "
-                                  "path (SURVEY 8f rank 4)")
+    """bindings.cu:77-121.  ``wrapped`` selects the torus tile boxes of forward.cu:34-36, 53-62."""
     _chk("centers", centers, torch.float32), _chk("extents", extents, torch.float32)
     _chk("depths", depths, torch.float32), _chk("cum_tiles_hit", cum_tiles_hit, torch.int32)
     dev = centers.device
     isect = torch.zeros((num_intersects,), dtype=torch.int64, device=dev)
     gids = torch.zeros((num_intersects,), dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
-        rc = _lib.load().gstex_map_gaussian_to_intersects(
+        lib = _lib.load()
+        fn = lib.gstex_map_gaussian_to_intersects_wrapped if wrapped else lib.gstex_map_gaussian_to_intersects
+        rc = fn(
             int(num_points), int(num_intersects), _p(centers), _p(extents), _p(depths), _p(cum_tiles_hit),
             int(tile_bounds[0]), int(tile_bounds[1]), int(block_width), _p(isect), _p(gids), _stream(dev))
     _lib.check(rc, "map_gaussian_to_intersects")

@@ -30,7 +30,7 @@ extern "C" {
 #define GSTEX_E_INVALID (-1)   /* bad argument (size, block width, channel count ...) */
 #define GSTEX_E_CUDA (-2)      /* a CUDA runtime call / launch failed */
 #define GSTEX_E_WORKSPACE (-3) /* scratch buffer too small */
-#define GSTEX_E_UNSUPPORTED (-4) /* settings bits outside the training path (visualisation modes) */
+#define GSTEX_E_UNSUPPORTED (-4) /* settings bits the entry point does not implement (visualisation bits in a backward call) */
 
 typedef void *gstex_stream_t;
 
@@ -43,6 +43,16 @@ int gstex_abi_version(void);
 #define GSTEX_SET_BLUR (1 << 9)          /* 2-D screen-space blur floor */
 #define GSTEX_SET_NDC (1 << 10)          /* distortion on NDC depth */
 #define GSTEX_SET_SUPPORTED (GSTEX_SET_NEAREST | GSTEX_SET_PROPAGATE_UV | GSTEX_SET_BLUR | GSTEX_SET_NDC)
+/* visualisation bits, forward only (texture.cu:58-63, :201-241, :269-274); the backward entry points reject them */
+#define GSTEX_SET_VIS_NORMALS (1 << 15)        /* normals flipped towards the camera */
+#define GSTEX_SET_VIS_ALPHA (1 << 16)          /* hard-edged footprints: alpha = 0.99 inside sigma <= alpha_bound^2 / 2 */
+#define GSTEX_SET_VIS_ALPHA_BOUND (0x1f << 17) /* alpha_bound * 8 */
+#define GSTEX_SET_VIS_WHITE_OUTLINE (1 << 24)  /* outline pixels add white instead of nothing */
+#define GSTEX_SET_VIS_OPACITY_THRESH (1 << 25) /* hide Gaussians of opacity < 0.5 */
+#define GSTEX_SET_VIS_OUTLINE_BOUND (0xf << 26) /* outline width * 4 (pixels) */
+#define GSTEX_SET_VIS_ALL (GSTEX_SET_VIS_NORMALS | GSTEX_SET_VIS_ALPHA | GSTEX_SET_VIS_ALPHA_BOUND | \
+                           GSTEX_SET_VIS_WHITE_OUTLINE | GSTEX_SET_VIS_OPACITY_THRESH | GSTEX_SET_VIS_OUTLINE_BOUND)
+#define GSTEX_SET_SUPPORTED_FORWARD (GSTEX_SET_SUPPORTED | GSTEX_SET_VIS_ALL)
 
 /* ======================================================================================== *
  * (1) projection, screen AABB, tile count
@@ -91,6 +101,14 @@ int gstex_map_gaussian_to_intersects(int n, int64_t num_intersects, const float 
                                      const float *depths, const int32_t *cum_tiles_hit, int tiles_x, int tiles_y,
                                      int block_width, int64_t *isect_ids, int32_t *gaussian_ids,
                                      gstex_stream_t stream);
+/* the same with wrapped=true (torus tile boxes, forward.cu:34-36, 53-62 + helpers.cuh:53-73, 94-111): tile boxes are not
+ * clamped and tile indices are taken modulo the grid.  cum_tiles_hit must be the running sum of the wrapped box sizes
+ * (the reference leaves that to the caller as well). */
+int gstex_map_gaussian_to_intersects_wrapped(int n, int64_t num_intersects, const float *centers,
+                                             const float *extents, const float *depths,
+                                             const int32_t *cum_tiles_hit, int tiles_x, int tiles_y,
+                                             int block_width, int64_t *isect_ids, int32_t *gaussian_ids,
+                                             gstex_stream_t stream);
 
 /* replaces torch.sort(int64) + torch.gather, gstex_cuda/utils.py:159-160: stable ascending LSD radix sort
  * of signed 64-bit keys carrying int32 values.  `end_bit` (1..64): keys are known to be non-negative and

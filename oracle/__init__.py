@@ -88,14 +88,22 @@ def compute_cumulative_intersects(num_tiles_hit) -> Tuple[int, np.ndarray]:
     return int(total), out
 
 
+def num_tiles_hit_wrapped(centers, extents, block_width) -> np.ndarray:
+    """Tiles a Gaussian writes under wrapped=True (helpers.cuh:53-73): what cum_tiles_hit must sum."""
+    centers, extents = _f(centers), _f(extents)
+    out = np.zeros((centers.shape[0],), np.int32)
+    lib().orc_num_tiles_hit_wrapped(C.c_int(centers.shape[0]), _p(centers), _p(extents), C.c_int(block_width), _p(out))
+    return out
+
+
 def map_gaussian_to_intersects(num_points, num_intersects, centers, extents, depths, cum_tiles_hit, tile_bounds,
-                               block_width):
+                               block_width, wrapped=False):
     centers, extents, depths, cum = _f(centers), _f(extents), _f(depths), _i(cum_tiles_hit)
     isect = np.zeros((num_intersects,), np.int64)
     gids = np.zeros((num_intersects,), np.int32)
     lib().orc_map_gaussian_to_intersects(C.c_int(num_points), _p(centers), _p(extents), _p(depths), _p(cum),
                                          C.c_int(tile_bounds[0]), C.c_int(tile_bounds[1]), C.c_int(block_width),
-                                         _p(isect), _p(gids))
+                                         C.c_int(1 if wrapped else 0), _p(isect), _p(gids))
     return isect, gids
 
 
@@ -115,10 +123,10 @@ def get_tile_bin_edges(num_intersects, isect_ids_sorted, tile_bounds) -> np.ndar
 
 
 def bin_and_sort_gaussians(num_points, num_intersects, centers, extents, depths, cum_tiles_hit, tile_bounds,
-                           block_width):
+                           block_width, wrapped=False):
     """utils.py:106-162"""
     isect, gids = map_gaussian_to_intersects(num_points, num_intersects, centers, extents, depths, cum_tiles_hit,
-                                             tile_bounds, block_width)
+                                             tile_bounds, block_width, wrapped)
     isect_s, gids_s = sort_pairs(isect, gids)
     bins = get_tile_bin_edges(num_intersects, isect_s, tile_bounds)
     return isect, gids, isect_s, gids_s, bins

@@ -172,7 +172,8 @@ int orc_cumsum(int n, const int32_t *v, int32_t *out) {
 }
 
 /* ------------------------------------------------------------------------------------------
- * map_gaussian_to_intersects: forward.cu:13-71 (+ helpers.cuh:37-51, 75-92), wrapped=false.
+ * map_gaussian_to_intersects: forward.cu:13-71 (+ helpers.cuh:37-51, 75-92); wrapped (torus) tile boxes:
+ * helpers.cuh:53-73, 94-111 and the modulo of forward.cu:53-62.
  * Outputs must be zero-initialised by the caller (bindings.cu:96-99).
  * ---------------------------------------------------------------------------------------- */
 static inline void tile_bbox(float cx, float cy, float ex, float ey, int tx, int ty, int bw, int *x0,
@@ -185,21 +186,56 @@ static inline void tile_bbox(float cx, float cy, float ex, float ey, int tx, int
     *y1 = clampi((int)(tcy + tey + 1), 0, ty);
 }
 
+/* helpers.cuh:53-73: no clamping; a box that starts at or left of / above tile 0 grows by one tile */
+static inline void tile_bbox_wrapped(float cx, float cy, float ex, float ey, int bw, int *x0, int *y0, int *x1,
+                                     int *y1) {
+    float fbw = (float)bw;
+    float tcx = cx / fbw, tcy = cy / fbw, tex = ex / fbw, tey = ey / fbw;
+    *x0 = (int)(tcx - tex);
+    if (*x0 <= 0) *x0 -= 1;
+    *x1 = (int)(tcx + tex + 1);
+    *y0 = (int)(tcy - tey);
+    if (*y0 <= 0) *y0 -= 1;
+    *y1 = (int)(tcy + tey + 1);
+}
+
+/* tiles a Gaussian writes under `wrapped` (what the caller's cum_tiles_hit must be the running sum of) */
+void orc_num_tiles_hit_wrapped(int n, const float *centers, const float *extents, int bw, int32_t *num_tiles_hit) {
+    for (int i = 0; i < n; ++i) {
+        float ex = extents[2 * i], ey = extents[2 * i + 1];
+        int x0, y0, x1, y1;
+        tile_bbox_wrapped(centers[2 * i], centers[2 * i + 1], ex, ey, bw, &x0, &y0, &x1, &y1);
+        int c = (x1 > x0 ? x1 - x0 : 0) * (y1 > y0 ? y1 - y0 : 0);
+        if (ex <= 1e-4 && ey <= 1e-4) c = 0;
+        num_tiles_hit[i] = c;
+    }
+}
+
 void orc_map_gaussian_to_intersects(int n, const float *centers, const float *extents, const float *depths,
-                                    const int32_t *cum_tiles_hit, int tiles_x, int tiles_y, int bw,
+                                    const int32_t *cum_tiles_hit, int tiles_x, int tiles_y, int bw, int wrapped,
                                     int64_t *isect_ids, int32_t *gaussian_ids) {
     for (int i = 0; i < n; ++i) {
         float ex = extents[2 * i], ey = extents[2 * i + 1];
         if (ex <= 1e-4 && ey <= 1e-4) continue; /* forward.cu:32 (double literal on purpose) */
         int x0, y0, x1, y1;
-        tile_bbox(centers[2 * i], centers[2 * i + 1], ex, ey, tiles_x, tiles_y, bw, &x0, &y0, &x1, &y1);
+        if (wrapped) tile_bbox_wrapped(centers[2 * i], centers[2 * i + 1], ex, ey, bw, &x0, &y0, &x1, &y1);
+        else tile_bbox(centers[2 * i], centers[2 * i + 1], ex, ey, tiles_x, tiles_y, bw, &x0, &y0, &x1, &y1);
         int32_t cur = i == 0 ? 0 : cum_tiles_hit[i - 1];
         int32_t dbits;
         memcpy(&dbits, depths + i, 4);
         int64_t depth_id = (int64_t)dbits; /* sign-extends, forward.cu:48 */
         for (int ty = y0; ty < y1; ++ty)
             for (int tx = x0; tx < x1; ++tx) {
-                int64_t tile = (int64_t)ty * tiles_x + tx;
+                int wy = ty, wx = tx;
+                if (wrapped) {
+                    /* forward.cu:53-62.  tile_bounds is a dim3 (unsigned), so `ti % tile_bounds.y` converts a
+                     * negative ti to unsigned first and the reference's `if (ti < 0)` fix-up never fires: a tile
+                     * index of -1 lands on (2^32 - 1) mod tiles, which is the torus neighbour only when the
+                     * tile count divides 2^32.  Reproduced as is. */
+                    wy = (int)((unsigned)wy % (unsigned)tiles_y);
+                    wx = (int)((unsigned)wx % (unsigned)tiles_x);
+                }
+                int64_t tile = (int64_t)wy * tiles_x + wx;
                 isect_ids[cur] = (tile << 32) | depth_id;
                 gaussian_ids[cur] = i;
                 ++cur;
@@ -386,10 +422,10 @@ typedef struct {
 } pixray;
 
 /* texture_helpers.cuh:336-352 and texture.cu:67-74 */
-static inline pixray make_ray(const float *c2w, const float *viewmat, float fx, float fy, float cx, float cy,
-                              int col, int row) {
+static inline pixray make_ray_at(const float *c2w, const float *viewmat, float fx, float fy, float cx, float cy,
+                                 float px, float py) {
     pixray r;
-    r.px = (float)col + 0.5f; r.py = (float)row + 0.5f;
+    r.px = px; r.py = py;
     r.origin = v3_make(c2w[3], c2w[7], c2w[11]);
     float u = (r.px - cx) / fx, v = (r.py - cy) / fy;
     v3 d = xform_point(c2w, v3_make(u, v, 1.f));
@@ -398,6 +434,11 @@ static inline pixray make_ray(const float *c2w, const float *viewmat, float fx, 
     r.ray = v3_make(d.x / nrm, d.y / nrm, d.z / nrm);
     r.view_depth = viewmat[8] * r.ray.x + viewmat[9] * r.ray.y + viewmat[10] * r.ray.z;
     return r;
+}
+
+static inline pixray make_ray(const float *c2w, const float *viewmat, float fx, float fy, float cx, float cy,
+                              int col, int row) {
+    return make_ray_at(c2w, viewmat, fx, fy, cx, cy, (float)col + 0.5f, (float)row + 0.5f);
 }
 
 /* texture_helpers.cuh:302-313 */
@@ -444,14 +485,40 @@ static inline void pair_geometry(const pixray *r, const float *mean, const float
 #define SET_NEAREST (1 << 2)
 #define SET_BLUR (1 << 9)
 #define SET_NDC (1 << 10)
+#define SET_VIS (1 << 15)        /* texture.cu:58  normals flipped towards the camera */
+#define SET_ALPHA_VIS (1 << 16)  /* texture.cu:59  hard-edged footprints + outlines */
 #define ORC_MAX_C 64
 
 static const float T_NEAR = 0.01f, T_FAR = 1000.0f;
 
 /* ------------------------------------------------------------------------------------------
  * texture_forward: texture.cu:11-329.  All outputs are written for every in-image pixel.
- * Visualisation bits (15-29) are not restated (out of scope).
+ * Visualisation bits (texture.cu:58-63, :201-241, :269-274): 15 flips normals towards the camera, 16 draws hard-edged
+ * footprints (alpha = 0.99 inside sigma <= alpha_bound^2/2, bits 17-21 = alpha_bound*8) with an outline of width
+ * outline_bound (bits 26-29 = *4) that is black or, with bit 24, white; bit 25 hides Gaussians of opacity < 0.5.
  * ---------------------------------------------------------------------------------------- */
+/* texture_helpers.cuh:390-416 (local_outline) with :355-366 (get_pixel_to_texel) inlined */
+static float local_outline(const float *c2w, const float *viewmat, float fx, float fy, float cx, float cy, float px,
+                           float py, const pairgeom *g, float glob_scale, int width, float sigma_thresh) {
+    float min_dis = 1000.0f;
+    const float scale1 = g->s1 * glob_scale, scale2 = g->s2 * glob_scale;
+    for (int dx = -width; dx <= width; ++dx)
+        for (int dy = -width; dy <= width; ++dy) {
+            pixray r = make_ray_at(c2w, viewmat, fx, fy, cx, cy, px + (float)dx, py + (float)dy);
+            v3 diff = v3_make(g->mean.x - r.origin.x, g->mean.y - r.origin.y, g->mean.z - r.origin.z);
+            float t = v3_dot(g->a3, diff) / plane_denominator(g->a3, r.ray);
+            v3 pos = v3_make(r.origin.x + t * r.ray.x, r.origin.y + t * r.ray.y, r.origin.z + t * r.ray.z);
+            v3 delta = v3_make(pos.x - g->mean.x, pos.y - g->mean.y, pos.z - g->mean.z);
+            float as1 = v3_dot(delta, g->a1) / scale1, as2 = v3_dot(delta, g->a2) / scale2;
+            float sigma = 0.5f * (as1 * as1 + as2 * as2);
+            if (sigma > sigma_thresh) {
+                float cur = sqrtf((float)(dx * dx + dy * dy));
+                if (min_dis > cur) min_dis = cur;
+            }
+        }
+    return min_dis;
+}
+
 void orc_texture_forward(int img_w, int img_h, int bw, int C, const int32_t *texture_dims,
                          const int32_t *gaussian_ids_sorted, const int32_t *tile_bins, const float *colors,
                          const float *opacities, const float *means, const float *scales, float glob_scale,
@@ -463,6 +530,11 @@ void orc_texture_forward(int img_w, int img_h, int bw, int C, const int32_t *tex
     const int tiles_x = (img_w + bw - 1) / bw;
     const int use_blur = (settings & SET_BLUR) != 0, use_ndc = (settings & SET_NDC) != 0;
     const int bilinear = !(settings & SET_NEAREST);
+    const int vis_mode = (settings & SET_VIS) != 0, alpha_vis = (settings & SET_ALPHA_VIS) != 0;
+    const float alpha_bound = (float)((settings & (0x1f << 17)) >> 17) / 8.0f;
+    const float outline_bound = (float)((settings & (0xf << 26)) >> 26) / 4.0f;
+    const int accept_opacity_thresh = (settings & (1 << 25)) != 0, white_outline = (settings & (1 << 24)) != 0;
+    const float sigma_thresh = 0.5f * alpha_bound * alpha_bound;
 #pragma omp parallel for schedule(dynamic, 4)
     for (int pix = 0; pix < img_w * img_h; ++pix) {
         int row = pix / img_w, col = pix % img_w;
@@ -478,13 +550,28 @@ void orc_texture_forward(int img_w, int img_h, int bw, int C, const int32_t *tex
             pairgeom pg;
             pair_geometry(&r, means + 3 * g, scales + 3 * g, quats + 4 * g, opacities[g], glob_scale, viewmat,
                           fx, fy, cx, cy, use_blur, &pg);
+            float pixel_dis = 1000.0f;
+            if (alpha_vis) { /* texture.cu:201-211 */
+                pg.alpha = 0.99f;
+                if (pg.sigma > sigma_thresh) pg.alpha = 0.0f;
+                if (accept_opacity_thresh && pg.opac < 0.5f) pg.alpha = 0.0f;
+                pixel_dis = local_outline(c2w, viewmat, fx, fy, cx, cy, r.px, r.py, &pg, glob_scale, 3, sigma_thresh);
+            }
             int skip = (pg.t < T_NEAR || pg.t > T_FAR || pg.alpha < 1.f / 255.f);
             float next_T = T * (1.f - pg.alpha);
             if (next_T <= 1e-4f) break; /* texture.cu:216-221: tested before the skip is honoured */
             if (skip) continue;
             float vis = pg.alpha * T;
-            for (int c = 0; c < 3; ++c) acc_c[c] += colors[3 * g + c] * vis;
-            acc_n[0] += vis * pg.a3.x; acc_n[1] += vis * pg.a3.y; acc_n[2] += vis * pg.a3.z;
+            const int draw = !alpha_vis || pixel_dis > outline_bound;   /* texture.cu:226-235 */
+            const int white = !draw && white_outline;
+            for (int c = 0; c < 3; ++c) {
+                if (draw) acc_c[c] += colors[3 * g + c] * vis;
+                else if (white) acc_c[c] += vis;
+            }
+            {
+                float sgn = (vis_mode && v3_dot(r.ray, pg.a3) > 0.f) ? -1.f : 1.f; /* texture.cu:236-241 */
+                acc_n[0] += vis * (sgn * pg.a3.x); acc_n[1] += vis * (sgn * pg.a3.y); acc_n[2] += vis * (sgn * pg.a3.z);
+            }
             float t_view = pg.t * r.view_depth;
             float u = clamp01(uv0[2 * g] + v3_dot(v3_load(umap + 3 * g), pg.delta));
             float v = clamp01(uv0[2 * g + 1] + v3_dot(v3_load(vmap + 3 * g), pg.delta));
@@ -493,7 +580,8 @@ void orc_texture_forward(int img_w, int img_h, int bw, int C, const int32_t *tex
             for (int c = 0; c < C; ++c) {
                 float val = f.w[0] * texture[f.idx[0] + c] + f.w[1] * texture[f.idx[1] + c] +
                             f.w[2] * texture[f.idx[2] + c] + f.w[3] * texture[f.idx[3] + c];
-                acc_t[c] += vis * val;
+                if (draw) acc_t[c] += vis * val;   /* texture.cu:269-274 */
+                else if (white) acc_t[c] += vis;
             }
             if (T > 0.5f) { depth = t_view; dlast = idx; } /* median depth, texture.cu:286-291 */
             float tv = pg.t;

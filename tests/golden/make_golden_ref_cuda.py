@@ -105,8 +105,69 @@ def make(ref, name, n, W, H, bw, settings, C, seed, opaque=False):
     print(name, "M =", m, "bytes =", os.path.getsize(os.path.join(OUT, name)))
 
 
+def make_vis(ref, name, n, W, H, bw, settings, C, seed):
+    """Viewer-only modes (settings bits 15-29, forward only) and wrapped (torus) key emission: SURVEY 8f rank 4."""
+    s = random_small_scene(n, W, H, seed=seed, channels=C, device=DEV, spread=20.0)
+    fx, fy, cx, cy = s["intrins"]
+    tb = ((W + bw - 1) // bw, (H + bw - 1) // bw, 1)
+    vm = s["viewmat"]
+    depths = (s["means"] @ vm[:3, :3].T + vm[:3, 3])[:, 2].contiguous()
+    centers, extents = ref.get_aabb_2d(s["means"], s["scales"], 1.0, s["quats"], vm, fx, fy, cx, cy)
+
+    def bin_(wrapped):
+        tc, te = centers / bw, extents / bw
+        if wrapped:  # helpers.cuh:53-73 (C truncation, no clamp, boxes starting at or before tile 0 grow by one)
+            lo = torch.trunc(tc - te).to(torch.int32)
+            lo = torch.where(lo <= 0, lo - 1, lo)
+            hi = torch.trunc(tc + te + 1).to(torch.int32)
+            nth = ((hi - lo).clamp(min=0)[:, 0] * (hi - lo).clamp(min=0)[:, 1]).to(torch.int32)
+            nth = torch.where((extents[:, 0] <= 1e-4) & (extents[:, 1] <= 1e-4), torch.zeros_like(nth), nth)
+        else:
+            tl = torch.floor(tc - te).to(torch.int32)
+            br = torch.floor(tc + te + 1).to(torch.int32)
+            tmin = torch.stack([tl[:, 0].clamp(0, tb[0]), tl[:, 1].clamp(0, tb[1])], -1)
+            tmax = torch.stack([br[:, 0].clamp(0, tb[0]), br[:, 1].clamp(0, tb[1])], -1)
+            nth = ((tmax - tmin)[:, 0] * (tmax - tmin)[:, 1]).to(torch.int32)
+        cum = torch.cumsum(nth, 0, dtype=torch.int32)
+        m = int(cum[-1])
+        isect, gids = ref.map_gaussian_to_intersects(n, m, centers, extents, depths, cum, tb, bw, wrapped)
+        isect_s, perm = torch.sort(isect)
+        gids_s = torch.gather(gids, 0, perm)
+        return nth, cum, m, isect, gids, isect_s, gids_s, ref.get_tile_bin_edges(m, isect_s, tb)
+
+    nth_w, cum_w, m_w, isect_w, gids_w, isect_ws, gids_ws, bins_w = bin_(True)
+    _, _, m, _, _, _, gids_s, bins = bin_(False)
+    outs = ref.texture_forward(tb, (bw, bw, 1), (W, H, 1), (n, 1, C), s["texture_dims"], gids_s, bins, s["colors"],
+                               s["opacities"], s["means"], s["scales"], 1.0, s["quats"], s["uv0"], s["umap"], s["vmap"],
+                               s["texture"], vm, s["c2w"], fx, fy, cx, cy, settings, s["background"])
+    torch.cuda.synchronize()
+    d = dict(H=H, W=W, block_width=bw, settings=settings, glob_scale=1.0, intrins=np.array(s["intrins"], np.float32),
+             centers=npy(centers), extents=npy(extents), depths=npy(depths), gaussian_ids_sorted=npy(gids_s),
+             tile_bins=npy(bins), wrapped_num_tiles_hit=npy(nth_w), wrapped_cum_tiles_hit=npy(cum_w),
+             wrapped_isect_ids=npy(isect_w), wrapped_gaussian_ids=npy(gids_w), wrapped_isect_ids_sorted=npy(isect_ws),
+             wrapped_gaussian_ids_sorted=npy(gids_ws), wrapped_tile_bins=npy(bins_w))
+    for k in ("means", "scales", "quats", "colors", "opacities", "uv0", "umap", "vmap", "texture", "texture_dims",
+              "viewmat", "c2w", "background"):
+        d[k] = npy(s[k])
+    for k, o in zip(("out_img", "out_depth", "out_reg", "out_texture", "out_normal", "final_Ts", "final_idx",
+                     "depth_idx", "out_reg_s"), outs):
+        d[k] = npy(o)
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, name), **d)
+    print(name, "M =", m, "wrapped M =", m_w, "bytes =", os.path.getsize(os.path.join(OUT, name)))
+
+
+def vis_settings(alpha_bound=0.0, outline=0.0, normals=False, alpha=False, white=False, opac=False, base=1 << 8):
+    return (base | (int(normals) << 15) | (int(alpha) << 16) | (int(round(alpha_bound * 8)) << 17) | (int(white) << 24)
+            | (int(opac) << 25) | (int(round(outline * 4)) << 26))
+
+
 if __name__ == "__main__":
     ref = load_ref()
+    make_vis(ref, "refvis_cuda_normals.npz", 80, 48, 48, 16, vis_settings(normals=True), 3, 201)
+    make_vis(ref, "refvis_cuda_alpha_outline.npz", 80, 64, 48, 16, vis_settings(alpha=True, alpha_bound=3.0, outline=1.0), 3, 202)
+    make_vis(ref, "refvis_cuda_white_opac_c5.npz", 80, 48, 48, 8,
+             vis_settings(alpha=True, alpha_bound=2.5, outline=1.5, white=True, opac=True, normals=True), 5, 203)
     make(ref, "ref_cuda_a.npz", 60, 48, 48, 16, 1 << 8, 3, 101)
     make(ref, "ref_cuda_nonsquare.npz", 150, 80, 48, 16, 1 << 8, 3, 102)
     make(ref, "ref_cuda_opaque.npz", 300, 48, 48, 16, 1 << 8, 3, 103, opaque=True)

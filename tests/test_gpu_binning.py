@@ -124,6 +124,28 @@ def test_binning_pipeline_bit_exact(n, W, H, bw):
     assert int((bins[:, 1] - bins[:, 0]).sum()) == m_o
 
 
+@pytest.mark.parametrize("n,W,H,bw", [(10, 32, 32, 16), (300, 96, 160, 16), (2000, 250, 130, 16), (500, 100, 60, 8)])
+def test_wrapped_binning_bit_exact(n, W, H, bw):
+    """wrapped=True (torus tile boxes, forward.cu:34-36, 53-62): keys / ids / tile ranges vs oracle.
+    Gaussians are spread past the image border so that boxes really wrap around."""
+    s = random_small_scene(n, W, H, seed=n + 3, device=DEV, spread=24.0)
+    b = bin_cuda(s, bw)
+    c, e, d = to_np(b["centers"]), to_np(b["extents"]), to_np(b["depths"])
+    nth = oracle.num_tiles_hit_wrapped(c, e, bw)
+    m, cum = oracle.compute_cumulative_intersects(nth)
+    tb = b["tile_bounds"]
+    i_o, g_o, is_o, gs_o, bins_o = oracle.bin_and_sort_gaussians(n, m, c, e, d, cum, tb, bw, wrapped=True)
+    cum_t = torch.from_numpy(cum).to(DEV)
+    i_c, g_c, is_c, gs_c, bins_c = U.bin_and_sort_gaussians(n, m, b["centers"], b["extents"], b["depths"], cum_t, tb, bw,
+                                                            wrapped=True)
+    for name, got, want in (("isect_ids", i_c, i_o), ("gaussian_ids", g_c, g_o), ("isect_ids_sorted", is_c, is_o),
+                            ("gaussian_ids_sorted", gs_c, gs_o), ("tile_bins", bins_c, bins_o)):
+        np.testing.assert_array_equal(to_np(got), want, err_msg=name)
+    tiles = to_np(i_c) >> 32
+    assert tiles.min() >= 0 and tiles.max() < tb[0] * tb[1]
+    assert m > b["num_intersects"]  # the torus boxes are a superset of the clamped ones (and some do wrap)
+
+
 def test_fused_project_aabb_count_matches_separate_calls():
     from gstex_cuda_b200 import _lib
     s = synthetic_scene(50000, 640, 360, seed=5, device=DEV)

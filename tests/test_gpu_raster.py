@@ -159,11 +159,62 @@ def test_c4_style_scene_reduced():
     compare_backward(b_c, b_o, rtol=5e-3, rel_atol=5e-4, max_bad_frac=5e-3, outlier_bound=None)
 
 
-def test_unsupported_settings_fail_loudly():
+def vis_settings(alpha_bound=0.0, outline=0.0, normals=False, alpha=False, white=False, opac=False, base=1 << 8):
+    """Viewer settings word (reference texture.cu:58-63): bit 15 normals, bit 16 alpha mode, bits 17-21 alpha_bound*8,
+    bit 24 white outline, bit 25 opacity threshold, bits 26-29 outline width*4."""
+    return (base | (int(normals) << 15) | (int(alpha) << 16) | (int(round(alpha_bound * 8)) << 17) | (int(white) << 24)
+            | (int(opac) << 25) | (int(round(outline * 4)) << 26))
+
+
+VIS_CASES = [
+    # settings, channels, seed
+    (vis_settings(normals=True), 3, 41),                                             # camera-facing normals only
+    (vis_settings(alpha=True, alpha_bound=2.0), 3, 42),                              # hard footprints, no outline
+    (vis_settings(alpha=True, alpha_bound=3.0, outline=1.0), 3, 43),                 # black outline
+    (vis_settings(alpha=True, alpha_bound=3.0, outline=1.5, white=True), 3, 44),     # white outline
+    (vis_settings(alpha=True, alpha_bound=2.5, outline=1.0, opac=True, normals=True), 3, 45),
+    (vis_settings(alpha=True, alpha_bound=3.0, outline=1.0, white=True), 5, 46),     # generic channel count
+    (vis_settings(alpha=True, alpha_bound=2.0, outline=1.0, base=(1 << 8) | (1 << 9)), 3, 47),  # with the blur bit set
+]
+# The hard footprint edge sigma <= alpha_bound^2/2 and the outline test are threshold decisions on every Gaussian's
+# border: a pixel within rounding of a border flips a whole (near-opaque) Gaussian, so the allowance for out-of-tolerance
+# pixels is 1 % instead of the 0.2 % of the smooth modes.
+VIS_FLIP = 1e-2
+
+
+@pytest.mark.parametrize("settings,C,seed", VIS_CASES)
+def test_visualisation_modes_vs_oracle(settings, C, seed):
+    """viewer-only settings bits 15-29 (forward only), reference texture.cu:58-63, :201-241."""
+    s = random_small_scene(250, 96, 80, seed=seed, channels=C, device=DEV)
+    s["settings"] = settings
+    b = bin_cuda(s)
+    ids, bins = b["gaussian_ids_sorted"], b["tile_bins"]
+    f_c, _ = forward_cuda(s, ids, bins)
+    f_o = forward_oracle(s, to_np(ids), to_np(bins))
+    cover = float((f_o["final_Ts"] < 0.5).mean())
+    print(f"settings={settings:#x}: covered pixels {cover:.2f}")
+    assert cover > 0.05
+    compare_forward(f_c, f_o, max_bad_frac=VIS_FLIP, int_bad_frac=VIS_FLIP)
+    if settings & (1 << 15):  # camera-facing normals: every blended normal opposes its pixel's ray, so does their sum
+        n = to_np(f_c["out_normal"]).astype(np.float64)
+        fx, fy, cx, cy = s["intrins"]
+        px, py = np.meshgrid(np.arange(s["W"]) + 0.5, np.arange(s["H"]) + 0.5)
+        rays = np.stack([(px - cx) / fx, (py - cy) / fy, np.ones_like(px)], -1) @ to_np(s["c2w"])[:3, :3].T.astype(np.float64)
+        assert float(((n * rays).sum(-1) > 1e-6).mean()) == 0.0
+
+
+def test_visualisation_bits_are_forward_only():
+    """The reference's backward ignores the viewer bits (it would differentiate a different image); here the backward
+    entry points reject them, and bits outside the reference's settings word are rejected everywhere."""
     s = random_small_scene(10, 32, 32, seed=1, device=DEV)
     b = bin_cuda(s)
+    ids, bins = b["gaussian_ids_sorted"], b["tile_bins"]
+    st = vis_settings(alpha=True, alpha_bound=2.0)
+    f, scratch = forward_cuda(s, ids, bins, settings=st)
     with pytest.raises(RuntimeError, match="settings"):
-        forward_cuda(s, b["gaussian_ids_sorted"], b["tile_bins"], settings=(1 << 8) | (1 << 16))
+        backward_cuda(s, ids, bins, f, random_vout(s, 0), settings=st, scratch=scratch)
+    with pytest.raises(RuntimeError, match="settings"):
+        forward_cuda(s, ids, bins, settings=(1 << 8) | (1 << 30))
 
 
 # ---- general cameras: every fixture above looks down +z with an identity rotation (as example.py does) -----------

@@ -91,6 +91,45 @@ def test_binning_bit_exact_vs_reference_cuda(ref, n, W, H, bw):
     assert torch.equal(b_m, b_r)
 
 
+@pytest.mark.parametrize("n,W,H,bw", [(300, 96, 160, 16), (3000, 256, 192, 16), (800, 100, 60, 8)])
+def test_wrapped_binning_bit_exact_vs_reference_cuda(ref, n, W, H, bw):
+    """wrapped=True key emission (forward.cu:34-36, 53-62): ours and the oracle against the reference kernel."""
+    s = random_small_scene(n, W, H, seed=n + 5, device=DEV, spread=24.0)
+    intr = s["intrins"]
+    c_r, e_r = ref.get_aabb_2d(s["means"], s["scales"], 1.0, s["quats"], s["viewmat"], *intr)
+    from gstex_cuda_b200.get_aabb_2d import project_points
+    _, depths = project_points(s["means"], s["viewmat"], intr)
+    torch.cuda.synchronize()
+    nth = oracle.num_tiles_hit_wrapped(to_np(c_r), to_np(e_r), bw)
+    m, cum_np = oracle.compute_cumulative_intersects(nth)
+    cum = torch.from_numpy(cum_np).to(DEV)
+    tb = ((W + bw - 1) // bw, (H + bw - 1) // bw, 1)
+    i_r, g_r = ref.map_gaussian_to_intersects(n, m, c_r, e_r, depths, cum, tb, bw, True)
+    i_m, g_m = _C.map_gaussian_to_intersects(n, m, c_r, e_r, depths, cum, tb, bw, True)
+    torch.cuda.synchronize()
+    assert torch.equal(i_m, i_r) and torch.equal(g_m, g_r)
+    i_o, g_o = oracle.map_gaussian_to_intersects(n, m, to_np(c_r), to_np(e_r), to_np(depths), cum_np, tb, bw, True)
+    np.testing.assert_array_equal(i_o, to_np(i_r))
+    np.testing.assert_array_equal(g_o, to_np(g_r))
+    assert int(((to_np(i_r) >> 32) >= tb[0] * tb[1]).sum()) == 0 and m > 0
+
+
+def test_visualisation_modes_vs_reference_cuda(ref):
+    """Viewer-only settings bits 15-29 (forward only): ours and the oracle against the reference kernel."""
+    from test_gpu_raster import VIS_CASES, VIS_FLIP
+    for settings, C, seed in VIS_CASES:
+        s = random_small_scene(250, 96, 80, seed=seed, channels=C, device=DEV)
+        s["settings"] = settings
+        b = bin_cuda(s)
+        ids, bins = b["gaussian_ids_sorted"], b["tile_bins"]
+        f_m, _ = forward_cuda(s, ids, bins)
+        f_r = {k: to_np(v) for k, v in ref_forward(ref, s, ids, bins, 16, settings).items()}
+        print(f"settings={settings:#x}: ours vs reference CUDA")
+        compare_forward(f_m, f_r, max_bad_frac=VIS_FLIP, int_bad_frac=VIS_FLIP)
+        print(f"settings={settings:#x}: CPU oracle vs reference CUDA  <- pins the oracle")
+        compare_forward(forward_oracle(s, to_np(ids), to_np(bins)), f_r, max_bad_frac=VIS_FLIP, int_bad_frac=VIS_FLIP)
+
+
 RCASES = [
     (10, 32, 32, 16, 1 << 8, 3, 1),
     (300, 96, 64, 16, 1 << 8, 3, 2),

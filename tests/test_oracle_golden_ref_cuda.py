@@ -74,3 +74,37 @@ def test_oracle_texture_edit_matches_reference_cuda(path):
     assert want[:, 4].sum() > 0, "fixture splats nothing"
     # a pair at the 1/255 / depth-window threshold may be kept by one side only: a few texels may differ by one splat
     _close("updated_texture", got, want, 1e-4, 1e-5, 40)
+
+
+VIS_FILES = sorted(glob.glob(os.path.join(GOLDEN, "refvis_cuda_*.npz")))
+
+
+@pytest.mark.skipif(not VIS_FILES, reason="reference-CUDA visualisation / wrapped golden vectors not generated yet")
+@pytest.mark.parametrize("path", VIS_FILES, ids=[os.path.basename(f) for f in VIS_FILES])
+def test_oracle_visualisation_and_wrapped_match_reference_cuda(path):
+    """the viewer-only settings bits 15-29 (forward) and wrapped (torus) key emission."""
+    g = dict(np.load(path))
+    H, W, bw, settings = int(g["H"]), int(g["W"]), int(g["block_width"]), int(g["settings"])
+    fx, fy, cx, cy = (float(v) for v in g["intrins"])
+    n = g["means"].shape[0]
+    tb = ((W + bw - 1) // bw, (H + bw - 1) // bw, 1)
+    # --- wrapped binning: integers, bit-exact ---
+    nth = oracle.num_tiles_hit_wrapped(g["centers"], g["extents"], bw)
+    np.testing.assert_array_equal(nth, g["wrapped_num_tiles_hit"])
+    m, cum = oracle.compute_cumulative_intersects(nth)
+    np.testing.assert_array_equal(cum, g["wrapped_cum_tiles_hit"])
+    i_, g_, is_, gs_, bins = oracle.bin_and_sort_gaussians(n, m, g["centers"], g["extents"], g["depths"], cum, tb, bw,
+                                                           wrapped=True)
+    for got, key in ((i_, "isect_ids"), (g_, "gaussian_ids"), (is_, "isect_ids_sorted"), (gs_, "gaussian_ids_sorted"),
+                     (bins, "tile_bins")):
+        np.testing.assert_array_equal(got, g["wrapped_" + key], err_msg=key)
+    # --- visualisation forward: hard footprint edges flip whole Gaussians at border pixels -> 1 % allowance ---
+    f = oracle.texture_forward(H, W, bw, g["texture_dims"], g["gaussian_ids_sorted"], g["tile_bins"], g["colors"],
+                               g["opacities"], g["means"], g["scales"], 1.0, g["quats"], g["uv0"], g["umap"], g["vmap"],
+                               g["texture"], g["viewmat"], g["c2w"], fx, fy, cx, cy, settings, g["background"])
+    assert float((g["final_Ts"] < 0.9).mean()) > 0.05, "fixture renders almost nothing"
+    npix = H * W
+    for k in ("final_idx", "depth_idx"):
+        assert int((f[k] != g[k]).sum()) <= npix // 100, k
+    for k in ("out_img", "out_depth", "out_reg", "out_texture", "out_normal", "final_Ts", "out_reg_s"):
+        _close(k, f[k], g[k], 1e-4, 2e-5, f[k].size // 100)
