@@ -87,6 +87,13 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
+    def wait_first(self, timeout_s: float = 15.0):
+        """Block until nvidia-smi has delivered its first sample (it can take seconds, longer with several ranks
+        querying at once): a short timed region must not end before the sampler has started."""
+        t0 = time.time()
+        while self.proc is not None and not self.rows and time.time() - t0 < timeout_s:
+            time.sleep(0.05)
+
     def mark(self):
         """Index of the next sample: call at the start of the loaded region."""
         return len(self.rows)
@@ -165,6 +172,8 @@ def run_reference(args, rank: int):
     from gstex_cuda_b200.scenes import synthetic_scene
 
     scene = scene_to_numpy(synthetic_scene(args.points, args.width, args.height, seed=1234))
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm uses every host core regardless
+    oracle.set_num_threads(os.cpu_count() or 1)
     cores = oracle.num_threads()
     rows = args.cpu_rows or 128
     rows = min(args.height, max(16, rows // 16 * 16))
@@ -197,8 +206,12 @@ def main():
         run_reference(args, rank)
         return
 
-    # rank 0 prints exactly one JSON line on stdout: keep NCCL's banner out of it (GSTEX_NCCL_DEBUG=INFO to see NCCL logs)
-    os.environ["NCCL_DEBUG"] = os.environ.get("GSTEX_NCCL_DEBUG", "WARN")
+    # rank 0 prints exactly one JSON line on stdout: NCCL writes its version banner and logs to stdout at any
+    # NCCL_DEBUG level >= VERSION, so the variable is cleared unless GSTEX_NCCL_DEBUG asks for logs, which then go to stderr
+    os.environ.pop("NCCL_DEBUG", None)
+    if os.environ.get("GSTEX_NCCL_DEBUG"):
+        os.environ["NCCL_DEBUG"] = os.environ["GSTEX_NCCL_DEBUG"]
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
 
@@ -244,6 +257,7 @@ def main():
         torch.cuda.synchronize()
 
     # ---- warm-up --------------------------------------------------------------------------------
+    sampler.wait_first()
     barrier()
     load_start = sampler.mark()
     for _ in range(args.warmup):
@@ -319,6 +333,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import oracle
 
+        oracle.set_num_threads(os.cpu_count() or 1)
         rows = args.cpu_rows or 256
         rows = min(H, max(16, rows // 16 * 16))
         t = cpu_step(scene_to_numpy(scene), rows)

@@ -19,7 +19,10 @@
 
 namespace gstex {
 
-constexpr int RASTER_BATCH = 128;      // Gaussians per shared-memory stage
+#ifndef GSTEX_RASTER_BATCH
+#define GSTEX_RASTER_BATCH 128
+#endif
+constexpr int RASTER_BATCH = GSTEX_RASTER_BATCH;  // Gaussians per shared-memory stage (<= 256: uint8 survivor indices)
 constexpr int RASTER_MAX_THREADS = 256;
 constexpr int RASTER_MAX_C = 64;       // generic-channel path (reference texture.cu:102-103)
 

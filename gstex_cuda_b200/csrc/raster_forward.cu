@@ -94,10 +94,12 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, 4) raster_forward_kernel(c
         // stage b is visible to the whole CTA after this barrier; leave if every pixel is finished
         if (__syncthreads_count(done) >= p.nthreads) break;
         const float4 *__restrict__ S = stage[b & 1];
+#ifndef GSTEX_EXP_NO_PREFETCH
         if (C3 && tr < cnt) {  // one thread per staged record: start fetching its texture block
             const float4 q3 = S[quad_slot(tr, 3)], q6 = S[quad_slot(tr, 6)];
             prefetch_texture_block(p.tex4, __float_as_int(q6.w), __float_as_int(q3.z), __float_as_int(q3.w));
         }
+#endif
         // warp-level culling: the warp walks only the records that can reach alpha >= 1/255 on its patch
         const int nsurv = __all_sync(0xffffffffu, done) ? 0 : build_survivors<BLUR, !VIS>(S, 0, cnt, wr, p.mean2d, my_list, lane);
         // The survivor walk is warp-uniform: finished pixels stay in the loop (predicated off) so that the blend
