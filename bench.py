@@ -16,8 +16,8 @@ N > 1 : BASELINE config 5 - 64 views per step (an arc of +-30 degrees around the
         what the C4 view costs), sharded round-robin over the ranks, replicated parameters, one all-reduce of the
         0.46 GB fp32 gradient arena per step  (strong scaling of the 64-view batch).
 `value` = pixels rendered (forward+backward) by all ranks / device time (max over ranks), inputs resident in HBM.
-`e2e`   = the same metric through the reference-shaped public API (project_points, get_aabb_2d,
-          get_num_tiles_hit_2d, texture_gaussians, autograd) with the step's inputs (camera matrices and target
+`e2e`   = the same metric through the reference-shaped public API (spherical_harmonics_colors, project_points,
+          get_aabb_2d, get_num_tiles_hit_2d, texture_gaussians, image_loss; torch autograd) with the step's inputs (camera matrices and target
           image) copied from pinned host memory and the loss read back, inside the timed region.
 """
 from __future__ import annotations
@@ -366,6 +366,7 @@ def run_e2e(args, scene, cams, mine, targets_host, dev, world, views):
 
     from gstex_cuda_b200 import sh as SH
     from gstex_cuda_b200.get_aabb_2d import get_aabb_2d, get_num_tiles_hit_2d, project_points
+    from gstex_cuda_b200.loss import image_loss
     from gstex_cuda_b200.texture import texture_gaussians
 
     H, W, bw, intr = args.height, args.width, 16, scene["intrins"]
@@ -374,14 +375,25 @@ def run_e2e(args, scene, cams, mine, targets_host, dev, world, views):
     cams_host = [(a.cpu().pin_memory(), b.cpu().pin_memory()) for a, b in cams]
     h2d = sum(targets_host[v].numel() * 4 + 2 * 64 for v in mine)
 
+    # the step's inputs come from pinned host memory through the package's double-buffered loader: the copy of view k+1
+    # runs on a copy stream underneath the kernels of view k.  Every timed step still copies every one of its views
+    # (the copy for the first view of the next step is issued by the step before it; the one before the timed region
+    # is issued by the warm-up, and the last timed step issues one for a step that never runs).
+    from gstex_cuda_b200.prefetch import ViewPrefetcher
+    loader = ViewPrefetcher(dev, depth=2)
+    order = list(mine)
+
+    def host_inputs(v):
+        return (cams_host[v][0], cams_host[v][1], targets_host[v])
+
+    loader.submit(host_inputs(order[0]))
+
     def one_step():
         total = None
-        for v in mine:
-            vm = cams_host[v][0].to(dev, non_blocking=True)
-            c2w = cams_host[v][1].to(dev, non_blocking=True)
-            gt = targets_host[v].to(dev, non_blocking=True)
-            dirs = leaves["means"].detach() - c2w[:3, 3]
-            colors = torch.clamp(SH.spherical_harmonics(3, dirs, leaves["sh_coeffs"]) + 0.5, 0.0, 1.0)
+        for idx, v in enumerate(order):
+            vm, c2w, gt = loader.get()
+            loader.submit(host_inputs(order[(idx + 1) % len(order)]))
+            colors = SH.spherical_harmonics_colors(3, leaves["means"], c2w, leaves["sh_coeffs"])
             _, depths = project_points(leaves["means"].detach(), vm, intr)
             centers, extents = get_aabb_2d(leaves["means"].detach(), leaves["scales"].detach(), 1.0,
                                            leaves["quats"].detach(), vm, intr)
@@ -390,10 +402,9 @@ def run_e2e(args, scene, cams, mine, targets_host, dev, world, views):
                                      leaves["opacities"], leaves["means"], leaves["scales"], 1.0, leaves["quats"],
                                      leaves["uv0"], leaves["umap"], leaves["vmap"], leaves["texture"], vm, c2w, *intr, H,
                                      W, bw, 1 << 8, scene["background"])
-            n_ = outs[5]
-            loss = (torch.nn.functional.mse_loss(outs[4], gt) + outs[2].mean()
-                    + (n_[..., 0] ** 2 + n_[..., 1] ** 2 + (1 - n_[..., 2]) ** 2).mean())
+            loss = image_loss(outs[4], outs[2], outs[5], gt)  # example.py:189-209, one kernel (csrc/loss.cu)
             loss.backward()
+            loader.release()
             total = loss.detach() if total is None else total + loss.detach()
         if world > 1:
             for t in leaves.values():
@@ -404,8 +415,10 @@ def run_e2e(args, scene, cams, mine, targets_host, dev, world, views):
         return val
 
     steps = max(3, min(args.steps, 10 if views == 1 else 3))
+    loader_steps = [0]
     for _ in range(2):
         one_step()
+    loader.bytes_copied = 0
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -414,6 +427,7 @@ def run_e2e(args, scene, cams, mine, targets_host, dev, world, views):
     for _ in range(steps):
         one_step()
     e1.record()
+    loader_steps[0] = steps
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -423,8 +437,10 @@ def run_e2e(args, scene, cams, mine, targets_host, dev, world, views):
     ms = float(ms.item())
     return {"value": views * H * W / (ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
             "d2h_bytes_per_step": 4, "ms_per_step": ms, "steps": steps,
-            "api": "project_points + get_aabb_2d + get_num_tiles_hit_2d + texture_gaussians (autograd), torch glue for "
-                   "SH+0.5 clamp and the example.py loss"}
+            "api": "spherical_harmonics_colors + project_points + get_aabb_2d + get_num_tiles_hit_2d + texture_gaussians + "
+                   "image_loss (the example.py loss), all autograd ops of the package; inputs staged by gstex_cuda_b200.prefetch.ViewPrefetcher "
+                   "(pinned host -> device on a copy stream, one view ahead)",
+            "h2d_bytes_measured_per_step": int(loader.bytes_copied // max(1, loader_steps[0]))}
 
 
 if __name__ == "__main__":

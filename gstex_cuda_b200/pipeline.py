@@ -130,6 +130,12 @@ class FusedTrainStep:
         self.time_kernels = False
         self.kernel_events: List[Tuple[str, torch.cuda.Event, torch.cuda.Event]] = []
         self._bin_launches = 6  # tile count, tile scan, scatter, three per-tile sort size classes
+        # The rasterisers are issue-bound and leave most of the HBM bandwidth idle; the bandwidth-bound housekeeping that
+        # does not depend on them (texture padding, zero-fills of the moment lines / texel-gradient buffer) runs on a
+        # side stream underneath binning and the forward rasteriser and is joined with events where its result is needed.
+        self.side = torch.cuda.Stream(device=dev)
+        self._tex_ready = torch.cuda.Event()
+        self._acc_ready = torch.cuda.Event()
 
     # ------------------------------------------------------------------------------------------
     def _s(self) -> int:
@@ -169,14 +175,18 @@ class FusedTrainStep:
 
     def begin_step(self) -> None:
         """Once per optimiser step: pad the texture, clear the texel-gradient buffer and the loss."""
-        lib, s = self.lib, self._s()
-        if self.C == 3:
-            pad = lib.gstex_sigmoid_pad_texture if self.texture_is_raw else lib.gstex_pad_texture
-            self._ck(pad(self.X, self.p["texture"].data_ptr(), self.tex4.data_ptr(), s), "pad_texture")
-            self.launches += 1
-            self.vtex4.zero_()
-        else:
-            self.grads["v_texture"].zero_()
+        lib = self.lib
+        main = torch.cuda.current_stream(self.dev)
+        self.side.wait_stream(main)  # the parameters (and last step's consumers of tex4 / vtex4) are settled on `main`
+        with torch.cuda.stream(self.side):
+            if self.C == 3:
+                pad = lib.gstex_sigmoid_pad_texture if self.texture_is_raw else lib.gstex_pad_texture
+                self._ck(pad(self.X, self.p["texture"].data_ptr(), self.tex4.data_ptr(), self._s()), "pad_texture")
+                self.launches += 1
+                self.vtex4.zero_()
+            else:
+                self.grads["v_texture"].zero_()
+            self._tex_ready.record(self.side)
         self.loss.zero_()
         self._first_view = True
 
@@ -187,6 +197,14 @@ class FusedTrainStep:
         fx, fy, cx, cy = self.intr
         P = lambda t: t.data_ptr()  # noqa: E731
         viewmat, c2w = self._cam(viewmat, "viewmat"), self._cam(c2w, "c2w")
+        # side stream: clear this view's moment lines (and per-view SH colour gradients) while the view is binned / rendered
+        main = torch.cuda.current_stream(self.dev)
+        self.side.wait_stream(main)  # the previous view's epilogue / SH backward have consumed them
+        with torch.cuda.stream(self.side):
+            self.acc.zero_()
+            if self.use_sh and not self._first_view:
+                self.v_colors.zero_()  # SH colours are per view (they feed this view's SH backward), never accumulated
+            self._acc_ready.record(self.side)
         if self.use_sh:
             self._ck(lib.gstex_sh_colors_forward(n, self.sh_degree, self.sh_degree, P(p["means"]), P(c2w),
                                                  P(p["sh_coeffs"]), P(self.colors), P(self.mask), s), "sh_colors_forward")
@@ -204,6 +222,8 @@ class FusedTrainStep:
                  "pack_records")
         tex = self.tex4 if self.C == 3 else p["texture"]
         o = self.out
+        if self._first_view:
+            main.wait_event(self._tex_ready)  # padded texture (begin_step, side stream)
         with self._timed("raster_forward"):
             self._ck(lib.gstex_raster_forward(H, W, bw, self.C, self.settings, P(self.ids_sorted), P(self.tile_bins),
                                               P(self.recs), P(self.mean2d), P(tex), P(viewmat), P(c2w), fx, fy, cx, cy,
@@ -234,9 +254,7 @@ class FusedTrainStep:
         viewmat, c2w = self._cam(viewmat, "viewmat"), self._cam(c2w, "c2w")
         o, g = self.out, self.grads
         acc_flag = 0 if self._first_view else 1
-        self.acc.zero_()
-        if acc_flag and self.use_sh:
-            self.v_colors.zero_()  # SH colours are per view (they feed this view's SH backward), never accumulated
+        torch.cuda.current_stream(self.dev).wait_event(self._acc_ready)  # zero-fills of view_forward (side stream)
         tex = self.tex4 if self.C == 3 else p["texture"]
         vtex = self.vtex4 if self.C == 3 else g["v_texture"]
         with self._timed("raster_backward"):

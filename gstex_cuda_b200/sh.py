@@ -1,9 +1,11 @@
 """Spherical-harmonics colour evaluation (mirror of ``gstex_cuda/sh.py``, victor-rong/GStex_cuda)."""
 from __future__ import annotations
 
+import torch
 from torch import Tensor
 from torch.autograd import Function
 
+from . import _lib
 from . import cuda as _C
 
 
@@ -39,3 +41,45 @@ class _SphericalHarmonics(Function):
         viewdirs = ctx.saved_tensors[0]
         return (None, None, _C.compute_sh_backward(v_colors.shape[0], ctx.degree, ctx.degrees_to_use, viewdirs,
                                                    v_colors.contiguous()))
+
+
+def spherical_harmonics_colors(degrees_to_use: int, means: Tensor, c2w: Tensor, coeffs: Tensor) -> Tensor:
+    """View-dependent colours as a trainer forms them around the SH op, in one kernel each way:
+    ``clamp(spherical_harmonics(deg, means - c2w[:3, 3], coeffs) + 0.5, 0, 1)``.  Differentiable w.r.t. ``coeffs``
+    only (like the reference op, sh.py:60-96, whose ``viewdirs`` carry no gradient); the clamp gates the gradient."""
+    assert coeffs.shape[-2] >= num_sh_bases(degrees_to_use)
+    return _SphericalHarmonicsColors.apply(degrees_to_use, means.detach().contiguous(), c2w.contiguous(),
+                                           coeffs.contiguous())
+
+
+class _SphericalHarmonicsColors(Function):
+    @staticmethod
+    def forward(ctx, degrees_to_use: int, means: Tensor, c2w: Tensor, coeffs: Tensor):
+        for name, t in (("means", means), ("c2w", c2w), ("coeffs", coeffs)):
+            if not (t.is_cuda and t.dtype == torch.float32):
+                raise RuntimeError(f"spherical_harmonics_colors: {name} must be a float32 CUDA tensor")
+        n, dev = coeffs.shape[0], coeffs.device
+        ctx.degrees_to_use, ctx.degree = degrees_to_use, deg_from_sh(coeffs.shape[-2])
+        colors = torch.empty((n, 3), dtype=torch.float32, device=dev)
+        mask = torch.empty((n,), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            rc = _lib.load().gstex_sh_colors_forward(n, ctx.degree, degrees_to_use, means.data_ptr(), c2w.data_ptr(),
+                                                     coeffs.data_ptr(), colors.data_ptr(), mask.data_ptr(),
+                                                     torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(rc, "sh_colors_forward")
+        ctx.save_for_backward(means, c2w, mask)
+        ctx.coeff_shape = tuple(coeffs.shape)
+        return colors
+
+    @staticmethod
+    def backward(ctx, v_colors: Tensor):
+        means, c2w, mask = ctx.saved_tensors
+        n, dev = means.shape[0], means.device
+        v_colors = v_colors.contiguous()
+        v_coeffs = torch.zeros(ctx.coeff_shape, dtype=torch.float32, device=dev)  # rows past degrees_to_use stay zero
+        with torch.cuda.device(dev):
+            rc = _lib.load().gstex_sh_colors_backward(n, ctx.degree, ctx.degrees_to_use, means.data_ptr(), c2w.data_ptr(),
+                                                      v_colors.data_ptr(), mask.data_ptr(), v_coeffs.data_ptr(), 0,
+                                                      torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(rc, "sh_colors_backward")
+        return None, None, None, v_coeffs

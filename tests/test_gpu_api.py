@@ -144,3 +144,68 @@ def test_clipped_gaussians_reproduce_reference_zero_slots():
     for got, want in zip((isect, gids, isect_s, gids_s, bins), b):
         np.testing.assert_array_equal(to_np(got), want)
     assert int((to_np(isect) == 0).sum()) == 3
+
+
+def test_view_prefetcher_ring_delivers_views_in_order():
+    """gstex_cuda_b200.prefetch: double-buffered pinned-host -> device staging on a copy stream."""
+    from gstex_cuda_b200.prefetch import ViewPrefetcher
+    g = torch.Generator().manual_seed(0)
+    views = [(torch.rand(4, 4, generator=g).pin_memory(), torch.rand(64, 48, 3, generator=g).pin_memory())
+             for _ in range(5)]
+    pf = ViewPrefetcher(torch.device(DEV), depth=2)
+    pf.submit(views[0])
+    acc = []
+    for k in range(5):
+        cam, img = pf.get()
+        if k + 1 < 5:
+            pf.submit(views[k + 1])
+        acc.append((cam.clone(), (img * 2.0).sum()))  # a consumer on the compute stream
+        pf.release()
+    torch.cuda.synchronize()
+    for k in range(5):
+        assert torch.equal(acc[k][0].cpu(), views[k][0])
+        torch.testing.assert_close(acc[k][1].cpu(), (views[k][1] * 2.0).sum(), rtol=1e-5, atol=1e-3)
+    assert pf.bytes_copied == sum(a.numel() * 4 + b.numel() * 4 for a, b in views)
+    pf.submit(views[0]); pf.submit(views[1])
+    with pytest.raises(RuntimeError, match="full"):
+        pf.submit(views[2])
+    with pytest.raises(RuntimeError, match="pinned"):
+        ViewPrefetcher(torch.device(DEV)).submit((torch.zeros(4),))
+
+
+def test_fused_image_loss_and_sh_colors_match_torch_glue():
+    """gstex_cuda_b200.loss.image_loss and sh.spherical_harmonics_colors against the torch ops they replace
+    (example.py:189-209 and clamp(SH + 0.5, 0, 1)), values and gradients, fp32 tolerances."""
+    from gstex_cuda_b200.loss import image_loss
+    from gstex_cuda_b200 import sh as SH
+    g = torch.Generator().manual_seed(3)
+    H, W = 90, 70
+    tex = torch.rand(H, W, 3, generator=g).to(DEV).requires_grad_(True)
+    reg = torch.rand(H, W, generator=g).to(DEV).requires_grad_(True)
+    nrm = torch.randn(H, W, 3, generator=g).to(DEV).requires_grad_(True)
+    gt = torch.rand(H, W, 3, generator=g).to(DEV)
+    ref = (torch.nn.functional.mse_loss(tex, gt) + reg.mean()
+           + (nrm[..., 0] ** 2 + nrm[..., 1] ** 2 + (1 - nrm[..., 2]) ** 2).mean())
+    g_ref = torch.autograd.grad(ref * 1.7, (tex, reg, nrm))
+    got = image_loss(tex, reg, nrm, gt)
+    g_got = torch.autograd.grad(got * 1.7, (tex, reg, nrm))
+    torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-6)
+    for a, b in zip(g_got, g_ref):
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-9)
+
+    n = 3000
+    means = torch.randn(n, 3, generator=g).to(DEV)
+    c2w = torch.eye(4); c2w[:3, 3] = torch.tensor([0.3, -0.2, -8.0]); c2w = c2w.to(DEV)
+    for deg in (0, 1, 2, 3):
+        K = (deg + 1) ** 2
+        co = (torch.randn(n, K, 3, generator=g) * 2.5).to(DEV).requires_grad_(True)
+        v = torch.randn(n, 3, generator=g).to(DEV)
+        ref = torch.clamp(SH.spherical_harmonics(deg, means - c2w[:3, 3], co) + 0.5, 0.0, 1.0)
+        got = SH.spherical_harmonics_colors(deg, means, c2w, co)
+        assert float(((ref == 0) | (ref == 1)).float().mean()) > 0.05  # the clamp is exercised
+        torch.testing.assert_close(got, ref, rtol=1e-5, atol=2e-6)
+        (g_ref,) = torch.autograd.grad(ref, co, v)
+        (g_got,) = torch.autograd.grad(got, co, v)
+        # a channel within rounding of the clamp can be gated on one side only
+        bad = ((g_got - g_ref).abs() > 1e-5 + 1e-4 * g_ref.abs()).float().mean()
+        assert float(bad) < 1e-3
