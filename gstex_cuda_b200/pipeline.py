@@ -13,7 +13,11 @@ utils.py:58) with ~16 launches of libgstex_b200 kernels on one stream over preal
 * the texture is padded to float4 once per step, texel gradients of all views accumulate in one padded
   buffer and are un-padded once per step;
 * parameter gradients of all views accumulate in ONE contiguous fp32 arena (``grad_arena``), which is what
-  the data-parallel wrapper all-reduces over NCCL (one collective per step).
+  the data-parallel wrapper all-reduces over NCCL (one collective per step, SURVEY 8e);
+* the step is a two-stream software pipeline over the views: the two rasteriser kernels (instruction-issue bound, most
+  of the HBM bandwidth idle) run back to back on the caller's stream, while everything bandwidth-bound - SH colours,
+  projection, binning and record packing of the NEXT view, the per-Gaussian epilogue and SH backward of the PREVIOUS
+  one, texture padding and zero-fills - runs underneath them on a side stream over double-buffered per-view state.
 """
 from __future__ import annotations
 
@@ -103,19 +107,11 @@ class FusedTrainStep:
         self.tex4 = torch.empty((X, 4), **f32) if C == 3 else None
         self.vtex4 = torch.empty((X, 4), **f32) if C == 3 else None
         self.loss = torch.zeros(1, **f32)
-        # ---- per-view buffers
-        if self.use_sh:  # per-view colours and their gradient (they feed this view's SH backward)
-            self.colors, self.mask, self.v_colors = torch.empty((n, 3), **f32), torch.empty((n,), dtype=torch.uint8, device=dev), torch.empty((n, 3), **f32)
-        else:
-            self.colors, self.mask, self.v_colors = params["colors"], None, self.grads["v_colors"]
-        self.centers, self.extents, self.depths = torch.empty((n, 2), **f32), torch.empty((n, 2), **f32), torch.empty((n,), **f32)
-        self.nth = torch.empty((n,), **i32)
-        self.ids_sorted = torch.empty((self.cap,), **i32)
-        self.num_isect = torch.zeros((1,), **i32)
+        # ---- per-view buffers.  Everything the side stream produces for a view (and the moment lines it consumes)
+        # exists twice, so that view k+1 can be prepared while view k is still being rasterised.
+        self.sets = [self._make_view_set(f32, i32) for _ in range(2)]
+        self.cur = self.sets[0]  # the set of the view rendered last
         self.masks = torch.empty((self.cap, 8), **i32)  # blend masks: forward -> backward (csrc/raster.cuh)
-        self.bin_temp = torch.empty((self.lib.gstex_bin_tiles_temp_bytes(self.num_tiles, self.cap),), dtype=torch.uint8, device=dev)
-        self.tile_bins = torch.empty((self.num_tiles, 2), **i32)
-        self.recs, self.mean2d, self.acc = torch.empty((n, 32), **f32), torch.empty((n, 2), **f32), torch.empty((n, 32), **f32)
         self.out = dict(out_img=torch.empty((H, W, 3), **f32), out_depth=torch.empty((H, W), **f32),
                         out_reg=torch.empty((H, W), **f32), out_texture=torch.empty((H, W, C), **f32),
                         out_normal=torch.empty((H, W, 3), **f32), final_Ts=torch.empty((H, W), **f32),
@@ -133,9 +129,41 @@ class FusedTrainStep:
         # The rasterisers are issue-bound and leave most of the HBM bandwidth idle; the bandwidth-bound housekeeping that
         # does not depend on them (texture padding, zero-fills of the moment lines / texel-gradient buffer) runs on a
         # side stream underneath binning and the forward rasteriser and is joined with events where its result is needed.
+        # default priority: measured on C5 (8 views/step, 1 GPU) a high-priority side stream only moves time from its own
+        # kernels into the rasterisers they displace (32.7 ms vs 32.4 ms per step; serial loop 33.6 ms)
         self.side = torch.cuda.Stream(device=dev)
         self._tex_ready = torch.cuda.Event()
-        self._acc_ready = torch.cuda.Event()
+
+    def _make_view_set(self, f32, i32):
+        n, dev = self.n, self.dev
+
+        class _ViewSet:
+            pass
+
+        v = _ViewSet()
+        if self.use_sh:  # per-view colours and their gradient (they feed this view's SH backward)
+            v.colors, v.mask = torch.empty((n, 3), **f32), torch.empty((n,), dtype=torch.uint8, device=dev)
+            v.v_colors = torch.empty((n, 3), **f32)
+        else:
+            v.colors, v.mask, v.v_colors = self.p["colors"], None, self.grads["v_colors"]
+        v.centers, v.extents, v.depths = torch.empty((n, 2), **f32), torch.empty((n, 2), **f32), torch.empty((n,), **f32)
+        v.nth = torch.empty((n,), **i32)
+        v.ids_sorted = torch.empty((self.cap,), **i32)
+        v.num_isect = torch.zeros((1,), **i32)
+        v.bin_temp = torch.empty((self.lib.gstex_bin_tiles_temp_bytes(self.num_tiles, self.cap),), dtype=torch.uint8,
+                                 device=dev)
+        v.tile_bins = torch.empty((self.num_tiles, 2), **i32)
+        v.recs, v.mean2d, v.acc = torch.empty((n, 32), **f32), torch.empty((n, 2), **f32), torch.empty((n, 32), **f32)
+        v.prep_done, v.bwd_done = torch.cuda.Event(), torch.cuda.Event()
+        return v
+
+    # buffers of the view rendered last (bench.py, tools/ and the tests read them)
+    num_isect = property(lambda self: self.cur.num_isect)
+    ids_sorted = property(lambda self: self.cur.ids_sorted)
+    tile_bins = property(lambda self: self.cur.tile_bins)
+    recs = property(lambda self: self.cur.recs)
+    acc = property(lambda self: self.cur.acc)
+    colors = property(lambda self: self.cur.colors)
 
     # ------------------------------------------------------------------------------------------
     def _s(self) -> int:
@@ -190,49 +218,99 @@ class FusedTrainStep:
         self.loss.zero_()
         self._first_view = True
 
-    def view_forward(self, viewmat: torch.Tensor, c2w: torch.Tensor) -> Dict[str, torch.Tensor]:
-        """SH colours + binning + rasterise forward of one camera.  Returns the output buffers (reused per view)."""
+    def _prepare(self, v, viewmat: torch.Tensor, c2w: torch.Tensor, first: bool) -> None:
+        """Bandwidth-bound head of a view on the CURRENT stream: zero-fills, SH colours, project / AABB / count, fused tile
+        binning, record packing.  Records ``v.prep_done``."""
         lib, s, p = self.lib, self._s(), self.p
         n, H, W, bw = self.n, self.H, self.W, self.bw
         fx, fy, cx, cy = self.intr
         P = lambda t: t.data_ptr()  # noqa: E731
-        viewmat, c2w = self._cam(viewmat, "viewmat"), self._cam(c2w, "c2w")
-        # side stream: clear this view's moment lines (and per-view SH colour gradients) while the view is binned / rendered
-        main = torch.cuda.current_stream(self.dev)
-        self.side.wait_stream(main)  # the previous view's epilogue / SH backward have consumed them
-        with torch.cuda.stream(self.side):
-            self.acc.zero_()
-            if self.use_sh and not self._first_view:
-                self.v_colors.zero_()  # SH colours are per view (they feed this view's SH backward), never accumulated
-            self._acc_ready.record(self.side)
+        v.acc.zero_()
+        if self.use_sh and not first:
+            v.v_colors.zero_()  # SH colours are per view (they feed this view's SH backward), never accumulated
         if self.use_sh:
             self._ck(lib.gstex_sh_colors_forward(n, self.sh_degree, self.sh_degree, P(p["means"]), P(c2w),
-                                                 P(p["sh_coeffs"]), P(self.colors), P(self.mask), s), "sh_colors_forward")
+                                                 P(p["sh_coeffs"]), P(v.colors), P(v.mask), s), "sh_colors_forward")
         self._ck(lib.gstex_project_aabb_count(n, P(p["means"]), P(p["scales"]), self.glob_scale, P(p["quats"]), P(viewmat),
-                                              fx, fy, cx, cy, H, W, bw, P(self.centers), P(self.extents), P(self.depths),
-                                              P(self.nth), s), "project_aabb_count")
+                                              fx, fy, cx, cy, H, W, bw, P(v.centers), P(v.extents), P(v.depths),
+                                              P(v.nth), s), "project_aabb_count")
         # fused tile binning: bucket by tile + per-tile shared-memory sort; the intersection count stays on the device
-        self._ck(lib.gstex_bin_tiles(n, P(self.centers), P(self.extents), P(self.depths), self.tiles_x, self.tiles_y, bw,
-                                     self.cap, P(self.ids_sorted), 0, P(self.tile_bins), P(self.num_isect),
-                                     P(self.bin_temp), self.bin_temp.numel(), s), "bin_tiles")
-        torch.maximum(self.max_count_seen, self.num_isect, out=self.max_count_seen)
-        self._ck(lib.gstex_pack_records(n, P(self.texture_dims), P(self.colors), P(p["opacities"]), P(p["means"]),
+        self._ck(lib.gstex_bin_tiles(n, P(v.centers), P(v.extents), P(v.depths), self.tiles_x, self.tiles_y, bw,
+                                     self.cap, P(v.ids_sorted), 0, P(v.tile_bins), P(v.num_isect),
+                                     P(v.bin_temp), v.bin_temp.numel(), s), "bin_tiles")
+        torch.maximum(self.max_count_seen, v.num_isect, out=self.max_count_seen)
+        self._ck(lib.gstex_pack_records(n, P(self.texture_dims), P(v.colors), P(p["opacities"]), P(p["means"]),
                                         P(p["scales"]), self.glob_scale, P(p["quats"]), P(p["uv0"]), P(p["umap"]),
-                                        P(p["vmap"]), P(viewmat), P(c2w), fx, fy, cx, cy, P(self.recs), P(self.mean2d), s),
+                                        P(p["vmap"]), P(viewmat), P(c2w), fx, fy, cx, cy, P(v.recs), P(v.mean2d), s),
                  "pack_records")
-        tex = self.tex4 if self.C == 3 else p["texture"]
+        v.prep_done.record(torch.cuda.current_stream(self.dev))
+        self.launches += int(self.use_sh) + 1 + self._bin_launches + 1  # sh, project, binning, pack
+
+    def _render(self, v, viewmat: torch.Tensor, c2w: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """Rasterise forward of a prepared view on the current stream."""
+        lib, s = self.lib, self._s()
+        fx, fy, cx, cy = self.intr
+        P = lambda t: t.data_ptr()  # noqa: E731
+        tex = self.tex4 if self.C == 3 else self.p["texture"]
         o = self.out
-        if self._first_view:
-            main.wait_event(self._tex_ready)  # padded texture (begin_step, side stream)
         with self._timed("raster_forward"):
-            self._ck(lib.gstex_raster_forward(H, W, bw, self.C, self.settings, P(self.ids_sorted), P(self.tile_bins),
-                                              P(self.recs), P(self.mean2d), P(tex), P(viewmat), P(c2w), fx, fy, cx, cy,
-                                              P(self.background), P(o["out_img"]), P(o["out_depth"]), P(o["out_reg"]),
-                                              P(o["out_texture"]), P(o["out_normal"]), P(o["final_Ts"]),
-                                              P(o["final_idx"]), P(o["depth_idx"]), P(o["out_reg_s"]), P(self.masks), self.cap,
-                                              P(self.num_isect), s), "raster_forward")
-        self.launches += int(self.use_sh) + 1 + self._bin_launches + 1 + 2  # sh, project, binning, pack, mask zero-fill + raster
+            self._ck(lib.gstex_raster_forward(self.H, self.W, self.bw, self.C, self.settings, P(v.ids_sorted),
+                                              P(v.tile_bins), P(v.recs), P(v.mean2d), P(tex), P(viewmat), P(c2w), fx, fy,
+                                              cx, cy, P(self.background), P(o["out_img"]), P(o["out_depth"]),
+                                              P(o["out_reg"]), P(o["out_texture"]), P(o["out_normal"]), P(o["final_Ts"]),
+                                              P(o["final_idx"]), P(o["depth_idx"]), P(o["out_reg_s"]), P(self.masks),
+                                              self.cap, P(v.num_isect), s), "raster_forward")
+        self.launches += 2  # mask zero-fill + raster
+        self.cur = v
         return o
+
+    def _raster_backward(self, v, viewmat: torch.Tensor, c2w: torch.Tensor, vout: Dict[str, torch.Tensor]) -> None:
+        lib, s = self.lib, self._s()
+        fx, fy, cx, cy = self.intr
+        P = lambda t: t.data_ptr()  # noqa: E731
+        o = self.out
+        tex = self.tex4 if self.C == 3 else self.p["texture"]
+        vtex = self.vtex4 if self.C == 3 else self.grads["v_texture"]
+        with self._timed("raster_backward"):
+            self._ck(lib.gstex_raster_backward(self.H, self.W, self.bw, self.C, self.settings, P(v.ids_sorted),
+                                               P(v.tile_bins), P(v.recs), P(v.mean2d), P(tex), P(viewmat), P(c2w), fx, fy,
+                                               cx, cy, P(self.background), P(o["final_Ts"]), P(o["final_idx"]),
+                                               P(o["depth_idx"]), P(o["out_reg_s"]), P(vout["v_out_img"]),
+                                               P(vout["v_out_depth"]), P(vout["v_out_reg"]), P(vout["v_out_alpha"]),
+                                               P(vout["v_out_texture"]), P(vout["v_out_normal"]), P(self.masks), P(v.acc),
+                                               P(vtex), s), "raster_backward")
+        v.bwd_done.record(torch.cuda.current_stream(self.dev))
+        self.launches += 1
+
+    def _tail(self, v, viewmat: torch.Tensor, c2w: torch.Tensor, first: bool) -> None:
+        """Bandwidth-bound tail of a view on the CURRENT stream: per-Gaussian epilogue (moments -> parameter gradients,
+        accumulated into the arena) and SH backward."""
+        lib, s, p, g = self.lib, self._s(), self.p, self.grads
+        fx, fy, cx, cy = self.intr
+        P = lambda t: t.data_ptr()  # noqa: E731
+        acc_flag = 0 if first else 1
+        self._ck(lib.gstex_raster_epilogue(self.n, P(p["means"]), P(p["scales"]), self.glob_scale, P(p["quats"]),
+                                           P(p["umap"]), P(p["vmap"]), P(viewmat), P(c2w), fx, fy, cx, cy, P(v.acc),
+                                           P(v.v_colors), P(g["v_opacity"]), P(g["v_means"]), P(g["v_scales"]),
+                                           P(g["v_quats"]), P(g["v_uv0"]), P(g["v_umap"]), P(g["v_vmap"]), acc_flag, s),
+                 "raster_epilogue")
+        if self.use_sh:
+            self._ck(lib.gstex_sh_colors_backward(self.n, self.sh_degree, self.sh_degree, P(p["means"]), P(c2w),
+                                                  P(v.v_colors), P(v.mask), P(g["v_sh_coeffs"]), acc_flag, s),
+                     "sh_colors_backward")
+        self.launches += 1 + int(self.use_sh)
+
+    # ---- one view at a time (tests, tools, callers that inject their own loss) -------------------------------------
+    def view_forward(self, viewmat: torch.Tensor, c2w: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """SH colours + binning + rasterise forward of one camera.  Returns the output buffers (reused per view)."""
+        viewmat, c2w = self._cam(viewmat, "viewmat"), self._cam(c2w, "c2w")
+        main = torch.cuda.current_stream(self.dev)
+        v = self.sets[0]
+        self.side.wait_stream(main)  # the previous view's backward / tail have consumed this set
+        with torch.cuda.stream(self.side):
+            self._prepare(v, viewmat, c2w, self._first_view)
+        main.wait_event(v.prep_done)  # the side stream is in order: this also covers begin_step's padding / fills
+        return self._render(v, viewmat, c2w)
 
     def view_loss(self, target: torch.Tensor) -> None:
         """example.py:189-209 loss, accumulated into self.loss; fills the upstream-gradient buffers."""
@@ -246,34 +324,10 @@ class FusedTrainStep:
 
     def view_backward(self, viewmat: torch.Tensor, c2w: torch.Tensor, vout: Optional[Dict[str, torch.Tensor]] = None) -> None:
         """Rasterise backward + epilogue + SH backward of the view last rendered; accumulates into the arena."""
-        lib, s, p = self.lib, self._s(), self.p
-        n, H, W, bw = self.n, self.H, self.W, self.bw
-        fx, fy, cx, cy = self.intr
-        P = lambda t: t.data_ptr()  # noqa: E731
-        v = vout if vout is not None else self.vout
         viewmat, c2w = self._cam(viewmat, "viewmat"), self._cam(c2w, "c2w")
-        o, g = self.out, self.grads
-        acc_flag = 0 if self._first_view else 1
-        torch.cuda.current_stream(self.dev).wait_event(self._acc_ready)  # zero-fills of view_forward (side stream)
-        tex = self.tex4 if self.C == 3 else p["texture"]
-        vtex = self.vtex4 if self.C == 3 else g["v_texture"]
-        with self._timed("raster_backward"):
-            self._ck(lib.gstex_raster_backward(H, W, bw, self.C, self.settings, P(self.ids_sorted), P(self.tile_bins),
-                                               P(self.recs), P(self.mean2d), P(tex), P(viewmat), P(c2w), fx, fy, cx, cy,
-                                               P(self.background), P(o["final_Ts"]), P(o["final_idx"]),
-                                               P(o["depth_idx"]), P(o["out_reg_s"]), P(v["v_out_img"]),
-                                               P(v["v_out_depth"]), P(v["v_out_reg"]), P(v["v_out_alpha"]),
-                                               P(v["v_out_texture"]), P(v["v_out_normal"]), P(self.masks), P(self.acc), P(vtex), s),
-                     "raster_backward")
-        self.launches += 2 + int(self.use_sh)  # raster backward, epilogue, SH backward
-        self._ck(lib.gstex_raster_epilogue(n, P(p["means"]), P(p["scales"]), self.glob_scale, P(p["quats"]), P(p["umap"]),
-                                           P(p["vmap"]), P(viewmat), P(c2w), fx, fy, cx, cy, P(self.acc), P(self.v_colors),
-                                           P(g["v_opacity"]), P(g["v_means"]), P(g["v_scales"]), P(g["v_quats"]),
-                                           P(g["v_uv0"]), P(g["v_umap"]), P(g["v_vmap"]), acc_flag, s), "raster_epilogue")
-        if self.use_sh:
-            self._ck(lib.gstex_sh_colors_backward(n, self.sh_degree, self.sh_degree, P(p["means"]), P(c2w),
-                                                  P(self.v_colors), P(self.mask), P(g["v_sh_coeffs"]), acc_flag, s),
-                     "sh_colors_backward")
+        v = self.cur
+        self._raster_backward(v, viewmat, c2w, vout if vout is not None else self.vout)
+        self._tail(v, viewmat, c2w, self._first_view)
         self._first_view = False
 
     def end_step(self) -> None:
@@ -290,12 +344,32 @@ class FusedTrainStep:
             self.launches += 1
 
     def step(self, cameras: Sequence[Tuple[torch.Tensor, torch.Tensor]], targets: Sequence[torch.Tensor]) -> torch.Tensor:
-        """forward + loss + backward for every (viewmat, c2w) of this rank; returns the summed loss (device)."""
+        """forward + loss + backward for every (viewmat, c2w) of this rank; returns the summed loss (device).
+
+        Two-stream pipeline: the caller's stream runs [rasterise forward, loss, rasterise backward] of view k while the
+        side stream runs the head of view k+1 and the tail of view k-1 (see the module docstring).  Gradients reach the
+        arena in view order (the tails are serialised on the side stream), exactly as in a serial loop."""
+        cams = [(self._cam(a, "viewmat"), self._cam(b, "c2w")) for a, b in cameras]
+        main, side = torch.cuda.current_stream(self.dev), self.side
         self.begin_step()
-        for (viewmat, c2w), target in zip(cameras, targets):
-            self.view_forward(viewmat, c2w)
-            self.view_loss(target)
-            self.view_backward(viewmat, c2w)
+        nv = len(cams)
+        if nv:
+            with torch.cuda.stream(side):
+                self._prepare(self.sets[0], *cams[0], True)
+        for k in range(nv):
+            v, (viewmat, c2w) = self.sets[k & 1], cams[k]
+            if k + 1 < nv:  # head of the next view, underneath this view's rasterisers (its set was freed by tail k-1,
+                with torch.cuda.stream(side):  # which precedes it on the side stream)
+                    self._prepare(self.sets[(k + 1) & 1], *cams[k + 1], False)
+            main.wait_event(v.prep_done)
+            self._render(v, viewmat, c2w)
+            self.view_loss(targets[k])
+            self._raster_backward(v, viewmat, c2w, self.vout)
+            with torch.cuda.stream(side):  # tail of this view, underneath the next view's rasterisers
+                side.wait_event(v.bwd_done)
+                self._tail(v, viewmat, c2w, k == 0)
+        main.wait_stream(side)
+        self._first_view = False
         self.end_step()
         return self.loss
 
