@@ -130,7 +130,7 @@ class FusedTrainStep:
         # does not depend on them (texture padding, zero-fills of the moment lines / texel-gradient buffer) runs on a
         # side stream underneath binning and the forward rasteriser and is joined with events where its result is needed.
         # default priority: measured on C5 (8 views/step, 1 GPU) a high-priority side stream only moves time from its own
-        # kernels into the rasterisers they displace (32.7 ms vs 32.4 ms per step; serial loop 33.6 ms)
+        # kernels into the rasterisers they displace (32.7 ms vs 32.4 ms per step)
         self.side = torch.cuda.Stream(device=dev)
         self._tex_ready = torch.cuda.Event()
 
