@@ -309,15 +309,31 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, GSTEX_BWD_MINB) raster_bac
         px.pix = C3 ? 0 : __shfl_sync(full, me.pix, pl);
     };
 
+    static_assert(BWD_BATCH == 64, "the mask prefetch below holds one batch as two words per lane");
+    // mask words and ids of batch b+1 are fetched while batch b is processed (two entries per lane)
+    uint32_t nx_m0 = 0u, nx_m1 = 0u;
+    int32_t nx_g0 = 0, nx_g1 = 0;
+    auto fetch_batch = [&](int b) {
+        const int first = max(range.x, hi - (b + 1) * BWD_BATCH), cnt = (hi - b * BWD_BATCH) - first;
+        const int r0 = lane, r1 = lane + 32;
+        nx_m0 = r0 < cnt ? __ldg(p.masks + (size_t)(first + r0) * MASK_WARPS + warp) : 0u;
+        nx_g0 = r0 < cnt ? __ldg(p.ids + first + r0) : 0;
+        nx_m1 = r1 < cnt ? __ldg(p.masks + (size_t)(first + r1) * MASK_WARPS + warp) : 0u;
+        nx_g1 = r1 < cnt ? __ldg(p.ids + first + r1) : 0;
+    };
+    fetch_batch(0);
     for (int b = 0; b < nbatch; ++b) {
         // batch b covers [first, first + cnt) counted from the back of [range.x, hi)
         const int first = max(range.x, hi - (b + 1) * BWD_BATCH), cnt = (hi - b * BWD_BATCH) - first;
         // this warp's non-empty mask words of the batch (and the Gaussian ids), compacted in list order
         int nsurv = 0;
+        const uint32_t cm0 = nx_m0, cm1 = nx_m1;
+        const int32_t cg0 = nx_g0, cg1 = nx_g1;
+        if (b + 1 < nbatch) fetch_batch(b + 1);
         for (int k = 0; k < cnt; k += 32) {
             const int r = k + lane;
-            const uint32_t mw = r < cnt ? __ldg(p.masks + (size_t)(first + r) * MASK_WARPS + warp) : 0u;
-            const int32_t g = r < cnt ? __ldg(p.ids + first + r) : 0;
+            const uint32_t mw = k ? cm1 : cm0;
+            const int32_t g = k ? cg1 : cg0;
             const unsigned m = __ballot_sync(full, mw != 0u);
             if (mw != 0u) {
                 const int pos = nsurv + __popc(m & lt);
@@ -353,6 +369,13 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, GSTEX_BWD_MINB) raster_bac
                 np = __shfl_sync(full, incl, ne - 1);
                 const int off = incl - cs;
                 if (lane < ne) W.ch_off[lane] = (uint16_t)off;
+                // stage the records of the chunk's entries (8 lanes fetch one 128-byte record); the copies fly while
+                // the pair queue is being written
+                for (int t = lane; t < ne * 8; t += 32) {
+                    const int j = t >> 3, q = t & 7;
+                    __pipeline_memcpy_async(W.rec + quad_slot(j, q), p.recs + (size_t)W.sv_gid[si0 - j] * 8 + q, 16);
+                }
+                __pipeline_commit();
                 unsigned mm = (lane < ne && sparse) ? m : 0u;
                 int slot = off;
                 while (__any_sync(full, mm != 0u)) {
@@ -363,14 +386,6 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, GSTEX_BWD_MINB) raster_bac
                     }
                 }
                 si = si0 - ne;
-            }
-            // stage the records of the chunk's entries: 8 lanes fetch one 128-byte record
-            {
-                for (int t = lane; t < ne * 8; t += 32) {
-                    const int j = t >> 3, q = t & 7;
-                    __pipeline_memcpy_async(W.rec + quad_slot(j, q), p.recs + (size_t)W.sv_gid[si0 - j] * 8 + q, 16);
-                }
-                __pipeline_commit();
                 __pipeline_wait_prior(0);
             }
             __syncwarp();
