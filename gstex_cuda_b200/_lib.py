@@ -65,6 +65,9 @@ _PROTOS = {
     "gstex_sigmoid_pad_texture": (c_i, [c_i64, c_fp, c_fp, c_fp]),
     "gstex_unpad_texture_grad_sigmoid": (c_i, [c_i64, c_fp, c_fp, c_fp, c_i, c_fp]),
     "gstex_adam_step": (c_i, [c_i64, c_fp, c_fp, c_fp, c_fp] + [C.c_double] * 4 + [c_i, c_f, c_fp]),
+    "gstex_adam_state_bytes": (c_sz, []),
+    "gstex_adam_step_device": (c_i, [c_i64, c_fp, c_fp, c_fp, c_fp, C.c_double, C.c_double, C.c_double, C.c_double, c_fp,
+                                     c_f, c_fp]),
 }
 
 # entry points that may be absent from an older build of the library (checked lazily)

@@ -143,9 +143,33 @@ __device__ __forceinline__ void adam_one(float &p, float g, float &m, float &v, 
     p = p - a.lr_over_bc1 * (m / denom);
 }
 
+// Device-resident optimiser state for CUDA-graph replay: the step counter and the scalars derived from it live in
+// memory, so that the same captured launch computes a different bias correction every replay.
+struct AdamDeviceState {
+    int32_t step;
+    int32_t pad[3];
+    AdamArgs args;
+};
+
+// one thread: ++step, then the scalars exactly as the host path forms them (double arithmetic, rounded to fp32 once)
+__global__ void adam_prepare_kernel(AdamDeviceState *st, double lr, double beta1, double beta2, double eps,
+                                    float grad_scale) {
+    const int step = ++st->step;
+    const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+    AdamArgs a;
+    a.lr_over_bc1 = (float)(lr / bc1);
+    a.sqrt_bc2 = (float)sqrt(bc2);
+    a.beta1 = (float)beta1; a.beta2 = (float)beta2; a.eps = (float)eps; a.grad_scale = grad_scale;
+    a.omb1 = (float)(1.0 - beta1);
+    a.omb2 = (float)(1.0 - beta2);
+    st->args = a;
+}
+
 __global__ void __launch_bounds__(256) adam_step_kernel(int64_t count, float *__restrict__ p,
                                                         const float *__restrict__ g, float *__restrict__ m,
-                                                        float *__restrict__ v, const AdamArgs a, int vec4) {
+                                                        float *__restrict__ v, const AdamArgs a_host,
+                                                        const AdamDeviceState *__restrict__ st, int vec4) {
+    const AdamArgs a = st ? st->args : a_host;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (vec4) {
@@ -240,7 +264,25 @@ extern "C" int gstex_adam_step(int64_t count, float *params, const float *grads,
     a.omb2 = (float)(1.0 - beta2);
     const int vec4 = (((uintptr_t)params | (uintptr_t)grads | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) % 16) == 0;
     const int blocks = (int)min((int64_t)148 * 8, ceil_div64(vec4 ? ceil_div64(count, 4) : count, 256));
-    adam_step_kernel<<<blocks, 256, 0, as_stream(stream)>>>(count, params, grads, exp_avg, exp_avg_sq, a, vec4);
+    adam_step_kernel<<<blocks, 256, 0, as_stream(stream)>>>(count, params, grads, exp_avg, exp_avg_sq, a, nullptr, vec4);
+    GSTEX_LAUNCH_OK("adam_step_kernel");
+    return GSTEX_OK;
+}
+
+extern "C" size_t gstex_adam_state_bytes(void) { return sizeof(AdamDeviceState); }
+
+extern "C" int gstex_adam_step_device(int64_t count, float *params, const float *grads, float *exp_avg,
+                                      float *exp_avg_sq, double lr, double beta1, double beta2, double eps,
+                                      void *state, float grad_scale, gstex_stream_t stream) {
+    GSTEX_REQUIRE(count >= 0 && state != nullptr, GSTEX_E_INVALID, "adam_step_device: count = %lld, state = %p",
+                  (long long)count, state);
+    AdamDeviceState *st = (AdamDeviceState *)state;
+    adam_prepare_kernel<<<1, 1, 0, as_stream(stream)>>>(st, lr, beta1, beta2, eps, grad_scale);
+    GSTEX_LAUNCH_OK("adam_prepare_kernel");
+    if (count == 0) return GSTEX_OK;
+    const int vec4 = (((uintptr_t)params | (uintptr_t)grads | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) % 16) == 0;
+    const int blocks = (int)min((int64_t)148 * 8, ceil_div64(vec4 ? ceil_div64(count, 4) : count, 256));
+    adam_step_kernel<<<blocks, 256, 0, as_stream(stream)>>>(count, params, grads, exp_avg, exp_avg_sq, AdamArgs{}, st, vec4);
     GSTEX_LAUNCH_OK("adam_step_kernel");
     return GSTEX_OK;
 }

@@ -11,6 +11,11 @@ on the way back, and a 7-tensor ``torch.optim.Adam`` step.  Here the whole itera
 with no host synchronisation.  Raw parameters, their gradients and both Adam moments live in four contiguous
 fp32 arenas with the same field layout, so the collective and the optimiser each touch one buffer.
 
+Because nothing in the iteration depends on the host - the intersection count stays on the device, and so does Adam's
+step counter (``gstex_adam_step_device``) - a whole optimiser step can be captured into ONE CUDA graph
+(``capture()`` / ``replay()``): the ~25 launches of a small scene (BASELINE configs 1-3 are launch-bound) become one
+graph launch.
+
 Parameter names follow example.py:69-119: ``means``, ``scales`` (log), ``quats`` (un-normalised), ``opacities``
 (pre-sigmoid), ``mapping`` (N,1,4) = (u0, v0, log uv-scale, theta), ``texture`` (pre-sigmoid, (X,3)), and for the
 colours either ``rgbs`` (pre-sigmoid, example.py:162) or ``sh_coeffs`` (N,K,3) with colours = clamp(SH + 0.5, 0, 1)
@@ -70,7 +75,10 @@ class GStexTrainStep:
         self.n, self.X = n, X
         self.lr, self.betas, self.eps, self.grad_scale = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(grad_scale)
         self.rank, self.world_size, self.group = int(rank), int(world_size), group
-        self.step_count = 0
+        self.step_count = 0  # host mirror of the device-resident step counter (adam_state)
+        self.adam_state = torch.zeros(self.lib.gstex_adam_state_bytes(), dtype=torch.uint8, device=dev)
+        self._graph = None
+        self._graph_loss = None
 
         # activated parameters (what the rasteriser consumes) and the gradients w.r.t. them
         self.act = dict(scales=torch.empty((n, 3), **f32), quats=torch.empty((n, 4), **f32),
@@ -131,18 +139,50 @@ class GStexTrainStep:
         return loss
 
     def optimizer_step(self) -> None:
-        """torch.optim.Adam's update over the parameter arena (example.py:223-225, :278); one launch."""
+        """torch.optim.Adam's update over the parameter arena (example.py:223-225, :278); the step counter and its bias
+        corrections live on the device, so the call is the same every iteration (and CUDA-graph replayable)."""
         self.step_count += 1
         P = lambda t: t.data_ptr()  # noqa: E731
-        _lib.check(self.lib.gstex_adam_step(self.n_train, P(self.param_arena), P(self.grad_arena), P(self.exp_avg),
-                                            P(self.exp_avg_sq), self.lr, self.betas[0], self.betas[1], self.eps,
-                                            self.step_count, self.grad_scale, self._s()), "adam_step")
-        self.launches += 1
+        _lib.check(self.lib.gstex_adam_step_device(self.n_train, P(self.param_arena), P(self.grad_arena), P(self.exp_avg),
+                                                   P(self.exp_avg_sq), self.lr, self.betas[0], self.betas[1], self.eps,
+                                                   P(self.adam_state), self.grad_scale, self._s()), "adam_step")
+        self.launches += 2
 
     def step(self, cameras, targets) -> torch.Tensor:
         loss = self.forward_backward(cameras, targets)
         self.optimizer_step()
         return loss
+
+    # ---- CUDA graph of one whole optimiser step ------------------------------------------------------------------
+    def capture(self, cameras: Sequence[Tuple[torch.Tensor, torch.Tensor]], targets: Sequence[torch.Tensor]) -> None:
+        """Capture ``step(cameras, targets)`` into a CUDA graph.  The camera matrices and target images are captured BY
+        ADDRESS: write new views into the same tensors (``copy_``) before a ``replay()``.  One eager warm-up step runs
+        first (kernel loading, allocator) and its effect on the parameters and optimiser state is rolled back, so
+        capture() itself does not train.  Single-process only (the NCCL all-reduce is left out of graphs here)."""
+        if self.world_size > 1:
+            raise RuntimeError("GStexTrainStep.capture(): graph capture is single-process; with world_size > 1 call step()")
+        saved = [t.clone() for t in (self.param_arena, self.exp_avg, self.exp_avg_sq, self.adam_state)]
+        count, launches, fused_launches = self.step_count, self.launches, self.fused.launches
+        self.step(cameras, targets)
+        self.fused.check_overflow()
+        for dst, src in zip((self.param_arena, self.exp_avg, self.exp_avg_sq, self.adam_state), saved):
+            dst.copy_(src)
+        self.step_count = count
+        torch.cuda.synchronize(self.dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            loss = self.step(cameras, targets)
+        # capturing enqueues nothing: undo the bookkeeping of the captured call
+        self.step_count, self.launches, self.fused.launches = count, launches, fused_launches
+        self._graph, self._graph_loss = graph, loss
+
+    def replay(self) -> torch.Tensor:
+        """One optimiser step = one graph launch.  Returns the (device) loss tensor of the captured step."""
+        if self._graph is None:
+            raise RuntimeError("GStexTrainStep.replay() before capture()")
+        self._graph.replay()
+        self.step_count += 1
+        return self._graph_loss
 
     @property
     def total_launches(self) -> int:

@@ -316,6 +316,15 @@ int gstex_unpad_texture_grad_sigmoid(int64_t num_texels, const float *g4, const 
 int gstex_adam_step(int64_t count, float *params, const float *grads, float *exp_avg, float *exp_avg_sq, double lr,
                     double beta1, double beta2, double eps, int step, float grad_scale, gstex_stream_t stream);
 
+/* The same update with the step counter (and the scalars derived from it) in device memory, for CUDA-graph replay of a
+ * whole optimiser step: `state` is gstex_adam_state_bytes() bytes, zero-filled before the first step; every call
+ * increments the counter on the device (one extra 1-thread launch), then applies the update with that step's bias
+ * corrections - bit-identical to gstex_adam_step(step = 1, 2, 3, ...). */
+size_t gstex_adam_state_bytes(void);
+int gstex_adam_step_device(int64_t count, float *params, const float *grads, float *exp_avg, float *exp_avg_sq,
+                           double lr, double beta1, double beta2, double eps, void *state, float grad_scale,
+                           gstex_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -256,3 +256,50 @@ def test_fused_trainer_matches_reference_shaped_trainer(mode, views, N, H, W):
             assert bad.mean() <= 5e-3, f"iteration {it}: parameter {k}: {bad.mean():.2e} of entries off"
     fused.fused.check_overflow()
     assert float(np.abs(to_np(fused.raw["mapping"]) - to_np(raw["mapping"])).max()) == 0.0  # frozen (example.py:118)
+
+
+def test_cuda_graph_replay_matches_eager_steps():
+    """GStexTrainStep.capture()/replay(): one CUDA graph per optimiser step (device-resident Adam step counter, no host
+    sync anywhere in the step) against the same steps launched eagerly; prints the per-step time of both on the
+    example.py default configuration (BASELINE config 2: 256x256, 100 Gaussians, 101x101 texels each)."""
+    import time
+    N, H, W = 100, 256, 256
+    raw, dims, intr = example_raw(N, H, W, 101, 101, seed=3)
+    vm = torch.eye(4, device=DEV)
+    vm[2, 3] = 8.0
+    cams = [(vm.contiguous(), torch.linalg.inv(vm).contiguous())]
+    targets = [torch.rand(H, W, 3, generator=torch.Generator().manual_seed(4)).to(DEV)]
+    bg = torch.zeros(3, device=DEV)
+    mk = lambda: GStexTrainStep(raw, dims, H, W, intrins=intr, sh_degree=3, lr=0.01, background=bg, max_intersects=64 * N)  # noqa: E731
+    eager, graphed = mk(), mk()
+    graphed.capture(cams, targets)
+    # capture() does not train: parameters and optimiser state are where they started
+    assert torch.equal(graphed.param_arena, eager.param_arena) and graphed.step_count == 0
+    assert float(graphed.exp_avg.abs().max()) == 0.0
+    losses_e, losses_g = [], []
+    for _ in range(5):
+        losses_e.append(float(eager.step(cams, targets)))
+        losses_g.append(float(graphed.replay()))
+    assert graphed.step_count == eager.step_count == 5
+    assert losses_e[-1] < losses_e[0]  # it trains
+    for a, b in zip(losses_e, losses_g):
+        assert abs(a - b) <= 2e-3 * abs(a) + 1e-6, (losses_e, losses_g)
+    for k in eager.raw:
+        got, ref = to_np(graphed.raw[k]), to_np(eager.raw[k])
+        bad = np.abs(got - ref) > 2e-4 + 1e-4 * np.abs(ref)  # atomic-order noise through Adam (see the test above)
+        assert bad.mean() <= 5e-3, f"parameter {k}: {bad.mean():.2e} of entries differ between graph replay and eager"
+
+    def per_step(fn, iters=200):
+        for _ in range(20):
+            fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            fn()
+        torch.cuda.synchronize()
+        return 1e6 * (time.perf_counter() - t0) / iters
+
+    t_e, t_g = per_step(lambda: eager.step(cams, targets)), per_step(graphed.replay)
+    print(f"  BASELINE config 2 optimiser step: eager {t_e:.0f} us, CUDA graph replay {t_g:.0f} us "
+          f"({eager.total_launches // max(1, eager.step_count)} launches -> 1)")
+    assert t_g < t_e
