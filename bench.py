@@ -387,6 +387,20 @@ def run_e2e(args, scene, cams, mine, targets_host, dev, world, views):
         return (cams_host[v][0], cams_host[v][1], targets_host[v])
 
     loader.submit(host_inputs(order[0]))
+    loss_host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ready = [torch.cuda.Event() for _ in range(2)]
+    state = {"k": 0, "pending": None}
+    losses = []
+
+    def read_pending():
+        """Host value of the most recent step whose loss copy was issued (waits for that copy only)."""
+        k = state["pending"]
+        if k is None:
+            return None
+        loss_ready[k].synchronize()
+        state["pending"] = None
+        losses.append(float(loss_host[k][0]))
+        return losses[-1]
 
     def one_step():
         total = None
@@ -409,7 +423,14 @@ def run_e2e(args, scene, cams, mine, targets_host, dev, world, views):
         if world > 1:
             for t in leaves.values():
                 dist.all_reduce(t.grad)
-        val = float(total.item())  # device -> host read of the step's result
+        # device -> host read of the step's result, every step: an asynchronous copy into pinned memory that is
+        # consumed one step later, so that reading the loss of step k does not drain the queue before step k+1 is
+        # enqueued (the usual way a training loop logs its loss); read_pending() collects the last one
+        k = state["k"] & 1
+        loss_host[k].copy_(total.reshape(1), non_blocking=True)
+        loss_ready[k].record()
+        val = read_pending()
+        state["pending"], state["k"] = k, state["k"] + 1
         for t in leaves.values():
             t.grad = None
         return val
@@ -419,14 +440,18 @@ def run_e2e(args, scene, cams, mine, targets_host, dev, world, views):
     for _ in range(2):
         one_step()
     loader.bytes_copied = 0
+    read_pending()  # the warm-up's last loss: nothing of the warm-up is left to read inside the timed region
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    n_read0 = len(losses)
     for _ in range(steps):
         one_step()
+    read_pending()  # the last step's loss is read inside the timed region too
     e1.record()
+    assert len(losses) - n_read0 == steps, "every timed step's loss must have been read back"
     loader_steps[0] = steps
     if world > 1:
         dist.barrier()
@@ -439,7 +464,8 @@ def run_e2e(args, scene, cams, mine, targets_host, dev, world, views):
             "d2h_bytes_per_step": 4, "ms_per_step": ms, "steps": steps,
             "api": "spherical_harmonics_colors + project_points + get_aabb_2d + get_num_tiles_hit_2d + texture_gaussians + "
                    "image_loss (the example.py loss), all autograd ops of the package; inputs staged by gstex_cuda_b200.prefetch.ViewPrefetcher "
-                   "(pinned host -> device on a copy stream, one view ahead)",
+                   "(pinned host -> device on a copy stream, one view ahead); the loss of every step is read back through "
+                   "an asynchronous copy into pinned memory, consumed one step later",
             "h2d_bytes_measured_per_step": int(loader.bytes_copied // max(1, loader_steps[0]))}
 
 

@@ -126,8 +126,9 @@ _RASTER_IN = ("texture_dims", "gaussian_ids_sorted", "tile_bins", "colors", "opa
 def _check_raster_inputs(texture_dims, gaussian_ids_sorted, tile_bins, colors, opacities, means, scales, quats, uv0,
                          umap, vmap, texture, viewmat, c2w, background):
     _chk("texture_dims", texture_dims, torch.int32)
-    _chk("gaussian_ids_sorted", gaussian_ids_sorted, torch.int32)
-    _chk("tile_bins", tile_bins, torch.int32)
+    if gaussian_ids_sorted is not None:  # None: the caller bins after this check (texture.py)
+        _chk("gaussian_ids_sorted", gaussian_ids_sorted, torch.int32)
+        _chk("tile_bins", tile_bins, torch.int32)
     for n, t in (("colors", colors), ("opacities", opacities), ("means", means), ("scales", scales), ("quats", quats),
                  ("uv0", uv0), ("umap", umap), ("vmap", vmap), ("texture", texture), ("viewmat", viewmat),
                  ("c2w", c2w), ("background", background)):

@@ -11,8 +11,9 @@ import torch
 from torch import Tensor
 from torch.autograd import Function
 
+from . import _lib
 from . import cuda as _C
-from .utils import bin_and_sort_gaussians, bin_tiles, compute_cumulative_intersects  # noqa: F401
+from .utils import bin_and_sort_gaussians, bin_tiles, compute_cumulative_intersects, cumsum_i32  # noqa: F401
 
 
 def texture_gaussians(texture_info: Tuple[int, int, int], texture_dims: Tensor, centers: Tensor, extents: Tensor,
@@ -44,43 +45,88 @@ def texture_gaussians(texture_info: Tuple[int, int, int], texture_dims: Tensor, 
         background.contiguous())
 
 
+def _p(t) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
 class _TextureGaussians(Function):
+    """Host side of texture_forward_tensor / texture_backward_tensor (reference texture.py:156-408) over the staged C-ABI
+    entry points: pack -> pad -> [intersection count read back] -> fused tile binning -> rasterise forward, and
+    rasterise backward -> per-Gaussian epilogue -> un-pad.  The one host synchronisation the reference has per call
+    (``num_intersects = cum_tiles_hit[-1].item()``, utils.py:58) is kept - the output sizes depend on it - but the copy
+    is asynchronous and everything that does not depend on the count (output allocation, record packing, texture
+    padding) is enqueued before the host waits for it, so the GPU keeps working through the round trip."""
+
     @staticmethod
     def forward(ctx, texture_info, texture_dims, centers, extents, depths, num_tiles_hit, colors, opacity, means,
                 scales, glob_scale, quats, uv0, umap, vmap, texture, viewmat, c2w, fx, fy, cx, cy, img_height,
                 img_width, block_width, settings, background):
-        num_points = centers.size(0)
-        tile_bounds = ((img_width + block_width - 1) // block_width, (img_height + block_width - 1) // block_width, 1)
-        block = (block_width, block_width, 1)
-        img_size = (img_width, img_height, 1)
+        lib = _lib.load()
+        H, W, bw = int(img_height), int(img_width), int(block_width)
+        tile_bounds = ((W + bw - 1) // bw, (H + bw - 1) // bw, 1)
         dev = centers.device
-        num_intersects, cum_tiles_hit = compute_cumulative_intersects(num_tiles_hit)
-        ctx.num_intersects = num_intersects
         C = int(texture_info[2])
+        n, X = means.shape[0], texture.shape[0]
+        _C._check_raster_inputs(texture_dims, None, None, colors, opacity, means, scales, quats, uv0, umap, vmap, texture,
+                                viewmat, c2w, background)
+        if texture.dim() != 2 or texture.shape[1] != C:
+            raise RuntimeError(f"texture must have dimensions (X, {C})")
+        f32, i32 = dict(dtype=torch.float32, device=dev), dict(dtype=torch.int32, device=dev)
+        stream = torch.cuda.current_stream(dev)
+        s = stream.cuda_stream
+        fx, fy, cx, cy = float(fx), float(fy), float(cx), float(cy)
+        with torch.cuda.device(dev):
+            # 1. inclusive scan of the tile counts; its last element starts travelling to the host
+            count_host, count_ready = None, None
+            if n > 0:
+                cum = cumsum_i32(num_tiles_hit.reshape(-1))
+                count_host = torch.empty((1,), dtype=torch.int32, pin_memory=True)
+                count_host.copy_(cum[-1:], non_blocking=True)
+                count_ready = torch.cuda.Event()
+                count_ready.record(stream)
+            # 2. everything that does not depend on the count
+            out_img, out_depth, out_reg = torch.empty((H, W, 3), **f32), torch.empty((H, W), **f32), torch.empty((H, W), **f32)
+            out_texture, out_normal = torch.empty((H, W, C), **f32), torch.empty((H, W, 3), **f32)
+            final_Ts, final_idx, depth_idx = torch.empty((H, W), **f32), torch.empty((H, W), **i32), torch.empty((H, W), **i32)
+            out_reg_s = torch.empty((H, W, 3), **f32)
+            recs, mean2d = torch.empty((max(n, 1), 32), **f32), torch.empty((max(n, 1), 2), **f32)
+            tex4 = torch.empty((max(X, 1), 4), **f32) if C == 3 else None
+            if n > 0:
+                _lib.check(lib.gstex_pack_records(n, _p(texture_dims), _p(colors), _p(opacity), _p(means), _p(scales),
+                                                  float(glob_scale), _p(quats), _p(uv0), _p(umap), _p(vmap), _p(viewmat),
+                                                  _p(c2w), fx, fy, cx, cy, _p(recs), _p(mean2d), s), "pack_records")
+            if C == 3 and X > 0:
+                _lib.check(lib.gstex_pad_texture(X, _p(texture), _p(tex4), s), "pad_texture")
+            # 3. the count (the reference's one sync per call)
+            num_intersects = 0
+            if count_ready is not None:
+                count_ready.synchronize()
+                num_intersects = int(count_host[0])
+        ctx.num_intersects = num_intersects
         if num_intersects < 1:
             # upstream leaves several outputs undefined in this branch (texture.py:197-205, :254-289);
             # we return the background-only image and zeros
-            f32 = dict(dtype=torch.float32, device=dev)
-            out_img = torch.ones(img_height, img_width, colors.shape[-1], **f32) * background
-            zeros = torch.zeros(img_height, img_width, **f32)
+            out_img = torch.ones(H, W, colors.shape[-1], **f32) * background
+            zeros = torch.zeros(H, W, **f32)
             ctx.save_for_backward(colors, opacity, means, scales, quats, uv0, umap, vmap, texture)
-            return (out_img, zeros, zeros.clone(), zeros.clone(), torch.zeros(img_height, img_width, C, **f32),
-                    torch.zeros(img_height, img_width, 3, **f32))
-        # same gaussian_ids_sorted / tile_bins as bin_and_sort_gaussians (utils.py:106-162 upstream), from the fused
-        # bucket-by-tile + per-tile sort (csrc/binning_tiles.cu) instead of the global 64-bit key sort
-        gaussian_ids_sorted, tile_bins, _, _ = bin_tiles(centers, extents, depths, tile_bounds, block_width,
-                                                         num_intersects)
-        outputs, scratch = _C.texture_forward_ex(
-            tile_bounds, block, img_size, texture_info, texture_dims, gaussian_ids_sorted, tile_bins, colors, opacity,
-            means, scales, glob_scale, quats, uv0, umap, vmap, texture, viewmat, c2w, fx, fy, cx, cy, settings,
-            background)
-        out_img, out_depth, out_reg, out_texture, out_normal, final_Ts, final_idx, depth_idx, out_reg_s = outputs
-        ctx.img_width, ctx.img_height, ctx.block_width = img_width, img_height, block_width
-        ctx.texture_info, ctx.settings, ctx.glob_scale = texture_info, settings, glob_scale
+            return (out_img, zeros, zeros.clone(), zeros.clone(), torch.zeros(H, W, C, **f32), torch.zeros(H, W, 3, **f32))
+        # 4. same gaussian_ids_sorted / tile_bins as bin_and_sort_gaussians (utils.py:106-162 upstream), from the fused
+        #    bucket-by-tile + per-tile sort (csrc/binning_tiles.cu) instead of the global 64-bit key sort
+        gaussian_ids_sorted, tile_bins, _, _ = bin_tiles(centers, extents, depths, tile_bounds, bw, num_intersects)
+        masks = torch.empty((num_intersects, 8), **i32)  # blend masks: forward -> backward (csrc/raster.cuh)
+        tex = tex4 if C == 3 else texture
+        with torch.cuda.device(dev):
+            rc = lib.gstex_raster_forward(H, W, bw, C, int(settings), _p(gaussian_ids_sorted), _p(tile_bins), _p(recs),
+                                          _p(mean2d), _p(tex), _p(viewmat), _p(c2w), fx, fy, cx, cy, _p(background),
+                                          _p(out_img), _p(out_depth), _p(out_reg), _p(out_texture), _p(out_normal),
+                                          _p(final_Ts), _p(final_idx), _p(depth_idx), _p(out_reg_s), _p(masks),
+                                          num_intersects, 0, s)
+        _lib.check(rc, "raster_forward")
+        ctx.img_width, ctx.img_height, ctx.block_width = W, H, bw
+        ctx.texture_info, ctx.settings, ctx.glob_scale = texture_info, int(settings), float(glob_scale)
         ctx.intr = (fx, fy, cx, cy)
-        ctx.save_for_backward(texture_dims, gaussian_ids_sorted, tile_bins, colors, opacity, means, scales, quats, uv0,
-                              umap, vmap, texture, viewmat, c2w, background, final_Ts, final_idx, depth_idx, out_reg_s,
-                              scratch)
+        ctx.save_for_backward(gaussian_ids_sorted, tile_bins, means, scales, quats, umap, vmap, texture, viewmat, c2w,
+                              background, final_Ts, final_idx, depth_idx, out_reg_s, recs, mean2d, tex4, masks)
         out_alpha = 1 - final_Ts
         return out_img, out_depth, out_reg, out_alpha, out_texture, out_normal
 
@@ -91,22 +137,48 @@ class _TextureGaussians(Function):
             colors, opacity, means, scales, quats, uv0, umap, vmap, texture = ctx.saved_tensors
             grads = [torch.zeros_like(t) for t in (colors, opacity, means, scales, quats, uv0, umap, vmap, texture)]
         else:
-            (texture_dims, gaussian_ids_sorted, tile_bins, colors, opacity, means, scales, quats, uv0, umap, vmap,
-             texture, viewmat, c2w, background, final_Ts, final_idx, depth_idx, out_reg_s, scratch) = ctx.saved_tensors
-            H, W = ctx.img_height, ctx.img_width
+            (gaussian_ids_sorted, tile_bins, means, scales, quats, umap, vmap, texture, viewmat, c2w, background,
+             final_Ts, final_idx, depth_idx, out_reg_s, recs, mean2d, tex4, masks) = ctx.saved_tensors
+            lib = _lib.load()
+            H, W, bw = ctx.img_height, ctx.img_width, ctx.block_width
             dev = means.device
+            f32 = dict(dtype=torch.float32, device=dev)
 
             def dense(v, shape):
-                return torch.zeros(shape, dtype=torch.float32, device=dev) if v is None else v.contiguous()
+                return torch.zeros(shape, **f32) if v is None else v.contiguous()
 
             C = int(ctx.texture_info[2])
+            n, X = means.shape[0], texture.shape[0]
             fx, fy, cx, cy = ctx.intr
-            grads = _C.texture_backward(
-                H, W, ctx.block_width, ctx.texture_info, texture_dims, gaussian_ids_sorted, tile_bins, colors, opacity,
-                means, scales, ctx.glob_scale, quats, uv0, umap, vmap, texture, viewmat, c2w, fx, fy, cx, cy,
-                ctx.settings, background, final_Ts, final_idx, depth_idx, out_reg_s, dense(v_out_img, (H, W, 3)),
-                dense(v_out_depth, (H, W)), dense(v_out_reg, (H, W)), dense(v_out_alpha, (H, W)),
-                dense(v_out_texture, (H, W, C)), dense(v_out_normal, (H, W, 3)), _fwd_scratch=scratch)
+            v_img, v_dep, v_reg = dense(v_out_img, (H, W, 3)), dense(v_out_depth, (H, W)), dense(v_out_reg, (H, W))
+            v_alp, v_tex, v_nrm = dense(v_out_alpha, (H, W)), dense(v_out_texture, (H, W, C)), dense(v_out_normal, (H, W, 3))
+            for name, t in (("v_output", v_img), ("v_output_depth", v_dep), ("v_output_reg", v_reg),
+                            ("v_output_alpha", v_alp), ("v_output_texture", v_tex), ("v_output_normal", v_nrm)):
+                _C._chk(name, t, torch.float32)
+            acc = torch.zeros((n, 32), **f32)                       # moment lines (csrc/common.cuh: AccSlot)
+            v_texture = torch.zeros((X, C), **f32) if C != 3 else torch.empty((X, C), **f32)
+            vtex4 = torch.zeros((X, 4), **f32) if C == 3 else None  # padded texel gradients
+            v_colors, v_opacity = torch.empty((n, 3), **f32), torch.empty((n, 1), **f32)
+            v_means, v_scales, v_quats = torch.empty((n, 3), **f32), torch.empty((n, 3), **f32), torch.empty((n, 4), **f32)
+            v_uv0, v_umap, v_vmap = torch.empty((n, 1, 2), **f32), torch.empty((n, 1, 3), **f32), torch.empty((n, 1, 3), **f32)
+            s = torch.cuda.current_stream(dev).cuda_stream
+            tex = tex4 if C == 3 else texture
+            vtex = vtex4 if C == 3 else v_texture
+            with torch.cuda.device(dev):
+                rc = lib.gstex_raster_backward(H, W, bw, C, ctx.settings, _p(gaussian_ids_sorted), _p(tile_bins), _p(recs),
+                                               _p(mean2d), _p(tex), _p(viewmat), _p(c2w), fx, fy, cx, cy, _p(background),
+                                               _p(final_Ts), _p(final_idx), _p(depth_idx), _p(out_reg_s), _p(v_img),
+                                               _p(v_dep), _p(v_reg), _p(v_alp), _p(v_tex), _p(v_nrm), _p(masks), _p(acc),
+                                               _p(vtex), s)
+                _lib.check(rc, "raster_backward")
+                rc = lib.gstex_raster_epilogue(n, _p(means), _p(scales), ctx.glob_scale, _p(quats), _p(umap), _p(vmap),
+                                               _p(viewmat), _p(c2w), fx, fy, cx, cy, _p(acc), _p(v_colors), _p(v_opacity),
+                                               _p(v_means), _p(v_scales), _p(v_quats), _p(v_uv0), _p(v_umap), _p(v_vmap),
+                                               0, s)
+                _lib.check(rc, "raster_epilogue")
+                if C == 3:
+                    _lib.check(lib.gstex_unpad_texture_grad(X, _p(vtex4), _p(v_texture), 0, s), "unpad_texture_grad")
+            grads = (v_colors, v_opacity, v_means, v_scales, v_quats, v_uv0, v_umap, v_vmap, v_texture)
         v_colors, v_opacity, v_means, v_scales, v_quats, v_uv0, v_umap, v_vmap, v_texture = grads
         none18[6], none18[7], none18[8], none18[9] = v_colors, v_opacity, v_means, v_scales
         none18[11], none18[12], none18[13], none18[14], none18[15] = v_quats, v_uv0, v_umap, v_vmap, v_texture
