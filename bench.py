@@ -175,7 +175,9 @@ def run_reference(args, rank: int):
     # torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm uses every host core regardless
     oracle.set_num_threads(os.cpu_count() or 1)
     cores = oracle.num_threads()
-    rows = args.cpu_rows or 128
+    # bounded sample: 128 rows of the frame cost about 1.1 s per step on 16 cores; shrink the crop for long runs so that
+    # the whole --steps K run stays within about a minute (the metric is per pixel, the crop is named in `sample`)
+    rows = args.cpu_rows or min(128, 128 * 40 // max(1, args.steps))
     rows = min(args.height, max(16, rows // 16 * 16))
     for _ in range(min(args.warmup, 1)):
         cpu_step(scene, rows)
