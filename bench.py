@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--views", type=int, default=0, help="views per step (0: 1 at N=1, 64 at N>1)")
+    ap.add_argument("--scale-mult", type=float, default=1.0,
+                    help="multiplies the C4 scene's Gaussian scales (SURVEY 8d: a denser second data point at 2.0)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the frame in the CPU sample (0 = auto)")
@@ -230,12 +232,13 @@ def main():
     n_gpus = world
     H, W, N = args.height, args.width, args.points
 
-    scene = synthetic_scene(N, W, H, seed=1234, device=dev)
+    scene = synthetic_scene(N, W, H, seed=1234, device=dev, scale_lo=0.004 * args.scale_mult,
+                            scale_hi=0.04 * args.scale_mult)
     params = {k: scene[k] for k in ("means", "scales", "quats", "opacities", "sh_coeffs", "uv0", "umap", "vmap", "texture")}
     views = args.views or (1 if world == 1 else 64)
     if views == 1:
         cams = [(scene["viewmat"], scene["c2w"])]
-        workload = "C4: 1 view/step, front camera"
+        workload = "C4: 1 view/step, front camera" + (f" (Gaussian scales x{args.scale_mult:g})" if args.scale_mult != 1.0 else "")
     else:
         cams = [(a.to(dev), b.to(dev)) for a, b in arc_cameras(views)]
         workload = (f"C5: {views} views/step on a +-30 degree arc around the C4 camera, sharded over {world} GPU(s), "
@@ -250,7 +253,7 @@ def main():
     targets = [targets_host[v].to(dev) if v in targets_host else None for v in range(views)]
 
     fused = FusedTrainStep(params, scene["texture_dims"], H, W, intrins=scene["intrins"], sh_degree=scene["sh_degree"],
-                           background=scene["background"], max_intersects=12 * N)
+                           background=scene["background"], max_intersects=int(12 * N * max(1.0, args.scale_mult ** 2)))
     dp = DataParallelTrainStep(fused, rank, world)
 
     def barrier():

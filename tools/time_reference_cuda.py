@@ -22,7 +22,8 @@ spec = importlib.util.spec_from_file_location("gstex_ref_C", os.path.join(ROOT, 
 ref = importlib.util.module_from_spec(spec)
 spec.loader.exec_module(ref)
 
-s = synthetic_scene(N, W, H, seed=1234, device=DEV)
+SCALE_MULT = float(os.environ.get("GSTEX_SCALE_MULT", "1.0"))  # bench.py --scale-mult
+s = synthetic_scene(N, W, H, seed=1234, device=DEV, scale_lo=0.004 * SCALE_MULT, scale_hi=0.04 * SCALE_MULT)
 fx, fy, cx, cy = s["intrins"]
 bw = 16
 tb = ((W + bw - 1) // bw, (H + bw - 1) // bw, 1)
