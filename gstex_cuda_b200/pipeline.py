@@ -132,7 +132,6 @@ class FusedTrainStep:
         # default priority: measured on C5 (8 views/step, 1 GPU) a high-priority side stream only moves time from its own
         # kernels into the rasterisers they displace (32.7 ms vs 32.4 ms per step)
         self.side = torch.cuda.Stream(device=dev)
-        self._tex_ready = torch.cuda.Event()
 
     def _make_view_set(self, f32, i32):
         n, dev = self.n, self.dev
@@ -214,7 +213,6 @@ class FusedTrainStep:
                 self.vtex4.zero_()
             else:
                 self.grads["v_texture"].zero_()
-            self._tex_ready.record(self.side)
         self.loss.zero_()
         self._first_view = True
 
