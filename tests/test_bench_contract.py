@@ -34,3 +34,31 @@ def test_reference_arm_prints_one_contract_line():
 def test_reference_arm_other_ranks_stay_silent():
     r = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_gpu_arm_prints_one_contract_line():
+    """-m gpu: the product arm at a reduced size: one JSON line with value / e2e / roofline / cpu_baseline / clocks."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--points", "20000", "--width", "320", "--height",
+                        "192", "--steps", "3", "--warmup", "3", "--cpu-rows", "32"], capture_output=True, text=True,
+                       timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["n_gpus"] == 1 and d["steps"] == 3 and d["warmup"] == 3 and d["unit"] == "Mpixel/s" and d["value"] > 0
+    assert d["scaling"] in ("weak", "strong") and d["vs_baseline"] is None and d["dtype"] == "f32"
+    assert d["gpu_launches"] >= 3 * 15  # every step launches the ~17 kernels of the path
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] >= 320 * 192 * 3 * 4 and e["d2h_bytes_per_step"] == 4
+    assert e["h2d_bytes_measured_per_step"] == e["h2d_bytes_per_step"]
+    rf = d["roofline"]
+    assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and rf["kernel"] in ("raster_backward", "raster_forward")
+    assert abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9 and 0 < rf["share_of_step"] <= 1.0
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] > 0
+    assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    assert "workload" in d["config"] and "l2" in d["config"]
