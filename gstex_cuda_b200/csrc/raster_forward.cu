@@ -40,8 +40,15 @@ __device__ __forceinline__ float outline_distance(const float4 q0, const float4 
 
 // VIS = true: the viewer-only settings bits 15-29 (texture.cu:58-63, :201-241, :269-274) are honoured; that build skips
 // the warp-level culling (its bound assumes alpha = opac * exp(-sigma)) and writes no blend masks (forward only).
+#ifndef GSTEX_FWD_MINB
+#define GSTEX_FWD_MINB 4
+#endif
+#ifndef GSTEX_FWD_UNROLL
+#define GSTEX_FWD_UNROLL 1
+#endif
+constexpr int FWD_UNROLL = GSTEX_FWD_UNROLL;
 template <bool C3, bool BLUR, bool VIS = false>
-__global__ void __launch_bounds__(RASTER_MAX_THREADS, 4) raster_forward_kernel(const RasterCommon p, const ForwardOut o) {
+__global__ void __launch_bounds__(RASTER_MAX_THREADS, GSTEX_FWD_MINB) raster_forward_kernel(const RasterCommon p, const ForwardOut o) {
     __shared__ float4 stage[2][RASTER_BATCH * REC_PITCH];
     __shared__ uint8_t survivors[RASTER_MAX_THREADS / 32][RASTER_BATCH];
 
@@ -105,6 +112,7 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, 4) raster_forward_kernel(c
         // The survivor walk is warp-uniform: finished pixels stay in the loop (predicated off) so that the blend
         // decision of all 32 pixels is one ballot - the mask word the backward pass reads - written with one plain
         // store per (entry, warp) instead of an atomic OR from inside the divergent blend path.
+#pragma unroll FWD_UNROLL
         for (int si = 0; si < nsurv; ++si) {
             if (__all_sync(0xffffffffu, done)) break;
             const int i = my_list[si];
