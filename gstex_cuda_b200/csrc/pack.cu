@@ -104,7 +104,8 @@ __global__ void __launch_bounds__(256) pack_kernel(int n, const float *__restric
     mean2d[g] = pinhole(fx, fy, cx, cy, xform_point(cam.vm, mean));
 }
 
-__device__ __forceinline__ float put(float old, float v, int accumulate) { return accumulate ? old + v : v; }
+// *p = v, or *p += v when accumulating: the old value is only read in the accumulating case
+__device__ __forceinline__ void put(float *__restrict__ p, float v, int accumulate) { *p = accumulate ? *p + v : v; }
 
 __global__ void __launch_bounds__(256) epilogue_kernel(
     int n, const float *__restrict__ means, const float *__restrict__ scales, float glob_scale,
@@ -166,26 +167,26 @@ __global__ void __launch_bounds__(256) epilogue_kernel(
     const float fg2 = fmaf(f.k2 * h2.x * ifx, q1.x, fmaf(f.k2 * h2.y * ify, q1.y, c2 * q1.z));
     const float4 vq = surfel_axes_vjp(quat, v_a1, v_a2, v_a3);
 
-    v_means[3 * g + 0] = put(v_means[3 * g + 0], v_d.x, accumulate);
-    v_means[3 * g + 1] = put(v_means[3 * g + 1], v_d.y, accumulate);
-    v_means[3 * g + 2] = put(v_means[3 * g + 2], v_d.z, accumulate);
-    v_scales[3 * g + 0] = put(v_scales[3 * g + 0], -fg1 / s1, accumulate);
-    v_scales[3 * g + 1] = put(v_scales[3 * g + 1], -fg2 / s2, accumulate);
-    v_scales[3 * g + 2] = put(v_scales[3 * g + 2], 0.f, accumulate);
+    put(&v_means[3 * g + 0], v_d.x, accumulate);
+    put(&v_means[3 * g + 1], v_d.y, accumulate);
+    put(&v_means[3 * g + 2], v_d.z, accumulate);
+    put(&v_scales[3 * g + 0], -fg1 / s1, accumulate);
+    put(&v_scales[3 * g + 1], -fg2 / s2, accumulate);
+    put(&v_scales[3 * g + 2], 0.f, accumulate);
     float4 oq = accumulate ? v_quats[g] : make_float4(0.f, 0.f, 0.f, 0.f);
     v_quats[g] = make_float4(oq.x + vq.x, oq.y + vq.y, oq.z + vq.z, oq.w + vq.w);
     float2 ou = accumulate ? v_uv0[g] : make_float2(0.f, 0.f);
     v_uv0[g] = make_float2(ou.x + q3.w, ou.y + q4.w);
-    v_umap[3 * g + 0] = put(v_umap[3 * g + 0], v_um.x, accumulate);
-    v_umap[3 * g + 1] = put(v_umap[3 * g + 1], v_um.y, accumulate);
-    v_umap[3 * g + 2] = put(v_umap[3 * g + 2], v_um.z, accumulate);
-    v_vmap[3 * g + 0] = put(v_vmap[3 * g + 0], v_vm.x, accumulate);
-    v_vmap[3 * g + 1] = put(v_vmap[3 * g + 1], v_vm.y, accumulate);
-    v_vmap[3 * g + 2] = put(v_vmap[3 * g + 2], v_vm.z, accumulate);
-    v_colors[3 * g + 0] = put(v_colors[3 * g + 0], q5.x, accumulate);
-    v_colors[3 * g + 1] = put(v_colors[3 * g + 1], q5.y, accumulate);
-    v_colors[3 * g + 2] = put(v_colors[3 * g + 2], q5.z, accumulate);
-    v_opacity[g] = put(v_opacity[g], q1.w, accumulate);
+    put(&v_umap[3 * g + 0], v_um.x, accumulate);
+    put(&v_umap[3 * g + 1], v_um.y, accumulate);
+    put(&v_umap[3 * g + 2], v_um.z, accumulate);
+    put(&v_vmap[3 * g + 0], v_vm.x, accumulate);
+    put(&v_vmap[3 * g + 1], v_vm.y, accumulate);
+    put(&v_vmap[3 * g + 2], v_vm.z, accumulate);
+    put(&v_colors[3 * g + 0], q5.x, accumulate);
+    put(&v_colors[3 * g + 1], q5.y, accumulate);
+    put(&v_colors[3 * g + 2], q5.z, accumulate);
+    put(&v_opacity[g], q1.w, accumulate);
 }
 
 // (X,3) -> (X,float4) so that a texel is one aligned 16-byte load / one vector atomic
@@ -201,9 +202,9 @@ __global__ void __launch_bounds__(256) unpad_texture_grad_kernel(int64_t num_tex
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= num_texels) return;
     const float4 g = g4[i];
-    v_texture[3 * i + 0] = put(v_texture[3 * i + 0], g.x, accumulate);
-    v_texture[3 * i + 1] = put(v_texture[3 * i + 1], g.y, accumulate);
-    v_texture[3 * i + 2] = put(v_texture[3 * i + 2], g.z, accumulate);
+    put(&v_texture[3 * i + 0], g.x, accumulate);
+    put(&v_texture[3 * i + 1], g.y, accumulate);
+    put(&v_texture[3 * i + 2], g.z, accumulate);
 }
 
 // ---- host launchers used by raster_forward.cu / raster_backward.cu ----------------------------------
