@@ -149,27 +149,32 @@ __device__ __forceinline__ void tile_sort_emit(const TileSortArgs &a, int tile, 
 }
 
 // CLASS 0: n <= TB_SMALL (static smem), 1: TB_SMALL < n <= TB_MEDIUM (dynamic smem), 2: longer (global memory)
+// Class 0 runs one CTA per tile; classes 1 and 2 (rare: more than 1024 entries in a tile) run a small grid whose CTAs
+// stride over all tiles looking for theirs, so that a frame without such tiles pays two near-empty launches instead of
+// two full grids of 1024-thread CTAs.
 template <int CLASS>
-__global__ void __launch_bounds__(CLASS == 0 ? 256 : 1024) tb_sort_kernel(const TileSortArgs a) {
-    const int tile = blockIdx.x;
-    const int2 r = a.tile_bins[tile];
-    const int n = r.y - r.x;
-    if (CLASS == 0 && (n <= 0 || n > TB_SMALL)) return;
-    if (CLASS == 1 && (n <= TB_SMALL || n > TB_MEDIUM)) return;
-    if (CLASS == 2 && n <= TB_MEDIUM) return;
-    unsigned long long *__restrict__ g = a.keys + r.x;
-    const int P = pow2_ceil(n);
-    if (CLASS == 2) {
-        bitonic_sort(n, P, [&](int i) { return __ldcg(g + i); }, [&](int i, unsigned long long v) { __stcg(g + i, v); });
-        for (int i = threadIdx.x; i < n; i += blockDim.x) tile_sort_emit(a, tile, r.x, i, __ldcg(g + i));
-    } else {
-        extern __shared__ unsigned long long sk_dyn[];
-        __shared__ unsigned long long sk_static[CLASS == 0 ? TB_SMALL : 1];
-        unsigned long long *sk = CLASS == 0 ? sk_static : sk_dyn;
-        for (int i = threadIdx.x; i < n; i += blockDim.x) sk[i] = g[i];
-        __syncthreads();
-        bitonic_sort(n, P, [&](int i) { return sk[i]; }, [&](int i, unsigned long long v) { sk[i] = v; });
-        for (int i = threadIdx.x; i < n; i += blockDim.x) tile_sort_emit(a, tile, r.x, i, sk[i]);
+__global__ void __launch_bounds__(CLASS == 0 ? 256 : 1024) tb_sort_kernel(const TileSortArgs a, int num_tiles) {
+    extern __shared__ unsigned long long sk_dyn[];
+    __shared__ unsigned long long sk_static[CLASS == 0 ? TB_SMALL : 1];
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {  // CTA-uniform: barriers inside are safe
+        const int2 r = a.tile_bins[tile];
+        const int n = r.y - r.x;
+        if (CLASS == 0 && (n <= 0 || n > TB_SMALL)) continue;
+        if (CLASS == 1 && (n <= TB_SMALL || n > TB_MEDIUM)) continue;
+        if (CLASS == 2 && n <= TB_MEDIUM) continue;
+        unsigned long long *__restrict__ g = a.keys + r.x;
+        const int P = pow2_ceil(n);
+        if (CLASS == 2) {
+            bitonic_sort(n, P, [&](int i) { return __ldcg(g + i); }, [&](int i, unsigned long long v) { __stcg(g + i, v); });
+            for (int i = threadIdx.x; i < n; i += blockDim.x) tile_sort_emit(a, tile, r.x, i, __ldcg(g + i));
+        } else {
+            unsigned long long *sk = CLASS == 0 ? sk_static : sk_dyn;
+            for (int i = threadIdx.x; i < n; i += blockDim.x) sk[i] = g[i];
+            __syncthreads();
+            bitonic_sort(n, P, [&](int i) { return sk[i]; }, [&](int i, unsigned long long v) { sk[i] = v; });
+            for (int i = threadIdx.x; i < n; i += blockDim.x) tile_sort_emit(a, tile, r.x, i, sk[i]);
+        }
+        __syncthreads();  // the shared buffer is reused by the CTA's next tile
     }
 }
 
@@ -232,14 +237,15 @@ extern "C" int gstex_bin_tiles(int n, const float *centers, const float *extents
                                                        tiles_x, tiles_y, fbw, tile_start, tile_fill, capacity, keys);
     GSTEX_LAUNCH_OK("tb_scatter_kernel");
     const TileSortArgs a{(const int2 *)tile_bins, keys, gaussian_ids_sorted, isect_ids_sorted};
-    tb_sort_kernel<0><<<num_tiles, 256, 0, s>>>(a);
+    tb_sort_kernel<0><<<num_tiles, 256, 0, s>>>(a, num_tiles);
     GSTEX_LAUNCH_OK("tb_sort_kernel<0>");
     static const size_t medium_smem = sizeof(unsigned long long) * TB_MEDIUM;
     GSTEX_CUDA_OK(cudaFuncSetAttribute((const void *)tb_sort_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)medium_smem));
-    tb_sort_kernel<1><<<num_tiles, 1024, medium_smem, s>>>(a);
+    const int rare_grid = num_tiles < 2 * 148 ? num_tiles : 2 * 148;
+    tb_sort_kernel<1><<<rare_grid, 1024, medium_smem, s>>>(a, num_tiles);
     GSTEX_LAUNCH_OK("tb_sort_kernel<1>");
-    tb_sort_kernel<2><<<num_tiles, 1024, 0, s>>>(a);
+    tb_sort_kernel<2><<<rare_grid, 1024, 0, s>>>(a, num_tiles);
     GSTEX_LAUNCH_OK("tb_sort_kernel<2>");
     return GSTEX_OK;
 }
