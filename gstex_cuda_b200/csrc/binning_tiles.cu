@@ -152,8 +152,11 @@ __device__ __forceinline__ void tile_sort_emit(const TileSortArgs &a, int tile, 
 // Class 0 runs one CTA per tile; classes 1 and 2 (rare: more than 1024 entries in a tile) run a small grid whose CTAs
 // stride over all tiles looking for theirs, so that a frame without such tiles pays two near-empty launches instead of
 // two full grids of 1024-thread CTAs.
+#ifndef GSTEX_TB_SMALL_THREADS
+#define GSTEX_TB_SMALL_THREADS 256
+#endif
 template <int CLASS>
-__global__ void __launch_bounds__(CLASS == 0 ? 256 : 1024) tb_sort_kernel(const TileSortArgs a, int num_tiles) {
+__global__ void __launch_bounds__(CLASS == 0 ? GSTEX_TB_SMALL_THREADS : 1024) tb_sort_kernel(const TileSortArgs a, int num_tiles) {
     extern __shared__ unsigned long long sk_dyn[];
     __shared__ unsigned long long sk_static[CLASS == 0 ? TB_SMALL : 1];
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {  // CTA-uniform: barriers inside are safe
@@ -237,7 +240,7 @@ extern "C" int gstex_bin_tiles(int n, const float *centers, const float *extents
                                                        tiles_x, tiles_y, fbw, tile_start, tile_fill, capacity, keys);
     GSTEX_LAUNCH_OK("tb_scatter_kernel");
     const TileSortArgs a{(const int2 *)tile_bins, keys, gaussian_ids_sorted, isect_ids_sorted};
-    tb_sort_kernel<0><<<num_tiles, 256, 0, s>>>(a, num_tiles);
+    tb_sort_kernel<0><<<num_tiles, GSTEX_TB_SMALL_THREADS, 0, s>>>(a, num_tiles);
     GSTEX_LAUNCH_OK("tb_sort_kernel<0>");
     static const size_t medium_smem = sizeof(unsigned long long) * TB_MEDIUM;
     GSTEX_CUDA_OK(cudaFuncSetAttribute((const void *)tb_sort_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
