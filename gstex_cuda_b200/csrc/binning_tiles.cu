@@ -135,6 +135,85 @@ __device__ __forceinline__ void bitonic_sort(int n, int P, LD ld, ST st) {
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Register-resident variant of the same network for the short lists (n <= TB_SMALL, the common case: ~400 entries
+// per tile on the C4 scene).  128 threads hold E = P/128 consecutive elements each (element i lives in thread i / E,
+// slot i % E).  A pass is an XOR mask m - the mirror step of stage k is i <-> i ^ (k-1), a half-cleaner is i <-> i ^ j -
+// and, depending on where the partner lives, it is
+//   m < E        : a compare-exchange between two registers of the same thread,
+//   m / E < 32   : a warp shuffle with lane ^ (m / E)  (the partner's slot is e for a cleaner, E-1-e for a mirror),
+//   otherwise    : one round trip through shared memory (write own elements, barrier, read the partners').
+// For P = 512 that is 17 + 25 + 3 of the 45 passes, i.e. 3 block barriers pairs instead of 45.  The comparator rule is the one
+// of bitonic_sort above (minimum to the lower index, +inf padding never moves), so the output is identical.
+// ------------------------------------------------------------------------------------------
+constexpr int TBR_THREADS = 128;
+constexpr unsigned long long TB_INF = ~0ull;
+
+__device__ __forceinline__ void cswap(unsigned long long &a, unsigned long long &b) {  // a <- min, b <- max
+    const unsigned long long lo = a < b ? a : b, hi = a < b ? b : a;
+    a = lo;
+    b = hi;
+}
+
+template <int E, int M>
+__device__ __forceinline__ void pass_in_thread(unsigned long long (&v)[E]) {
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+        if ((e ^ M) > e && (e ^ M) < E) cswap(v[e], v[e ^ M]);
+}
+
+template <int E>
+__device__ __forceinline__ void sort_pass(unsigned long long (&v)[E], int m, bool mirror, unsigned long long *sk,
+                                          int t) {
+    constexpr int LOGE = E == 1 ? 0 : E == 2 ? 1 : E == 4 ? 2 : 3;
+    const int mt = m >> LOGE;
+    if (mt == 0) {  // m < E: both elements of every comparator are in this thread
+        switch (m) {
+            case 1: pass_in_thread<E, 1>(v); break;
+            case 2: pass_in_thread<E, 2>(v); break;
+            case 3: pass_in_thread<E, 3>(v); break;
+            case 4: pass_in_thread<E, 4>(v); break;
+            default: pass_in_thread<E, 7>(v); break;
+        }
+        return;
+    }
+    const int hb = 1 << (31 - __clz(m));  // element i is the lower end of its comparator iff bit hb of i is clear
+    unsigned long long other[E];
+    if (mt < 32) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) other[e] = __shfl_xor_sync(0xffffffffu, v[e], mt);
+    } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) sk[t * E + e] = v[e];
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < E; ++e) other[e] = sk[((t ^ mt) << LOGE) + e];
+        __syncthreads();
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const unsigned long long o = mirror ? other[E - 1 - e] : other[e];  // slot e ^ (m & (E-1)): E-1-e or e
+        const bool lower = (((t << LOGE) + e) & hb) == 0;
+        v[e] = lower ? (v[e] < o ? v[e] : o) : (v[e] < o ? o : v[e]);
+    }
+}
+
+template <int E, class EMIT>
+__device__ __forceinline__ void tile_sort_registers(const unsigned long long *__restrict__ g, int n, int P,
+                                                    unsigned long long *sk, EMIT emit) {
+    const int t = threadIdx.x;
+    unsigned long long v[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) v[e] = (t * E + e) < n ? g[t * E + e] : TB_INF;
+    for (int k = 2; k <= P; k <<= 1) {
+        sort_pass<E>(v, k - 1, true, sk, t);
+        for (int j = k >> 2; j > 0; j >>= 1) sort_pass<E>(v, j, false, sk, t);
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+        if ((t * E + e) < n) emit(t * E + e, v[e]);
+}
+
 struct TileSortArgs {
     const int2 *tile_bins;
     unsigned long long *keys;     // (depth bits << 32 | gaussian id), bucketed by tile
@@ -152,11 +231,8 @@ __device__ __forceinline__ void tile_sort_emit(const TileSortArgs &a, int tile, 
 // Class 0 runs one CTA per tile; classes 1 and 2 (rare: more than 1024 entries in a tile) run a small grid whose CTAs
 // stride over all tiles looking for theirs, so that a frame without such tiles pays two near-empty launches instead of
 // two full grids of 1024-thread CTAs.
-#ifndef GSTEX_TB_SMALL_THREADS
-#define GSTEX_TB_SMALL_THREADS 256
-#endif
 template <int CLASS>
-__global__ void __launch_bounds__(CLASS == 0 ? GSTEX_TB_SMALL_THREADS : 1024) tb_sort_kernel(const TileSortArgs a, int num_tiles) {
+__global__ void __launch_bounds__(CLASS == 0 ? TBR_THREADS : 1024) tb_sort_kernel(const TileSortArgs a, int num_tiles) {
     extern __shared__ unsigned long long sk_dyn[];
     __shared__ unsigned long long sk_static[CLASS == 0 ? TB_SMALL : 1];
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {  // CTA-uniform: barriers inside are safe
@@ -167,11 +243,17 @@ __global__ void __launch_bounds__(CLASS == 0 ? GSTEX_TB_SMALL_THREADS : 1024) tb
         if (CLASS == 2 && n <= TB_MEDIUM) continue;
         unsigned long long *__restrict__ g = a.keys + r.x;
         const int P = pow2_ceil(n);
-        if (CLASS == 2) {
+        if (CLASS == 0) {
+            auto emit = [&](int i, unsigned long long key) { tile_sort_emit(a, tile, r.x, i, key); };
+            if (P <= TBR_THREADS) tile_sort_registers<1>(g, n, P, sk_static, emit);
+            else if (P == 2 * TBR_THREADS) tile_sort_registers<2>(g, n, P, sk_static, emit);
+            else if (P == 4 * TBR_THREADS) tile_sort_registers<4>(g, n, P, sk_static, emit);
+            else tile_sort_registers<8>(g, n, P, sk_static, emit);
+        } else if (CLASS == 2) {
             bitonic_sort(n, P, [&](int i) { return __ldcg(g + i); }, [&](int i, unsigned long long v) { __stcg(g + i, v); });
             for (int i = threadIdx.x; i < n; i += blockDim.x) tile_sort_emit(a, tile, r.x, i, __ldcg(g + i));
         } else {
-            unsigned long long *sk = CLASS == 0 ? sk_static : sk_dyn;
+            unsigned long long *sk = sk_dyn;
             for (int i = threadIdx.x; i < n; i += blockDim.x) sk[i] = g[i];
             __syncthreads();
             bitonic_sort(n, P, [&](int i) { return sk[i]; }, [&](int i, unsigned long long v) { sk[i] = v; });
@@ -240,7 +322,7 @@ extern "C" int gstex_bin_tiles(int n, const float *centers, const float *extents
                                                        tiles_x, tiles_y, fbw, tile_start, tile_fill, capacity, keys);
     GSTEX_LAUNCH_OK("tb_scatter_kernel");
     const TileSortArgs a{(const int2 *)tile_bins, keys, gaussian_ids_sorted, isect_ids_sorted};
-    tb_sort_kernel<0><<<num_tiles, GSTEX_TB_SMALL_THREADS, 0, s>>>(a, num_tiles);
+    tb_sort_kernel<0><<<num_tiles, TBR_THREADS, 0, s>>>(a, num_tiles);
     GSTEX_LAUNCH_OK("tb_sort_kernel<0>");
     static const size_t medium_smem = sizeof(unsigned long long) * TB_MEDIUM;
     GSTEX_CUDA_OK(cudaFuncSetAttribute((const void *)tb_sort_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
