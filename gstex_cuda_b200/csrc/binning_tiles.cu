@@ -21,6 +21,12 @@
 
 namespace gstex {
 
+// Per-tile counters live one per 32-byte sector: with 8 counters in a sector the ~400 atomics each tile receives
+// serialise against its 7 neighbours' in the L2 atomic unit (measured on C4: count + scatter 0.142 -> 0.09 ms).
+#ifndef GSTEX_TB_STRIDE
+#define GSTEX_TB_STRIDE 8
+#endif
+constexpr int TB_STRIDE = GSTEX_TB_STRIDE;  // ints between consecutive tiles' counters
 constexpr int TB_SMALL = 1024;    // keys sorted in static shared memory by 256 threads
 constexpr int TB_MEDIUM = 8192;   // keys sorted in 64 KB of dynamic shared memory by 1024 threads
                                   // longer lists: same network, in place in global memory (L2), 1024 threads
@@ -35,7 +41,7 @@ __global__ void __launch_bounds__(256) tb_count_kernel(int n, const float2 *__re
     int x0, y0, x1, y1;
     tile_bbox(c.x, c.y, e.x, e.y, tiles_x, tiles_y, fbw, x0, y0, x1, y1);
     for (int ty = y0; ty < y1; ++ty)
-        for (int tx = x0; tx < x1; ++tx) atomicAdd(&tile_count[ty * tiles_x + tx], 1);
+        for (int tx = x0; tx < x1; ++tx) atomicAdd(&tile_count[(ty * tiles_x + tx) * TB_STRIDE], 1);
 }
 
 // one CTA of 1024 threads: exclusive scan of tile_count -> tile_start, tile_bins, total
@@ -49,7 +55,7 @@ __global__ void __launch_bounds__(1024) tb_scan_kernel(int num_tiles, const int3
     __syncthreads();
     for (int base = 0; base < num_tiles; base += 1024) {
         const int t = base + threadIdx.x;
-        const int v = t < num_tiles ? tile_count[t] : 0;
+        const int v = t < num_tiles ? tile_count[t * TB_STRIDE] : 0;
         int incl = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -99,7 +105,7 @@ __global__ void __launch_bounds__(256) tb_scatter_kernel(int n, const float2 *__
     for (int ty = y0; ty < y1; ++ty)
         for (int tx = x0; tx < x1; ++tx) {
             const int t = ty * tiles_x + tx;
-            const int64_t pos = (int64_t)tile_start[t] + atomicAdd(&tile_fill[t], 1);
+            const int64_t pos = (int64_t)tile_start[t] + atomicAdd(&tile_fill[t * TB_STRIDE], 1);
             if (pos < cap) keys[pos] = key;
         }
 }
@@ -272,9 +278,9 @@ static TileBinLayout tile_bin_layout(int num_tiles, int64_t cap) {
     const size_t t = (size_t)(num_tiles > 0 ? num_tiles : 1);
     size_t off = 0;
     L.count_off = off;
-    off += sizeof(int32_t) * t;       // count and fill are contiguous: one memset clears both
+    off += sizeof(int32_t) * t * TB_STRIDE;       // count and fill are contiguous: one memset clears both
     L.fill_off = off;
-    off = align_up(off + sizeof(int32_t) * t, 256);
+    off = align_up(off + sizeof(int32_t) * t * TB_STRIDE, 256);
     L.start_off = off;
     off = align_up(off + sizeof(int32_t) * t, 256);
     L.keys_off = off;
@@ -308,7 +314,7 @@ extern "C" int gstex_bin_tiles(int n, const float *centers, const float *extents
     int32_t *tile_count = (int32_t *)(base + L.count_off), *tile_fill = (int32_t *)(base + L.fill_off);
     int32_t *tile_start = (int32_t *)(base + L.start_off);
     unsigned long long *keys = (unsigned long long *)(base + L.keys_off);
-    GSTEX_CUDA_OK(cudaMemsetAsync(tile_count, 0, sizeof(int32_t) * 2 * (size_t)num_tiles, s));
+    GSTEX_CUDA_OK(cudaMemsetAsync(tile_count, 0, sizeof(int32_t) * 2 * (size_t)num_tiles * TB_STRIDE, s));
     const float fbw = (float)block_width;
     if (n > 0) {
         tb_count_kernel<<<ceil_div(n, 256), 256, 0, s>>>(n, (const float2 *)centers, (const float2 *)extents, tiles_x,
