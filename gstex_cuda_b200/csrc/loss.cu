@@ -13,10 +13,10 @@ __global__ void __launch_bounds__(256) image_loss_kernel(int npix, const float *
                                                          float *__restrict__ v_reg, float *__restrict__ v_alpha,
                                                          float *__restrict__ v_tex, float *__restrict__ v_normal) {
     __shared__ float warp_part[8];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const float inv_p = 1.f / (float)npix, inv_3p = 1.f / (3.f * (float)npix);
     float part = 0.f;
-    if (i < npix) {
+    // grid-stride: a bounded number of CTAs, so that the single loss accumulator receives ~1 k atomics, not one per 256 pixels
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
         float mse = 0.f;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(256) image_loss_kernel(int npix, const float *
             v_img[3 * i + c] = 0.f;
         }
         const float nx = out_normal[3 * i], ny = out_normal[3 * i + 1], nz = out_normal[3 * i + 2];
-        part = mse * inv_3p + out_reg[i] * inv_p + (nx * nx + ny * ny + (1.f - nz) * (1.f - nz)) * inv_p;
+        part += mse * inv_3p + out_reg[i] * inv_p + (nx * nx + ny * ny + (1.f - nz) * (1.f - nz)) * inv_p;
         v_normal[3 * i] = 2.f * nx * inv_p;
         v_normal[3 * i + 1] = 2.f * ny * inv_p;
         v_normal[3 * i + 2] = -2.f * (1.f - nz) * inv_p;
@@ -55,7 +55,8 @@ extern "C" int gstex_image_loss(int img_height, int img_width, const float *out_
                                 float *v_out_normal, gstex_stream_t stream) {
     GSTEX_REQUIRE(img_height > 0 && img_width > 0, GSTEX_E_INVALID, "image_loss: image %dx%d", img_height, img_width);
     const int npix = img_height * img_width;
-    image_loss_kernel<<<ceil_div(npix, 256), 256, 0, as_stream(stream)>>>(
+    const int blocks = min(ceil_div(npix, 256), 148 * 8);
+    image_loss_kernel<<<blocks, 256, 0, as_stream(stream)>>>(
         npix, out_texture, out_reg, out_normal, gt, loss_accum, v_out_img, v_out_depth, v_out_reg, v_out_alpha,
         v_out_texture, v_out_normal);
     GSTEX_LAUNCH_OK("image_loss_kernel");
