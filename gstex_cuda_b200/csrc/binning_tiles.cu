@@ -233,7 +233,7 @@ __device__ __forceinline__ void tile_sort_emit(const TileSortArgs &a, int tile, 
     if (a.isect_out) a.isect_out[start + idx] = ((int64_t)tile << 32) | (int64_t)(key >> 32);
 }
 
-// CLASS 0: n <= TB_SMALL (static smem), 1: TB_SMALL < n <= TB_MEDIUM (dynamic smem), 2: longer (global memory)
+// CLASS 0: n <= TB_SMALL (registers + static smem); CLASS 1: longer lists - dynamic smem up to TB_MEDIUM, global memory beyond
 // Class 0 runs one CTA per tile; classes 1 and 2 (rare: more than 1024 entries in a tile) run a small grid whose CTAs
 // stride over all tiles looking for theirs, so that a frame without such tiles pays two near-empty launches instead of
 // two full grids of 1024-thread CTAs.
@@ -245,8 +245,7 @@ __global__ void __launch_bounds__(CLASS == 0 ? TBR_THREADS : 1024) tb_sort_kerne
         const int2 r = a.tile_bins[tile];
         const int n = r.y - r.x;
         if (CLASS == 0 && (n <= 0 || n > TB_SMALL)) continue;
-        if (CLASS == 1 && (n <= TB_SMALL || n > TB_MEDIUM)) continue;
-        if (CLASS == 2 && n <= TB_MEDIUM) continue;
+        if (CLASS == 1 && n <= TB_SMALL) continue;  // class 1 = every longer list: shared memory up to TB_MEDIUM, else global
         unsigned long long *__restrict__ g = a.keys + r.x;
         const int P = pow2_ceil(n);
         if (CLASS == 0) {
@@ -255,7 +254,7 @@ __global__ void __launch_bounds__(CLASS == 0 ? TBR_THREADS : 1024) tb_sort_kerne
             else if (P == 2 * TBR_THREADS) tile_sort_registers<2>(g, n, P, sk_static, emit);
             else if (P == 4 * TBR_THREADS) tile_sort_registers<4>(g, n, P, sk_static, emit);
             else tile_sort_registers<8>(g, n, P, sk_static, emit);
-        } else if (CLASS == 2) {
+        } else if (n > TB_MEDIUM) {
             bitonic_sort(n, P, [&](int i) { return __ldcg(g + i); }, [&](int i, unsigned long long v) { __stcg(g + i, v); });
             for (int i = threadIdx.x; i < n; i += blockDim.x) tile_sort_emit(a, tile, r.x, i, __ldcg(g + i));
         } else {
@@ -336,7 +335,5 @@ extern "C" int gstex_bin_tiles(int n, const float *centers, const float *extents
     const int rare_grid = num_tiles < 2 * 148 ? num_tiles : 2 * 148;
     tb_sort_kernel<1><<<rare_grid, 1024, medium_smem, s>>>(a, num_tiles);
     GSTEX_LAUNCH_OK("tb_sort_kernel<1>");
-    tb_sort_kernel<2><<<rare_grid, 1024, 0, s>>>(a, num_tiles);
-    GSTEX_LAUNCH_OK("tb_sort_kernel<2>");
     return GSTEX_OK;
 }

@@ -125,7 +125,7 @@ class FusedTrainStep:
         self.launches = 0
         self.time_kernels = False
         self.kernel_events: List[Tuple[str, torch.cuda.Event, torch.cuda.Event]] = []
-        self._bin_launches = 6  # tile count, tile scan, scatter, three per-tile sort size classes
+        self._bin_launches = 5  # tile count, tile scan, scatter, two per-tile sort size classes
         # The rasterisers are issue-bound and leave most of the HBM bandwidth idle; the bandwidth-bound housekeeping that
         # does not depend on them (texture padding, zero-fills of the moment lines / texel-gradient buffer) runs on a
         # side stream underneath binning and the forward rasteriser and is joined with events where its result is needed.
