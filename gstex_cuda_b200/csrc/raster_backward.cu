@@ -5,11 +5,10 @@
 //   * per pair the kernel differentiates the three affine forms of raster.cuh, not the quat->R /
 //     ray-plane chain: a lane produces 25 moment values (sum g*(ex, ey, 1) per form, plus colour,
 //     normal, opacity, c0, uv0), laid out as 8 float4 quads (common.cuh: AccSlot);
-//   * those 32 slots are reduced over the warp with a recursive-halving butterfly (16+8+4 shuffles
-//     exchange half of the slots each, then 2x4 to finish a quad): 36 shuffles instead of the
-//     reference's 25 x 5 = 125, after which 8 lanes issue ONE 16-byte vector reduction each
-//     (REDG.E.ADD.F32x4) into the Gaussian's 128-byte moment line - 8 vector atomics per
-//     (warp, Gaussian) instead of 25 scalar ones, and none of the per-pair quat/rotation VJPs;
+//   * those 32 slots are reduced over the warp by recursive halving (16+8+4+2+1 = 31 shuffles, each step exchanges
+//     half of the slots a lane still holds) instead of the reference's 25 x 5 = 125, after which lane L holds the total
+//     of slot L and the warp issues ONE reduction instruction (28 lanes x 4 bytes, contiguous in the Gaussian's
+//     128-byte moment line) - instead of 25 scalar atomics to 9 arrays, and none of the per-pair quat/rotation VJPs;
 //   * the chain rule from moments to means / scales / quats / uv maps runs once per Gaussian in
 //     pack.cu::epilogue_kernel, without atomics;
 //   * texel gradients are one float4 vector reduction per bilinear corner into a padded (X,4) buffer
@@ -204,48 +203,27 @@ __device__ __forceinline__ void pair_rows(const RasterCommon &p, const BackwardI
     }
 }
 
-// Sum 8 float4 quads held per lane over the warp: recursive halving, 36 shuffles; every lane returns the total of
-// quad (lane >> 2).
-__device__ __forceinline__ float4 warp_reduce_quads(const float4 (&r)[8], int lane) {
+// Sum 8 float4 quads (32 slots) held per lane over the warp by recursive halving: at the step with partner lane ^ b
+// a lane keeps the upper half of its slots if (lane & b) and sends the other half, so after 16 + 8 + 4 + 2 + 1 = 31
+// shuffles lane L holds the warp total of slot L.
+__device__ __forceinline__ float warp_reduce_slots(const float4 (&r)[8], int lane) {
     const unsigned full = 0xffffffffu;
     float a[32];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         a[4 * k] = r[k].x; a[4 * k + 1] = r[k].y; a[4 * k + 2] = r[k].z; a[4 * k + 3] = r[k].w;
     }
-    {
-        const bool hi = (lane & 16) != 0;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const float send = hi ? a[i] : a[i + 16];
-            const float keep = hi ? a[i + 16] : a[i];
-            a[i] = keep + __shfl_xor_sync(full, send, 16);
+    for (int b = 16; b >= 1; b >>= 1) {
+        const bool hi = (lane & b) != 0;
+#pragma unroll
+        for (int i = 0; i < b; ++i) {
+            const float send = hi ? a[i] : a[i + b];
+            const float keep = hi ? a[i + b] : a[i];
+            a[i] = keep + __shfl_xor_sync(full, send, b);
         }
     }
-    {
-        const bool hi = (lane & 8) != 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float send = hi ? a[i] : a[i + 8];
-            const float keep = hi ? a[i + 8] : a[i];
-            a[i] = keep + __shfl_xor_sync(full, send, 8);
-        }
-    }
-    {
-        const bool hi = (lane & 4) != 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float send = hi ? a[i] : a[i + 4];
-            const float keep = hi ? a[i + 4] : a[i];
-            a[i] = keep + __shfl_xor_sync(full, send, 4);
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        a[i] += __shfl_xor_sync(full, a[i], 2);
-        a[i] += __shfl_xor_sync(full, a[i], 1);
-    }
-    return make_float4(a[0], a[1], a[2], a[3]);
+    return a[0];
 }
 
 template <bool C3, bool BLUR>
@@ -453,9 +431,9 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, GSTEX_BWD_MINB) raster_bac
                             pair_rows<C3, BLUR>(p, in, o, fl, q0, q3, q4, q5, q6, pe, pc, me, alpha * T, v_alpha, gu, gv,
                                                 idx == me.dfinal && me.dfinal != -1, r);
                         }
-                        const float4 tot = warp_reduce_quads(r, lane);
-                        if ((lane & 3) == 0 && (BLUR || lane < 28))
-                            atomicAdd(o.acc + (size_t)__float_as_int(q2.w) * 8 + (lane >> 2), tot);
+                        const float tot = warp_reduce_slots(r, lane);
+                        if (lane < (BLUR ? 30 : 28))  // one 4-byte reduction per lane, 112 contiguous bytes of the moment line
+                            atomicAdd(reinterpret_cast<float *>(o.acc) + (size_t)__float_as_int(q2.w) * 32 + lane, tot);
                     } else {
                         if (mine) {
                             const int e = (int)W.ch_off[jj] + __popc(m & lt);
