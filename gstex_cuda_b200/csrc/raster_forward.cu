@@ -2,8 +2,8 @@
 //
 // One CTA per screen tile, one thread per pixel; for 16x16 tiles each warp owns an 8x4 pixel patch.
 // The tile's depth-sorted Gaussian list is streamed through shared memory in 128-record stages with
-// cp.async (LDGSTS) double buffering: while the CTA composites stage b, the 16 KB of stage b+1 are in
-// flight.  Each record is one 128-byte line gathered through gaussian_ids_sorted; all lanes read the
+// cp.async (LDGSTS): while the CTA composites stage b, the 18 KB of stage b+1 are in flight.  Three
+// stage buffers (dynamic shared memory) make ONE block barrier per stage enough.  Each record is one 128-byte line gathered through gaussian_ids_sorted; all lanes read the
 // same record at the same time, so the shared-memory reads are broadcasts (LDS.128, no conflicts).
 // The texture is read as one aligned float4 per corner from the padded copy (4 LDG.128 per blended
 // pair instead of 12 scalar loads).
@@ -40,6 +40,9 @@ __device__ __forceinline__ float outline_distance(const float4 q0, const float4 
 
 // VIS = true: the viewer-only settings bits 15-29 (texture.cu:58-63, :201-241, :269-274) are honoured; that build skips
 // the warp-level culling (its bound assumes alpha = opac * exp(-sigma)) and writes no blend masks (forward only).
+#ifndef GSTEX_FWD_STAGES
+#define GSTEX_FWD_STAGES 3
+#endif
 #ifndef GSTEX_FWD_MINB
 #define GSTEX_FWD_MINB 4
 #endif
@@ -49,7 +52,14 @@ __device__ __forceinline__ float outline_distance(const float4 q0, const float4 
 constexpr int FWD_UNROLL = GSTEX_FWD_UNROLL;
 template <bool C3, bool BLUR, bool VIS = false>
 __global__ void __launch_bounds__(RASTER_MAX_THREADS, GSTEX_FWD_MINB) raster_forward_kernel(const RasterCommon p, const ForwardOut o) {
+#if GSTEX_FWD_STAGES == 3
+    // three stage buffers in dynamic shared memory: stage b+1 is filled into the buffer last read two iterations ago,
+    // which every warp has left by the time it passed this iteration's barrier, so ONE barrier per stage suffices
+    extern __shared__ __align__(16) unsigned char fwd_smem[];
+    float4 (*stage)[RASTER_BATCH * REC_PITCH] = reinterpret_cast<float4 (*)[RASTER_BATCH * REC_PITCH]>(fwd_smem);
+#else
     __shared__ float4 stage[2][RASTER_BATCH * REC_PITCH];
+#endif
     __shared__ uint8_t survivors[RASTER_MAX_THREADS / 32][RASTER_BATCH];
 
     const int tr = threadIdx.x, lane = tr & 31;
@@ -92,15 +102,19 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, GSTEX_FWD_MINB) raster_for
         const int first = range.x + b * RASTER_BATCH;
         const int cnt = min(RASTER_BATCH, range.y - first);
         if (b + 1 < nbatch) {
-            stage_records(stage[(b + 1) & 1], p.recs, p.ids, first + RASTER_BATCH,
+            stage_records(stage[(b + 1) % GSTEX_FWD_STAGES], p.recs, p.ids, first + RASTER_BATCH,
                           min(RASTER_BATCH, range.y - first - RASTER_BATCH), tr, p.nthreads);
+            // the ids of stage b+2 (512 contiguous bytes) start travelling now: the gather of the next iteration begins
+            // with a dependent load of them
+            if (tr < 4 && first + 2 * RASTER_BATCH + 32 * tr < range.y)
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(p.ids + first + 2 * RASTER_BATCH + 32 * tr));
             __pipeline_wait_prior(1);
         } else {
             __pipeline_wait_prior(0);
         }
         // stage b is visible to the whole CTA after this barrier; leave if every pixel is finished
         if (__syncthreads_count(done) >= p.nthreads) break;
-        const float4 *__restrict__ S = stage[b & 1];
+        const float4 *__restrict__ S = stage[b % GSTEX_FWD_STAGES];
 #ifndef GSTEX_EXP_NO_PREFETCH
         if (C3 && tr < cnt) {  // one thread per staged record: start fetching its texture block
             const float4 q3 = S[quad_slot(tr, 3)], q6 = S[quad_slot(tr, 6)];
@@ -190,7 +204,9 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, GSTEX_FWD_MINB) raster_for
                 last = first + i;
             }
         }
+#if GSTEX_FWD_STAGES == 2
         __syncthreads();  // everyone is done with stage b before it is refilled (two iterations ahead)
+#endif
     }
     __pipeline_wait_prior(0);
 
@@ -265,20 +281,31 @@ int launch_raster_forward(const RasterCommon &p, const ForwardOut &o, int64_t ma
     }
     const dim3 grid(p.tiles_x, ceil_div(p.img_h, p.bw));
     const bool blur = (p.settings & GSTEX_SET_BLUR) != 0;
+    const size_t dsm = GSTEX_FWD_STAGES == 3 ? sizeof(float4) * 3 * RASTER_BATCH * REC_PITCH : 0;
+    if (dsm) {
+        const void *fns[] = {(const void *)raster_forward_kernel<true, true, true>, (const void *)raster_forward_kernel<true, false, true>,
+                             (const void *)raster_forward_kernel<false, true, true>, (const void *)raster_forward_kernel<false, false, true>,
+                             (const void *)raster_forward_kernel<true, true>, (const void *)raster_forward_kernel<true, false>,
+                             (const void *)raster_forward_kernel<false, true>, (const void *)raster_forward_kernel<false, false>};
+        for (const void *f : fns) {
+            GSTEX_CUDA_OK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+            GSTEX_CUDA_OK(cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        }
+    }
     if (p.settings & GSTEX_SET_VIS_ALL) {  // viewer-only modes: one generic build per channel layout, forward only
         if (p.channels == 3) {
-            if (blur) raster_forward_kernel<true, true, true><<<grid, p.nthreads, 0, s>>>(p, o);
-            else raster_forward_kernel<true, false, true><<<grid, p.nthreads, 0, s>>>(p, o);
+            if (blur) raster_forward_kernel<true, true, true><<<grid, p.nthreads, dsm, s>>>(p, o);
+            else raster_forward_kernel<true, false, true><<<grid, p.nthreads, dsm, s>>>(p, o);
         } else {
-            if (blur) raster_forward_kernel<false, true, true><<<grid, p.nthreads, 0, s>>>(p, o);
-            else raster_forward_kernel<false, false, true><<<grid, p.nthreads, 0, s>>>(p, o);
+            if (blur) raster_forward_kernel<false, true, true><<<grid, p.nthreads, dsm, s>>>(p, o);
+            else raster_forward_kernel<false, false, true><<<grid, p.nthreads, dsm, s>>>(p, o);
         }
     } else if (p.channels == 3) {
-        if (blur) raster_forward_kernel<true, true><<<grid, p.nthreads, 0, s>>>(p, o);
-        else raster_forward_kernel<true, false><<<grid, p.nthreads, 0, s>>>(p, o);
+        if (blur) raster_forward_kernel<true, true><<<grid, p.nthreads, dsm, s>>>(p, o);
+        else raster_forward_kernel<true, false><<<grid, p.nthreads, dsm, s>>>(p, o);
     } else {
-        if (blur) raster_forward_kernel<false, true><<<grid, p.nthreads, 0, s>>>(p, o);
-        else raster_forward_kernel<false, false><<<grid, p.nthreads, 0, s>>>(p, o);
+        if (blur) raster_forward_kernel<false, true><<<grid, p.nthreads, dsm, s>>>(p, o);
+        else raster_forward_kernel<false, false><<<grid, p.nthreads, dsm, s>>>(p, o);
     }
     GSTEX_LAUNCH_OK("raster_forward_kernel");
     return GSTEX_OK;
