@@ -204,15 +204,19 @@ __device__ __forceinline__ void sort_pass(unsigned long long (&v)[E], int m, boo
     }
 }
 
-template <int E, class EMIT>
-__device__ __forceinline__ void tile_sort_registers(const unsigned long long *__restrict__ g, int n, int P,
+// P is a template parameter so that both loops unroll and every pass's mask, partner distance and comparator rule are
+// compile-time constants (no switch / clz / variable shifts at run time).
+template <int E, int P, class EMIT>
+__device__ __forceinline__ void tile_sort_registers(const unsigned long long *__restrict__ g, int n,
                                                     unsigned long long *sk, EMIT emit) {
     const int t = threadIdx.x;
     unsigned long long v[E];
 #pragma unroll
     for (int e = 0; e < E; ++e) v[e] = (t * E + e) < n ? g[t * E + e] : TB_INF;
+#pragma unroll
     for (int k = 2; k <= P; k <<= 1) {
         sort_pass<E>(v, k - 1, true, sk, t);
+#pragma unroll
         for (int j = k >> 2; j > 0; j >>= 1) sort_pass<E>(v, j, false, sk, t);
     }
 #pragma unroll
@@ -250,10 +254,11 @@ __global__ void __launch_bounds__(CLASS == 0 ? TBR_THREADS : 1024) tb_sort_kerne
         const int P = pow2_ceil(n);
         if (CLASS == 0) {
             auto emit = [&](int i, unsigned long long key) { tile_sort_emit(a, tile, r.x, i, key); };
-            if (P <= TBR_THREADS) tile_sort_registers<1>(g, n, P, sk_static, emit);
-            else if (P == 2 * TBR_THREADS) tile_sort_registers<2>(g, n, P, sk_static, emit);
-            else if (P == 4 * TBR_THREADS) tile_sort_registers<4>(g, n, P, sk_static, emit);
-            else tile_sort_registers<8>(g, n, P, sk_static, emit);
+            if (P <= 32) tile_sort_registers<1, 32>(g, n, sk_static, emit);  // tiny lists: 15 passes, one warp's worth
+            else if (P <= TBR_THREADS) tile_sort_registers<1, TBR_THREADS>(g, n, sk_static, emit);
+            else if (P == 2 * TBR_THREADS) tile_sort_registers<2, 2 * TBR_THREADS>(g, n, sk_static, emit);
+            else if (P == 4 * TBR_THREADS) tile_sort_registers<4, 4 * TBR_THREADS>(g, n, sk_static, emit);
+            else tile_sort_registers<8, 8 * TBR_THREADS>(g, n, sk_static, emit);
         } else if (n > TB_MEDIUM) {
             bitonic_sort(n, P, [&](int i) { return __ldcg(g + i); }, [&](int i, unsigned long long v) { __stcg(g + i, v); });
             for (int i = threadIdx.x; i < n; i += blockDim.x) tile_sort_emit(a, tile, r.x, i, __ldcg(g + i));
