@@ -431,7 +431,11 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, GSTEX_BWD_MINB) raster_bac
                             pair_rows<C3, BLUR>(p, in, o, fl, q0, q3, q4, q5, q6, pe, pc, me, alpha * T, v_alpha, gu, gv,
                                                 idx == me.dfinal && me.dfinal != -1, r);
                         }
+#ifdef GSTEX_EXP_NO_BUTTERFLY  // timing experiment only (wrong gradients): what the moment reduction costs
+                        const float tot = r[0].x + r[1].y + r[2].z + r[3].w + r[4].x + r[5].y + r[6].z;
+#else
                         const float tot = warp_reduce_slots(r, lane);
+#endif
                         if (lane < (BLUR ? 30 : 28))  // one 4-byte reduction per lane, 112 contiguous bytes of the moment line
                             atomicAdd(reinterpret_cast<float *>(o.acc) + (size_t)__float_as_int(q2.w) * 32 + lane, tot);
                     } else {
