@@ -169,8 +169,14 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, GSTEX_FWD_MINB) raster_for
                 TexFetch tf;
                 texel_setup(__float_as_int(q3.z), __float_as_int(q3.w), __float_as_int(q6.w), u, v, bilinear, tf);
                 if (C3) {
+#ifdef GSTEX_EXP_NO_TEXLOAD  // timing experiment only: what the four texel loads cost
+                    const float4 t0 = make_float4(u, v, u, v), t1 = make_float4(v, u, v, u);
+                    const float4 t2 = make_float4(tf.w[0], u, v, u), t3 = make_float4(tf.w[1], v, u, v);
+                    if (tf.idx[0] + tf.idx[1] + tf.idx[2] + tf.idx[3] == -12345) acc_t[0] += 1.f;
+#else
                     const float4 t0 = __ldg(p.tex4 + tf.idx[0]), t1 = __ldg(p.tex4 + tf.idx[1]);
                     const float4 t2 = __ldg(p.tex4 + tf.idx[2]), t3 = __ldg(p.tex4 + tf.idx[3]);
+#endif
                     const float tvis = VIS ? cvis : vis;
                     const float w0 = tf.w[0] * tvis, w1 = tf.w[1] * tvis, w2 = tf.w[2] * tvis, w3 = tf.w[3] * tvis;
                     acc_t[0] += w0 * t0.x + w1 * t1.x + w2 * t2.x + w3 * t3.x;
