@@ -63,7 +63,10 @@ __device__ __forceinline__ Vec3 form_vector(const SurfelFrame &f, Vec3 a, float 
     return rot_apply_t(cam.Rc, w);
 }
 
-__global__ void __launch_bounds__(256) pack_kernel(int n, const float *__restrict__ means,
+#ifndef GSTEX_PACK_MINB
+#define GSTEX_PACK_MINB 1
+#endif
+__global__ void __launch_bounds__(256, GSTEX_PACK_MINB) pack_kernel(int n, const float *__restrict__ means,
                                                    const float *__restrict__ scales, float glob_scale,
                                                    const float4 *__restrict__ quats,
                                                    const float *__restrict__ opacities,
@@ -107,7 +110,10 @@ __global__ void __launch_bounds__(256) pack_kernel(int n, const float *__restric
 // *p = v, or *p += v when accumulating: the old value is only read in the accumulating case
 __device__ __forceinline__ void put(float *__restrict__ p, float v, int accumulate) { *p = accumulate ? *p + v : v; }
 
-__global__ void __launch_bounds__(256) epilogue_kernel(
+#ifndef GSTEX_EPI_MINB
+#define GSTEX_EPI_MINB 1
+#endif
+__global__ void __launch_bounds__(256, GSTEX_EPI_MINB) epilogue_kernel(
     int n, const float *__restrict__ means, const float *__restrict__ scales, float glob_scale,
     const float4 *__restrict__ quats, const float *__restrict__ umap, const float *__restrict__ vmap,
     const float *__restrict__ viewmat, const float *__restrict__ c2w, float fx, float fy, float cx, float cy,

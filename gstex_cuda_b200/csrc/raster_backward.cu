@@ -507,13 +507,19 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, GSTEX_BWD_MINB) raster_bac
     }
 }
 
-static int set_bwd_smem(const void *fn, size_t BWD_SMEM_BYTES) {
-    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM_BYTES);
+// opt in to > 48 KB of dynamic shared memory: once per device and kernel variant
+static int set_bwd_smem(const void *fn, size_t BWD_SMEM_BYTES, int variant) {
+    static bool configured[64][4];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess && dev >= 0 && dev < 64 && configured[dev][variant]) return GSTEX_OK;
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (e != cudaSuccess) {
         set_error("cudaFuncSetAttribute(raster_backward_kernel, %zu bytes) failed: %s", BWD_SMEM_BYTES, cudaGetErrorString(e));
         return GSTEX_E_CUDA;
     }
+    if (dev >= 0 && dev < 64) configured[dev][variant] = true;
     return GSTEX_OK;
 }
 
@@ -521,7 +527,7 @@ template <bool C3, bool BLUR>
 static int launch_bwd_variant(const dim3 grid, const RasterCommon &p, const BackwardIn &in, const BackwardOut &o,
                               cudaStream_t s) {
     const size_t smem = sizeof(BwdWarpSmem<BLUR>) * BWD_WARPS;
-    int rc = set_bwd_smem((const void *)raster_backward_kernel<C3, BLUR>, smem);
+    int rc = set_bwd_smem((const void *)raster_backward_kernel<C3, BLUR>, smem, (C3 ? 2 : 0) | (BLUR ? 1 : 0));
     if (rc != GSTEX_OK) return rc;
     raster_backward_kernel<C3, BLUR><<<grid, p.nthreads, smem, s>>>(p, in, o);
     return GSTEX_OK;

@@ -288,14 +288,20 @@ int launch_raster_forward(const RasterCommon &p, const ForwardOut &o, int64_t ma
     const dim3 grid(p.tiles_x, ceil_div(p.img_h, p.bw));
     const bool blur = (p.settings & GSTEX_SET_BLUR) != 0;
     const size_t dsm = GSTEX_FWD_STAGES == 3 ? sizeof(float4) * 3 * RASTER_BATCH * REC_PITCH : 0;
-    if (dsm) {
-        const void *fns[] = {(const void *)raster_forward_kernel<true, true, true>, (const void *)raster_forward_kernel<true, false, true>,
-                             (const void *)raster_forward_kernel<false, true, true>, (const void *)raster_forward_kernel<false, false, true>,
-                             (const void *)raster_forward_kernel<true, true>, (const void *)raster_forward_kernel<true, false>,
-                             (const void *)raster_forward_kernel<false, true>, (const void *)raster_forward_kernel<false, false>};
-        for (const void *f : fns) {
-            GSTEX_CUDA_OK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
-            GSTEX_CUDA_OK(cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    if (dsm) {  // opt in to > 48 KB of dynamic shared memory: once per device, only for the variant about to be launched
+        const bool vis = (p.settings & GSTEX_SET_VIS_ALL) != 0, c3 = p.channels == 3;
+        const int variant = (vis ? 4 : 0) | (c3 ? 2 : 0) | (blur ? 1 : 0);
+        static bool configured[64][8];
+        int dev = 0;
+        GSTEX_CUDA_OK(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= 64 || !configured[dev][variant]) {
+            const void *fns[8] = {(const void *)raster_forward_kernel<false, false>, (const void *)raster_forward_kernel<false, true>,
+                                  (const void *)raster_forward_kernel<true, false>, (const void *)raster_forward_kernel<true, true>,
+                                  (const void *)raster_forward_kernel<false, false, true>, (const void *)raster_forward_kernel<false, true, true>,
+                                  (const void *)raster_forward_kernel<true, false, true>, (const void *)raster_forward_kernel<true, true, true>};
+            GSTEX_CUDA_OK(cudaFuncSetAttribute(fns[variant], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+            GSTEX_CUDA_OK(cudaFuncSetAttribute(fns[variant], cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            if (dev >= 0 && dev < 64) configured[dev][variant] = true;
         }
     }
     if (p.settings & GSTEX_SET_VIS_ALL) {  // viewer-only modes: one generic build per channel layout, forward only
