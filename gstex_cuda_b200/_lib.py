@@ -40,6 +40,7 @@ _PROTOS = {
     "gstex_bin_tiles": (c_i, [c_i, c_fp, c_fp, c_fp, c_i, c_i, c_i, c_i64, c_fp, c_fp, c_fp, c_fp, c_fp, c_sz, c_fp]),
     "gstex_texture_forward_temp_bytes": (c_sz, [c_i, c_i64, c_i, c_i64]),
     "gstex_texture_backward_temp_bytes": (c_sz, [c_i, c_i64, c_i]),
+    "gstex_texture_backward_stateless_temp_bytes": (c_sz, [c_i, c_i64, c_i, c_i64]),
     "gstex_texture_forward": (c_i, [c_i, c_i, c_i, c_i, c_i64, c_i, c_i64] + [c_fp] * 7 + [c_f] + [c_fp] * 7 + [c_f] * 4
                               + [c_i] + [c_fp] * 10 + [c_fp, c_sz, c_fp]),
     "gstex_texture_backward": (c_i, [c_i, c_i, c_i, c_i, c_i64, c_i, c_i64] + [c_fp] * 7 + [c_f] + [c_fp] * 7 + [c_f] * 4
@@ -56,6 +57,7 @@ _PROTOS = {
     "gstex_unpad_texture_grad": (c_i, [c_i64, c_fp, c_fp, c_i, c_fp]),
     "gstex_pack_records": (c_i, [c_i] + [c_fp] * 5 + [c_f] + [c_fp] * 6 + [c_f] * 4 + [c_fp, c_fp, c_fp]),
     "gstex_raster_forward": (c_i, [c_i] * 5 + [c_fp] * 7 + [c_f] * 4 + [c_fp] * 10 + [c_fp, c_i64, c_fp] + [c_fp]),
+    "gstex_raster_masks": (c_i, [c_i] * 4 + [c_fp] * 6 + [c_f] * 4 + [c_fp] * 3 + [c_i64, c_fp] + [c_fp]),
     "gstex_raster_backward": (c_i, [c_i] * 5 + [c_fp] * 7 + [c_f] * 4 + [c_fp] * 11 + [c_fp, c_fp, c_fp] + [c_fp]),
     "gstex_raster_epilogue": (c_i, [c_i, c_fp, c_fp, c_f] + [c_fp] * 5 + [c_f] * 4 + [c_fp] * 9 + [c_i, c_fp]),
     "gstex_sh_colors_forward": (c_i, [c_i, c_i, c_i] + [c_fp] * 5 + [c_fp]),

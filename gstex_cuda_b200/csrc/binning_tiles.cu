@@ -336,14 +336,9 @@ extern "C" int gstex_bin_tiles(int n, const float *centers, const float *extents
     GSTEX_LAUNCH_OK("tb_sort_kernel<0>");
     static const size_t medium_smem = sizeof(unsigned long long) * TB_MEDIUM;
     {
-        static bool configured[64];
-        int dev = 0;
-        GSTEX_CUDA_OK(cudaGetDevice(&dev));
-        if (dev < 0 || dev >= 64 || !configured[dev]) {
-            GSTEX_CUDA_OK(cudaFuncSetAttribute((const void *)tb_sort_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)medium_smem));
-            if (dev >= 0 && dev < 64) configured[dev] = true;
-        }
+        static SmemOnceFlags once;
+        const int rc = configure_dynamic_smem((const void *)tb_sort_kernel<1>, medium_smem, false, once);
+        if (rc != GSTEX_OK) return rc;
     }
     const int rare_grid = num_tiles < 2 * 148 ? num_tiles : 2 * 148;
     tb_sort_kernel<1><<<rare_grid, 1024, medium_smem, s>>>(a, num_tiles);

@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/gstex_b200.h"
 
 namespace gstex {
@@ -38,6 +40,13 @@ void set_error(const char *fmt, ...);
             return GSTEX_E_CUDA;                                                                    \
         }                                                                                           \
     } while (0)
+
+// per-device "dynamic shared memory configured" flags of one kernel (see configure_dynamic_smem in util.cu)
+struct SmemOnceFlags {
+    static constexpr int MAX_DEVICES = 64;
+    std::atomic<bool> done[MAX_DEVICES];
+};
+int configure_dynamic_smem(const void *fn, size_t bytes, bool max_carveout, SmemOnceFlags &flags);
 
 static inline cudaStream_t as_stream(gstex_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

@@ -49,6 +49,20 @@ extern "C" int gstex_raster_forward(int img_height, int img_width, int block_wid
     return launch_raster_forward(p, o, mask_entries, d_num_intersects, as_stream(stream));
 }
 
+extern "C" int gstex_raster_masks(int img_height, int img_width, int block_width, int settings,
+                                  const int32_t *gaussian_ids_sorted, const int32_t *tile_bins, const float *recs,
+                                  const float *mean2d, const float *viewmat, const float *c2w, float fx, float fy,
+                                  float cx, float cy, const float *final_Ts, const int32_t *final_idx, uint32_t *masks,
+                                  int64_t mask_entries, const int32_t *d_num_intersects, gstex_stream_t stream) {
+    int rc = check_raster_args("raster_masks", img_height, img_width, block_width, 0, 0, 3, settings);
+    if (rc != GSTEX_OK) return rc;
+    GSTEX_REQUIRE(masks && final_Ts && final_idx, GSTEX_E_INVALID, "raster_masks: NULL masks / final_Ts / final_idx");
+    const RasterCommon p = make_raster_common(img_height, img_width, block_width, 3, settings, gaussian_ids_sorted,
+                                              tile_bins, (const float4 *)recs, (const float2 *)mean2d, nullptr, nullptr,
+                                              viewmat, c2w, nullptr, fx, fy, cx, cy, masks);
+    return launch_raster_masks(p, final_Ts, final_idx, mask_entries, d_num_intersects, as_stream(stream));
+}
+
 extern "C" int gstex_raster_backward(int img_height, int img_width, int block_width, int channels, int settings,
                                      const int32_t *gaussian_ids_sorted, const int32_t *tile_bins, const float *recs,
                                      const float *mean2d, const float *tex, const float *viewmat, const float *c2w,

@@ -269,6 +269,11 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, GSTEX_BWD_MINB) raster_bac
     const int nbatch = (hi - range.x + BWD_BATCH - 1) / BWD_BATCH;
 
     float T = in.final_Ts[me.pix];
+    // The forward pass's mask words are a superset of what was composited: they also carry the bits of candidates that
+    // come after a pixel's stop (raster_forward.cu).  Pixel p composited entry i iff its bit is set and
+    // i <= final_idx[p].  Entries up to the smallest final_idx among the warp's pixels that composited anything need no
+    // filtering; in the tail beyond it the bits of the pixels that had already stopped are cleared as the words are fetched.
+    const int filter_from = __reduce_min_sync(full, (inside && T < 1.f) ? bfinal : 0x7fffffff);
     me.Sf0 = in.final_s[3 * me.pix]; me.Sf1 = in.final_s[3 * me.pix + 1]; me.Sf2 = in.final_s[3 * me.pix + 2];
     me.dfinal = in.depth_idx[me.pix];
     me.vi0 = in.v_img[3 * me.pix]; me.vi1 = in.v_img[3 * me.pix + 1]; me.vi2 = in.v_img[3 * me.pix + 2];
@@ -305,6 +310,17 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, GSTEX_BWD_MINB) raster_bac
         nx_g0 = r0 < cnt ? __ldg(p.ids + first + r0) : 0;
         nx_m1 = r1 < cnt ? __ldg(p.masks + (size_t)(first + r1) * MASK_WARPS + warp) : 0u;
         nx_g1 = r1 < cnt ? __ldg(p.ids + first + r1) : 0;
+        if (first + cnt - 1 > filter_from) {  // warp-uniform: only the tail of the walk
+            unsigned v0 = 0u, v1 = 0u;
+#pragma unroll 4
+            for (int pl = 0; pl < 32; ++pl) {
+                const int bp = __shfl_sync(full, bfinal, pl);
+                v0 |= (bp >= first + r0 ? 1u : 0u) << pl;
+                v1 |= (bp >= first + r1 ? 1u : 0u) << pl;
+            }
+            nx_m0 &= v0;
+            nx_m1 &= v1;
+        }
     };
     fetch_batch(0);
     for (int b = 0; b < nbatch; ++b) {
@@ -507,27 +523,12 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, GSTEX_BWD_MINB) raster_bac
     }
 }
 
-// opt in to > 48 KB of dynamic shared memory: once per device and kernel variant
-static int set_bwd_smem(const void *fn, size_t BWD_SMEM_BYTES, int variant) {
-    static bool configured[64][4];
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e == cudaSuccess && dev >= 0 && dev < 64 && configured[dev][variant]) return GSTEX_OK;
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    if (e != cudaSuccess) {
-        set_error("cudaFuncSetAttribute(raster_backward_kernel, %zu bytes) failed: %s", BWD_SMEM_BYTES, cudaGetErrorString(e));
-        return GSTEX_E_CUDA;
-    }
-    if (dev >= 0 && dev < 64) configured[dev][variant] = true;
-    return GSTEX_OK;
-}
-
 template <bool C3, bool BLUR>
 static int launch_bwd_variant(const dim3 grid, const RasterCommon &p, const BackwardIn &in, const BackwardOut &o,
                               cudaStream_t s) {
     const size_t smem = sizeof(BwdWarpSmem<BLUR>) * BWD_WARPS;
-    int rc = set_bwd_smem((const void *)raster_backward_kernel<C3, BLUR>, smem, (C3 ? 2 : 0) | (BLUR ? 1 : 0));
+    static SmemOnceFlags once;  // one per template instantiation
+    const int rc = configure_dynamic_smem((const void *)raster_backward_kernel<C3, BLUR>, smem, true, once);
     if (rc != GSTEX_OK) return rc;
     raster_backward_kernel<C3, BLUR><<<grid, p.nthreads, smem, s>>>(p, in, o);
     return GSTEX_OK;
@@ -545,16 +546,19 @@ int launch_raster_backward(const RasterCommon &p, const BackwardIn &in, const Ba
 }
 
 struct BwdLayout {
-    size_t acc_off, vtex4_off, total;
+    size_t acc_off, vtex4_off, fwd_off, total;
 };
 
-static BwdLayout backward_layout(int n, int64_t num_texels, int channels) {
+// `own_forward_state`: the call has no forward scratch to read and rebuilds records / padded texture / masks itself
+static BwdLayout backward_layout(int n, int64_t num_texels, int channels, int64_t num_intersects, bool own_forward_state) {
     BwdLayout L;
     size_t off = 0;
     L.acc_off = off;
     off = align_up(off + sizeof(float) * ACC_FLOATS * (size_t)(n > 0 ? n : 1), 256);
     L.vtex4_off = off;
     if (channels == 3) off = align_up(off + sizeof(float4) * (size_t)(num_texels > 0 ? num_texels : 1), 256);
+    L.fwd_off = off;
+    if (own_forward_state) off += forward_layout(n, num_texels, channels, num_intersects).total;
     L.total = off;
     return L;
 }
@@ -564,7 +568,12 @@ static BwdLayout backward_layout(int n, int64_t num_texels, int channels) {
 using namespace gstex;
 
 extern "C" size_t gstex_texture_backward_temp_bytes(int n, int64_t num_texels, int channels) {
-    return backward_layout(n, num_texels, channels).total;
+    return backward_layout(n, num_texels, channels, 0, false).total;
+}
+
+extern "C" size_t gstex_texture_backward_stateless_temp_bytes(int n, int64_t num_texels, int channels,
+                                                              int64_t num_intersects) {
+    return backward_layout(n, num_texels, channels, num_intersects, true).total;
 }
 
 extern "C" int gstex_texture_backward(
@@ -580,16 +589,15 @@ extern "C" int gstex_texture_backward(
     const void *fwd_temp, void *temp, size_t temp_bytes, gstex_stream_t stream) {
     GSTEX_REQUIRE(num_intersects >= 0 && num_intersects < ((int64_t)1 << 31), GSTEX_E_INVALID,
                   "texture_backward: num_intersects = %lld", (long long)num_intersects);
-    (void)texture_dims; (void)colors; (void)opacities; (void)uv0;
     int rc = check_raster_args("texture_backward", img_height, img_width, block_width, n, num_texels, channels, settings);
     if (rc != GSTEX_OK) return rc;
-    GSTEX_REQUIRE(fwd_temp != nullptr, GSTEX_E_INVALID, "texture_backward: fwd_temp (forward scratch) is NULL");
+    const bool stateless = fwd_temp == nullptr;
     const FwdLayout FL = forward_layout(n, num_texels, channels, num_intersects);
-    const BwdLayout L = backward_layout(n, num_texels, channels);
-    GSTEX_REQUIRE(temp && temp_bytes >= L.total, GSTEX_E_WORKSPACE, "texture_backward: temp too small (%zu < %zu)",
-                  temp_bytes, L.total);
+    const BwdLayout L = backward_layout(n, num_texels, channels, num_intersects, stateless);
+    GSTEX_REQUIRE(temp && temp_bytes >= L.total, GSTEX_E_WORKSPACE,
+                  "texture_backward: temp too small (%zu < %zu; without fwd_temp the call needs "
+                  "gstex_texture_backward_stateless_temp_bytes)", temp_bytes, L.total);
     cudaStream_t s = as_stream(stream);
-    const char *fbase = (const char *)fwd_temp;
     char *base = (char *)temp;
     float4 *acc = (float4 *)(base + L.acc_off);
     float4 *vtex4 = (float4 *)(base + L.vtex4_off);
@@ -600,16 +608,35 @@ extern "C" int gstex_texture_backward(
         GSTEX_CUDA_OK(cudaMemsetAsync(v_texture, 0, sizeof(float) * (size_t)channels * (size_t)num_texels, s));
     }
 
-    const RasterCommon p = make_raster_common(
+    // Forward state: the caller's scratch when it kept one, else rebuilt here from the call's own arguments - the
+    // reference's texture_backward_tensor is a pure function of them (texture.cu:915-1053): records and padded texture
+    // are re-packed, and the blend masks are re-derived from final_Ts / final_idx by the MODE_MASKS walk (no second
+    // forward pass: no compositing, no texel fetch, no outputs).
+    const char *fbase = stateless ? base + L.fwd_off : (const char *)fwd_temp;
+    RasterCommon p = make_raster_common(
         img_height, img_width, block_width, channels, settings, gaussian_ids_sorted, tile_bins,
         (const float4 *)(fbase + FL.recs_off), (const float2 *)(fbase + FL.mean2d_off),
         (const float4 *)(fbase + FL.tex4_off), texture, viewmat, c2w, background, fx, fy, cx, cy,
         (uint32_t *)const_cast<char *>(fbase + FL.masks_off));
+    if (stateless && num_intersects > 0) {
+        rc = launch_pack(n, means, scales, glob_scale, quats, opacities, colors, uv0, umap, vmap, texture_dims, viewmat,
+                         c2w, fx, fy, cx, cy, (float4 *)const_cast<char *>(fbase + FL.recs_off),
+                         (float2 *)const_cast<char *>(fbase + FL.mean2d_off), s);
+        if (rc != GSTEX_OK) return rc;
+        if (channels == 3) {
+            rc = launch_pad_texture(num_texels, texture, (float4 *)const_cast<char *>(fbase + FL.tex4_off), s);
+            if (rc != GSTEX_OK) return rc;
+        }
+        rc = launch_raster_masks(p, final_Ts, final_idx, num_intersects, nullptr, s);
+        if (rc != GSTEX_OK) return rc;
+    }
     BackwardIn in{final_Ts, final_s, final_idx, depth_idx, v_out_img, v_out_depth, v_out_reg, v_out_alpha, v_out_texture,
                   v_out_normal};
     BackwardOut o{acc, vtex4, v_texture};
-    rc = launch_raster_backward(p, in, o, s);
-    if (rc != GSTEX_OK) return rc;
+    if (num_intersects > 0) {
+        rc = launch_raster_backward(p, in, o, s);
+        if (rc != GSTEX_OK) return rc;
+    }
     rc = launch_epilogue(n, means, scales, glob_scale, quats, umap, vmap, viewmat, c2w, fx, fy, cx, cy, acc, v_colors,
                          v_opacity, v_means, v_scales, v_quats, v_uv0, v_umap, v_vmap, accumulate, s);
     if (rc != GSTEX_OK) return rc;

@@ -38,32 +38,270 @@ __device__ __forceinline__ float outline_distance(const float4 q0, const float4 
     return min_dis;
 }
 
-// VIS = true: the viewer-only settings bits 15-29 (texture.cu:58-63, :201-241, :269-274) are honoured; that build skips
-// the warp-level culling (its bound assumes alpha = opac * exp(-sigma)) and writes no blend masks (forward only).
-#ifndef GSTEX_FWD_STAGES
-#define GSTEX_FWD_STAGES 3
+// ------------------------------------------------------------------------------------------------------------------
+// Two kernel bodies.
+//
+// raster_forward_queued_kernel - 3-channel textures, training / inference (the hot path) and MODE_MASKS.
+//   Walk (phase 1).  The warp walks the survivors of the stage together, one record per iteration, every lane
+//   evaluating ITS pixel's alpha and ray distance from the broadcast record.  Nothing in this phase depends on the
+//   transmittance: a lane whose alpha reaches 1/255 appends (entry, alpha) to its own queue in shared memory
+//   (slot-major: queue[slot][lane], conflict free), and the ballot of the lanes that may blend the entry is the mask
+//   word the backward pass reads - one plain store per (entry, warp).  No divergent code.
+//   Drain (phase 2).  When a pixel's queue is full, and at the end of every stage, every lane composites ITS OWN queue
+//   front to back: stop rule, transmittance, colour / normal / depth / distortion sums, texture coordinate, the four
+//   16-byte texel loads, out_texture.  The lanes of a warp work on different Gaussians at the same time, so the ~135
+//   instructions of a blended pair run with 62-69 % of the lanes active (measured on the C4 masks, tools/sim_masks.py)
+//   instead of the 36 % (11.5 of 32 pixels) a per-Gaussian lock-step walk gets.
+//   Per pixel the candidates are composited in list order with the reference's rules, so the outputs are what the
+//   lock-step evaluation gives.  Two things need an argument:
+//   * The reference tests the stop rule T(1-alpha) <= 1e-4 on EVERY Gaussian, including those it skips for
+//     alpha < 1/255 (texture.cu:213-222), which never enter a queue here (nor survive the warp-level cull).  That
+//     cannot change any output: if such a Gaussian (alpha_s < 1/255) trips the rule at transmittance T, then for the
+//     next candidate (alpha_c >= 1/255 > alpha_s) fl(T * fl(1-alpha_c)) <= fl(T * fl(1-alpha_s)) <= 1e-4 by monotonicity
+//     of rounding, so that candidate trips the rule too and nothing is composited after the point where the reference
+//     stopped; T, final_idx and every sum are identical.  Candidates skipped for their ray distance (t < 0.01 or
+//     t > 1000) can have any alpha, so they ARE queued (sign bit set) and take part in the stop rule.
+//   * The mask word is a superset of the composited pixels: it also has the bits of candidates that come after the
+//     pixel's stop.  Pixel p composited entry i iff its bit is set and i <= final_idx[p]; the backward pass applies
+//     that filter (raster_backward.cu).  MODE_MASKS - re-deriving the masks for the stateless reference-shaped
+//     backward (texture.cu:915-1053 is a pure function of its arguments) - is therefore phase 1 alone.
+//
+// raster_forward_inline_kernel - runtime channel count (<= 64, texels read from the caller's (X,C) array) and the
+//   viewer-only settings bits 15-29 (texture.cu:58-63, :201-241, :269-274; no culling - its bound assumes
+//   alpha = opac * exp(-sigma) -, no masks, forward only): the lock-step walk with the blend in line.
+// ------------------------------------------------------------------------------------------------------------------
+#ifndef GSTEX_FWD_BATCH
+#define GSTEX_FWD_BATCH 88
+#endif
+#ifndef GSTEX_FWD_Q
+#define GSTEX_FWD_Q 12
 #endif
 #ifndef GSTEX_FWD_MINB
 #define GSTEX_FWD_MINB 4
 #endif
-#ifndef GSTEX_FWD_UNROLL
-#define GSTEX_FWD_UNROLL 1
-#endif
-constexpr int FWD_UNROLL = GSTEX_FWD_UNROLL;
-template <bool C3, bool BLUR, bool VIS = false>
-__global__ void __launch_bounds__(RASTER_MAX_THREADS, GSTEX_FWD_MINB) raster_forward_kernel(const RasterCommon p, const ForwardOut o) {
-#if GSTEX_FWD_STAGES == 3
-    // three stage buffers in dynamic shared memory: stage b+1 is filled into the buffer last read two iterations ago,
-    // which every warp has left by the time it passed this iteration's barrier, so ONE barrier per stage suffices
-    extern __shared__ __align__(16) unsigned char fwd_smem[];
-    float4 (*stage)[RASTER_BATCH * REC_PITCH] = reinterpret_cast<float4 (*)[RASTER_BATCH * REC_PITCH]>(fwd_smem);
-#else
-    __shared__ float4 stage[2][RASTER_BATCH * REC_PITCH];
-#endif
-    __shared__ uint8_t survivors[RASTER_MAX_THREADS / 32][RASTER_BATCH];
+constexpr int FWD_BATCH = GSTEX_FWD_BATCH;  // records per shared-memory stage (<= 256: uint8 indices)
+constexpr int FWD_Q = GSTEX_FWD_Q;          // queue slots per pixel
+constexpr int FWD_STAGES = 3;
+constexpr int FWD_WARPS = RASTER_MAX_THREADS / 32;
+enum FwdMode : int { MODE_RENDER = 0, MODE_MASKS = 1 };
 
-    const int tr = threadIdx.x, lane = tr & 31;
-    uint8_t *__restrict__ my_list = survivors[tr >> 5];
+constexpr size_t fwd_smem_bytes(bool queued) {
+    return sizeof(float4) * FWD_STAGES * FWD_BATCH * REC_PITCH + (size_t)FWD_WARPS * FWD_BATCH +
+           (queued ? (size_t)FWD_WARPS * FWD_Q * 32 * (sizeof(float) + 1) : 0);
+}
+static_assert(fwd_smem_bytes(true) + 1024 <= 227 * 1024 / GSTEX_FWD_MINB, "forward stage buffers + queues exceed the per-CTA shared memory budget");
+static_assert(FWD_BATCH % 4 == 0 && FWD_BATCH <= 256, "stage size");
+
+// Shared prologue of one stage iteration: issue stage b+1, wait for stage b, CTA barrier.  Returns false when every
+// pixel of the CTA is finished.
+__device__ __forceinline__ bool fwd_stage_advance(float4 (*stage)[FWD_BATCH * REC_PITCH], const RasterCommon &p, int2 range,
+                                                  int b, int nbatch, int tr, bool done) {
+    const int first = range.x + b * FWD_BATCH;
+    if (b + 1 < nbatch) {
+        stage_records(stage[(b + 1) % FWD_STAGES], p.recs, p.ids, first + FWD_BATCH,
+                      min(FWD_BATCH, range.y - first - FWD_BATCH), tr, p.nthreads);
+        // the ids of stage b+2 start travelling now: the gather of the next iteration begins with a dependent load of them
+        if (tr < (FWD_BATCH + 31) / 32 && first + 2 * FWD_BATCH + 32 * tr < range.y)
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(p.ids + first + 2 * FWD_BATCH + 32 * tr));
+        __pipeline_wait_prior(1);
+    } else {
+        __pipeline_wait_prior(0);
+    }
+    // stage b is visible to the whole CTA after this barrier
+    return __syncthreads_count(done) < p.nthreads;
+}
+
+template <bool BLUR, int MODE>
+__global__ void __launch_bounds__(RASTER_MAX_THREADS, GSTEX_FWD_MINB) raster_forward_queued_kernel(const RasterCommon p, const ForwardOut o,
+                                                                                                   const float *__restrict__ final_Ts_in,
+                                                                                                   const int32_t *__restrict__ final_idx_in) {
+    constexpr bool RENDER = MODE == MODE_RENDER;
+    // dynamic shared memory: three stage buffers (stage b+1 is filled into the buffer last read two iterations ago,
+    // which every warp has left by the time it passed this iteration's barrier, so ONE barrier per stage suffices),
+    // the per-warp survivor lists, and the per-pixel queues
+    extern __shared__ __align__(16) unsigned char fwd_smem[];
+    float4 (*stage)[FWD_BATCH * REC_PITCH] = reinterpret_cast<float4 (*)[FWD_BATCH * REC_PITCH]>(fwd_smem);
+    uint8_t *const surv_base = fwd_smem + sizeof(float4) * FWD_STAGES * FWD_BATCH * REC_PITCH;
+
+    const int tr = threadIdx.x, warp = tr >> 5;
+    // Under the 64-register cap ptxas re-derives the lane and this warp's shared-memory offsets from S2R SR_TID.X inside
+    // the hot loops; passing them through an empty asm makes them opaque, so they stay in registers (the same cure as in
+    // raster_backward.cu).
+    int lane = tr & 31;
+    unsigned list_off = (unsigned)warp * FWD_BATCH, queue_off = (unsigned)warp * (FWD_Q * 32) + (unsigned)lane;
+#ifndef GSTEX_FWD_NO_OPAQUE
+    asm volatile("" : "+r"(lane));
+    asm volatile("" : "+r"(list_off));
+    asm volatile("" : "+r"(queue_off));
+#endif
+    uint8_t *__restrict__ my_list = surv_base + list_off;
+    float *__restrict__ q_alpha = reinterpret_cast<float *>(surv_base + FWD_WARPS * FWD_BATCH) + queue_off;
+    uint8_t *__restrict__ q_ent = surv_base + FWD_WARPS * FWD_BATCH + sizeof(float) * FWD_WARPS * FWD_Q * 32 + queue_off;
+    const int tile = blockIdx.y * p.tiles_x + blockIdx.x;
+    int lx, ly;
+    tile_pixel(p.bw, tr, lx, ly);
+    const int col = blockIdx.x * p.bw + lx, row = blockIdx.y * p.bw + ly;
+    const bool inside = (tr < p.bw * p.bw) && col < p.img_w && row < p.img_h;
+    const PixelConsts pc = make_pixel(col, row, p.c2w, p.viewmat, p.fx, p.fy, p.cx, p.cy);
+    const WarpRect wr = make_warp_rect(col, row, inside);
+    const bool use_ndc = (p.settings & GSTEX_SET_NDC) != 0;
+    const bool bilinear = !(p.settings & GSTEX_SET_NEAREST);
+
+    const int2 range = p.bins[tile];
+    const int total = range.y - range.x;
+    const int nbatch = (total + FWD_BATCH - 1) / FWD_BATCH;
+
+    float T = 1.f;
+    float acc_c0 = 0.f, acc_c1 = 0.f, acc_c2 = 0.f;
+    float acc_n0 = 0.f, acc_n1 = 0.f, acc_n2 = 0.f;
+    float acc_t0 = 0.f, acc_t1 = 0.f, acc_t2 = 0.f;
+    float depth = 0.f, reg = 0.f, S0 = 0.f, S1 = 0.f, S2 = 0.f;
+    int last = 0, dlast = -1;
+    int qn = 0;  // candidates queued for this pixel
+    bool done = !inside;
+    // MODE_MASKS: the saved state bounds the walk - a pixel's candidates end at the last entry it composited (a pixel
+    // that composited nothing has final_T == 1 exactly; its final_idx of 0 would be ambiguous)
+    int my_last = -1;
+    if (!RENDER && inside) {
+        const int pix = row * p.img_w + col;
+        my_last = final_Ts_in[pix] < 1.f ? final_idx_in[pix] : -1;
+    }
+
+    // phase 2: every lane composites its own queue against stage buffer S (the records the queued entries index)
+    auto drain = [&](const float4 *__restrict__ S, int first) {
+        const int qmax = __reduce_max_sync(0xffffffffu, qn);
+        for (int k = 0; k < qmax; ++k) {
+            if (k < qn && !done) {
+                const float qa = q_alpha[k * 32];
+                const int i = q_ent[k * 32];
+                const float alpha = fabsf(qa);
+                const float next_T = __fmul_rn(T, __fsub_rn(1.f, alpha));
+                if (next_T <= T_STOP) {  // tested before the skip is honoured (reference texture.cu:216-221)
+                    done = true;
+                } else if (qa > 0.f) {   // sign bit: skipped for its ray distance (texture.cu:213)
+                    const float4 *__restrict__ R = S + i * REC_PITCH;
+                    const float4 q0 = R[0], q3 = R[3], q4 = R[4], q5 = R[5], q6 = R[6], q7 = R[7];
+                    const float c3 = R[1].w;
+                    // the same operations, in the same order, as eval_pair(): t, u and v come out bit-identical to what
+                    // phase 1 tested and to what the backward pass recomputes for this pair
+                    const float ex = __fsub_rn(pc.px, q0.x), ey = __fsub_rn(pc.py, q0.y);
+                    float d = fmaf(q3.x, ex, fmaf(q3.y, ey, c3));
+                    if (fabsf(d) < pc.eps) d = copysignf(pc.eps, d);
+                    const float rD = fast_rcp(d);
+                    const float t = __fmul_rn(__fmul_rn(q0.z, rD), pc.rn);
+                    const float vis = alpha * T;
+                    acc_c0 = fmaf(q6.x, vis, acc_c0);
+                    acc_c1 = fmaf(q6.y, vis, acc_c1);
+                    acc_c2 = fmaf(q6.z, vis, acc_c2);
+                    acc_n0 = fmaf(q7.x, vis, acc_n0);
+                    acc_n1 = fmaf(q7.y, vis, acc_n1);
+                    acc_n2 = fmaf(q7.z, vis, acc_n2);
+                    const float nu = fmaf(q4.x, ex, fmaf(q4.y, ey, q4.z));
+                    const float nv = fmaf(q5.x, ex, fmaf(q5.y, ey, q5.z));
+                    const float u = clamp01(fmaf(nu, rD, q4.w)), v = clamp01(fmaf(nv, rD, q5.w));
+                    TexFetch tf;
+                    texel_setup(__float_as_int(q3.z), __float_as_int(q3.w), __float_as_int(q6.w), u, v, bilinear, tf);
+                    const float4 t0 = __ldg(p.tex4 + tf.idx[0]), t1 = __ldg(p.tex4 + tf.idx[1]);
+                    const float4 t2 = __ldg(p.tex4 + tf.idx[2]), t3 = __ldg(p.tex4 + tf.idx[3]);
+                    const float t_view = t * pc.vdep;
+                    if (T > 0.5f) {  // median depth (reference texture.cu:286-291)
+                        depth = t_view;
+                        dlast = first + i;
+                    }
+                    float tv = t;
+                    if (use_ndc) tv = (T_FAR * t_view - T_FAR * T_NEAR) / ((T_FAR - T_NEAR) * t_view);
+                    reg += vis * (tv * tv * S0 + S2 - 2.f * tv * S1);  // helpers.cuh:259-264
+                    S0 += vis;
+                    S1 += vis * tv;
+                    S2 += vis * tv * tv;
+                    T = next_T;
+                    last = first + i;
+                    const float w0 = tf.w[0] * vis, w1 = tf.w[1] * vis, w2 = tf.w[2] * vis, w3 = tf.w[3] * vis;
+                    acc_t0 += w0 * t0.x + w1 * t1.x + w2 * t2.x + w3 * t3.x;
+                    acc_t1 += w0 * t0.y + w1 * t1.y + w2 * t2.y + w3 * t3.y;
+                    acc_t2 += w0 * t0.z + w1 * t1.z + w2 * t2.z + w3 * t3.z;
+                }
+            }
+        }
+        qn = 0;
+    };
+
+    if (nbatch > 0) stage_records(stage[0], p.recs, p.ids, range.x, min(FWD_BATCH, total), tr, p.nthreads);
+
+    for (int b = 0; b < nbatch; ++b) {
+        const int first = range.x + b * FWD_BATCH;
+        const int cnt = min(FWD_BATCH, range.y - first);
+        if (!fwd_stage_advance(stage, p, range, b, nbatch, tr, done)) break;
+        const float4 *__restrict__ S = stage[b % FWD_STAGES];
+        if (RENDER && tr < cnt) {  // one thread per staged record: start fetching its texture block
+            const float4 q3 = S[quad_slot(tr, 3)], q6 = S[quad_slot(tr, 6)];
+            prefetch_texture_block(p.tex4, __float_as_int(q6.w), __float_as_int(q3.z), __float_as_int(q3.w));
+        }
+        // warp-level culling: the warp walks only the records that can reach alpha >= 1/255 on its patch
+        const int nsurv = __all_sync(0xffffffffu, done) ? 0 : build_survivors<BLUR, true>(S, 0, cnt, wr, p.mean2d, my_list, lane);
+        for (int si = 0; si < nsurv; ++si) {
+            const int i = my_list[si];
+            const float4 *__restrict__ R = S + i * REC_PITCH;
+            const float4 q0 = R[0], q1 = R[1], q2 = R[2], q3 = R[3];
+            PairEval pe;
+            eval_pair<BLUR>(q0, q1, q2, q3, pc, p.mean2d, pe);
+            if (!RENDER) done = done || first + i > my_last;
+            const bool cand = !done && pe.alpha >= ALPHA_MIN;
+            const bool tskip = pe.t < T_NEAR || pe.t > T_FAR;
+            const unsigned bm = __ballot_sync(0xffffffffu, cand && !tskip);
+            if (p.masks && bm != 0u && lane == 0) p.masks[(size_t)(first + i) * MASK_WARPS + warp] = bm;
+            if (!RENDER) {
+                if (__all_sync(0xffffffffu, done)) break;
+            } else {
+                if (cand) {
+                    q_alpha[qn * 32] = tskip ? -pe.alpha : pe.alpha;
+                    q_ent[qn * 32] = (uint8_t)i;
+                    ++qn;
+                }
+                if (__any_sync(0xffffffffu, qn >= FWD_Q)) {
+                    drain(S, first);
+                    if (__all_sync(0xffffffffu, done)) break;
+                }
+            }
+        }
+        // the queued entries index this stage's records: drain before the buffer can be refilled
+        if (RENDER && __any_sync(0xffffffffu, qn > 0)) drain(S, first);
+    }
+    __pipeline_wait_prior(0);
+
+    if (RENDER && inside) {
+        const int pix = row * p.img_w + col;
+        const float bg0 = p.background[0], bg1 = p.background[1], bg2 = p.background[2];
+        o.final_Ts[pix] = T;
+        o.final_idx[pix] = last;
+        o.depth_idx[pix] = dlast;
+        o.out_img[3 * pix + 0] = fmaf(T, bg0, acc_c0);
+        o.out_img[3 * pix + 1] = fmaf(T, bg1, acc_c1);
+        o.out_img[3 * pix + 2] = fmaf(T, bg2, acc_c2);
+        o.out_normal[3 * pix + 0] = acc_n0;
+        o.out_normal[3 * pix + 1] = acc_n1;
+        o.out_normal[3 * pix + 2] = acc_n2;
+        o.out_depth[pix] = depth;
+        o.out_reg[pix] = reg;
+        o.out_reg_s[3 * pix + 0] = S0;
+        o.out_reg_s[3 * pix + 1] = S1;
+        o.out_reg_s[3 * pix + 2] = S2;
+        o.out_texture[3 * pix + 0] = acc_t0;
+        o.out_texture[3 * pix + 1] = acc_t1;
+        o.out_texture[3 * pix + 2] = acc_t2;
+    }
+}
+
+// C3 = true : 3-channel texture read through the padded float4 copy (VIS builds only; the non-VIS 3-channel case is the
+//             queued kernel above).  C3 = false: runtime channel count (<= 64) read from the caller's (X,C) array.
+template <bool C3, bool BLUR, bool VIS>
+__global__ void __launch_bounds__(RASTER_MAX_THREADS, GSTEX_FWD_MINB) raster_forward_inline_kernel(const RasterCommon p, const ForwardOut o) {
+    extern __shared__ __align__(16) unsigned char fwd_smem[];
+    float4 (*stage)[FWD_BATCH * REC_PITCH] = reinterpret_cast<float4 (*)[FWD_BATCH * REC_PITCH]>(fwd_smem);
+    uint8_t *const surv_base = fwd_smem + sizeof(float4) * FWD_STAGES * FWD_BATCH * REC_PITCH;
+
+    const int tr = threadIdx.x, lane = tr & 31, warp = tr >> 5;
+    uint8_t *__restrict__ my_list = surv_base + warp * FWD_BATCH;
     const int tile = blockIdx.y * p.tiles_x + blockIdx.x;
     int lx, ly;
     tile_pixel(p.bw, tr, lx, ly);
@@ -84,7 +322,7 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, GSTEX_FWD_MINB) raster_for
 
     const int2 range = p.bins[tile];
     const int total = range.y - range.x;
-    const int nbatch = (total + RASTER_BATCH - 1) / RASTER_BATCH;
+    const int nbatch = (total + FWD_BATCH - 1) / FWD_BATCH;
 
     float T = 1.f;
     float acc_c0 = 0.f, acc_c1 = 0.f, acc_c2 = 0.f;
@@ -96,37 +334,16 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, GSTEX_FWD_MINB) raster_for
     int last = 0, dlast = -1;
     bool done = !inside;
 
-    if (nbatch > 0) stage_records(stage[0], p.recs, p.ids, range.x, min(RASTER_BATCH, total), tr, p.nthreads);
+    if (nbatch > 0) stage_records(stage[0], p.recs, p.ids, range.x, min(FWD_BATCH, total), tr, p.nthreads);
 
     for (int b = 0; b < nbatch; ++b) {
-        const int first = range.x + b * RASTER_BATCH;
-        const int cnt = min(RASTER_BATCH, range.y - first);
-        if (b + 1 < nbatch) {
-            stage_records(stage[(b + 1) % GSTEX_FWD_STAGES], p.recs, p.ids, first + RASTER_BATCH,
-                          min(RASTER_BATCH, range.y - first - RASTER_BATCH), tr, p.nthreads);
-            // the ids of stage b+2 (512 contiguous bytes) start travelling now: the gather of the next iteration begins
-            // with a dependent load of them
-            if (tr < 4 && first + 2 * RASTER_BATCH + 32 * tr < range.y)
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(p.ids + first + 2 * RASTER_BATCH + 32 * tr));
-            __pipeline_wait_prior(1);
-        } else {
-            __pipeline_wait_prior(0);
-        }
-        // stage b is visible to the whole CTA after this barrier; leave if every pixel is finished
-        if (__syncthreads_count(done) >= p.nthreads) break;
-        const float4 *__restrict__ S = stage[b % GSTEX_FWD_STAGES];
-#ifndef GSTEX_EXP_NO_PREFETCH
-        if (C3 && tr < cnt) {  // one thread per staged record: start fetching its texture block
-            const float4 q3 = S[quad_slot(tr, 3)], q6 = S[quad_slot(tr, 6)];
-            prefetch_texture_block(p.tex4, __float_as_int(q6.w), __float_as_int(q3.z), __float_as_int(q3.w));
-        }
-#endif
-        // warp-level culling: the warp walks only the records that can reach alpha >= 1/255 on its patch
+        const int first = range.x + b * FWD_BATCH;
+        const int cnt = min(FWD_BATCH, range.y - first);
+        if (!fwd_stage_advance(stage, p, range, b, nbatch, tr, done)) break;
+        const float4 *__restrict__ S = stage[b % FWD_STAGES];
         const int nsurv = __all_sync(0xffffffffu, done) ? 0 : build_survivors<BLUR, !VIS>(S, 0, cnt, wr, p.mean2d, my_list, lane);
         // The survivor walk is warp-uniform: finished pixels stay in the loop (predicated off) so that the blend
-        // decision of all 32 pixels is one ballot - the mask word the backward pass reads - written with one plain
-        // store per (entry, warp) instead of an atomic OR from inside the divergent blend path.
-#pragma unroll FWD_UNROLL
+        // decision of all 32 pixels is one ballot - the mask word the backward pass reads.
         for (int si = 0; si < nsurv; ++si) {
             if (__all_sync(0xffffffffu, done)) break;
             const int i = my_list[si];
@@ -144,7 +361,7 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, GSTEX_FWD_MINB) raster_for
             const bool blend = !done && !pair_skipped(pe);
             const unsigned bm = __ballot_sync(0xffffffffu, blend);
             if (bm == 0u) continue;
-            if (!VIS && p.masks && lane == 0) p.masks[(size_t)(first + i) * MASK_WARPS + (tr >> 5)] = bm;
+            if (!VIS && p.masks && lane == 0) p.masks[(size_t)(first + i) * MASK_WARPS + warp] = bm;
             if (blend) {
                 const float4 q4 = R[4], q5 = R[5], q6 = R[6], q7 = R[7];
                 const float vis = pe.alpha * T;
@@ -169,14 +386,8 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, GSTEX_FWD_MINB) raster_for
                 TexFetch tf;
                 texel_setup(__float_as_int(q3.z), __float_as_int(q3.w), __float_as_int(q6.w), u, v, bilinear, tf);
                 if (C3) {
-#ifdef GSTEX_EXP_NO_TEXLOAD  // timing experiment only: what the four texel loads cost
-                    const float4 t0 = make_float4(u, v, u, v), t1 = make_float4(v, u, v, u);
-                    const float4 t2 = make_float4(tf.w[0], u, v, u), t3 = make_float4(tf.w[1], v, u, v);
-                    if (tf.idx[0] + tf.idx[1] + tf.idx[2] + tf.idx[3] == -12345) acc_t[0] += 1.f;
-#else
                     const float4 t0 = __ldg(p.tex4 + tf.idx[0]), t1 = __ldg(p.tex4 + tf.idx[1]);
                     const float4 t2 = __ldg(p.tex4 + tf.idx[2]), t3 = __ldg(p.tex4 + tf.idx[3]);
-#endif
                     const float tvis = VIS ? cvis : vis;
                     const float w0 = tf.w[0] * tvis, w1 = tf.w[1] * tvis, w2 = tf.w[2] * tvis, w3 = tf.w[3] * tvis;
                     acc_t[0] += w0 * t0.x + w1 * t1.x + w2 * t2.x + w3 * t3.x;
@@ -210,9 +421,6 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, GSTEX_FWD_MINB) raster_for
                 last = first + i;
             }
         }
-#if GSTEX_FWD_STAGES == 2
-        __syncthreads();  // everyone is done with stage b before it is refilled (two iterations ahead)
-#endif
     }
     __pipeline_wait_prior(0);
 
@@ -253,7 +461,7 @@ RasterCommon make_raster_common(int img_height, int img_width, int block_width, 
     p.tiles_x = ceil_div(img_width, block_width);
     p.bw = block_width;
     p.nthreads = ceil_div(block_width * block_width, 32) * 32;
-    p.settings = settings;
+    p.settings = settings & GSTEX_SET_SUPPORTED_FORWARD;  // unknown bits are ignored (see check_raster_args)
     p.channels = channels;
     p.ids = ids;
     p.bins = (const int2 *)tile_bins;
@@ -278,48 +486,68 @@ __global__ void __launch_bounds__(256) zero_masks_kernel(uint4 *__restrict__ mas
         masks[q] = make_uint4(0u, 0u, 0u, 0u);
 }
 
-int launch_raster_forward(const RasterCommon &p, const ForwardOut &o, int64_t mask_entries, const int32_t *d_count,
-                          cudaStream_t s) {
+template <bool BLUR, int MODE>
+static int launch_fwd_queued(const dim3 grid, const RasterCommon &p, const ForwardOut &o, const float *final_Ts_in,
+                             const int32_t *final_idx_in, cudaStream_t s) {
+    constexpr size_t smem = fwd_smem_bytes(MODE == MODE_RENDER);
+    static SmemOnceFlags once;  // one per template instantiation
+    const int rc = configure_dynamic_smem((const void *)raster_forward_queued_kernel<BLUR, MODE>, smem, true, once);
+    if (rc != GSTEX_OK) return rc;
+    raster_forward_queued_kernel<BLUR, MODE><<<grid, p.nthreads, smem, s>>>(p, o, final_Ts_in, final_idx_in);
+    return GSTEX_OK;
+}
+
+template <bool C3, bool BLUR, bool VIS>
+static int launch_fwd_inline(const dim3 grid, const RasterCommon &p, const ForwardOut &o, cudaStream_t s) {
+    constexpr size_t smem = fwd_smem_bytes(false);
+    static SmemOnceFlags once;
+    const int rc = configure_dynamic_smem((const void *)raster_forward_inline_kernel<C3, BLUR, VIS>, smem, true, once);
+    if (rc != GSTEX_OK) return rc;
+    raster_forward_inline_kernel<C3, BLUR, VIS><<<grid, p.nthreads, smem, s>>>(p, o);
+    return GSTEX_OK;
+}
+
+static int zero_masks(const RasterCommon &p, int64_t mask_entries, const int32_t *d_count, cudaStream_t s) {
     if (p.masks && mask_entries > 0) {
         const int blocks = (int)min((int64_t)148 * 8, ceil_div64(mask_entries * (MASK_WARPS / 4), 256));
         zero_masks_kernel<<<blocks, 256, 0, s>>>((uint4 *)p.masks, mask_entries, d_count);
         GSTEX_LAUNCH_OK("zero_masks_kernel");
     }
+    return GSTEX_OK;
+}
+
+int launch_raster_forward(const RasterCommon &p, const ForwardOut &o, int64_t mask_entries, const int32_t *d_count,
+                          cudaStream_t s) {
+    int rc = zero_masks(p, mask_entries, d_count, s);
+    if (rc != GSTEX_OK) return rc;
     const dim3 grid(p.tiles_x, ceil_div(p.img_h, p.bw));
     const bool blur = (p.settings & GSTEX_SET_BLUR) != 0;
-    const size_t dsm = GSTEX_FWD_STAGES == 3 ? sizeof(float4) * 3 * RASTER_BATCH * REC_PITCH : 0;
-    if (dsm) {  // opt in to > 48 KB of dynamic shared memory: once per device, only for the variant about to be launched
-        const bool vis = (p.settings & GSTEX_SET_VIS_ALL) != 0, c3 = p.channels == 3;
-        const int variant = (vis ? 4 : 0) | (c3 ? 2 : 0) | (blur ? 1 : 0);
-        static bool configured[64][8];
-        int dev = 0;
-        GSTEX_CUDA_OK(cudaGetDevice(&dev));
-        if (dev < 0 || dev >= 64 || !configured[dev][variant]) {
-            const void *fns[8] = {(const void *)raster_forward_kernel<false, false>, (const void *)raster_forward_kernel<false, true>,
-                                  (const void *)raster_forward_kernel<true, false>, (const void *)raster_forward_kernel<true, true>,
-                                  (const void *)raster_forward_kernel<false, false, true>, (const void *)raster_forward_kernel<false, true, true>,
-                                  (const void *)raster_forward_kernel<true, false, true>, (const void *)raster_forward_kernel<true, true, true>};
-            GSTEX_CUDA_OK(cudaFuncSetAttribute(fns[variant], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
-            GSTEX_CUDA_OK(cudaFuncSetAttribute(fns[variant], cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            if (dev >= 0 && dev < 64) configured[dev][variant] = true;
-        }
-    }
     if (p.settings & GSTEX_SET_VIS_ALL) {  // viewer-only modes: one generic build per channel layout, forward only
-        if (p.channels == 3) {
-            if (blur) raster_forward_kernel<true, true, true><<<grid, p.nthreads, dsm, s>>>(p, o);
-            else raster_forward_kernel<true, false, true><<<grid, p.nthreads, dsm, s>>>(p, o);
-        } else {
-            if (blur) raster_forward_kernel<false, true, true><<<grid, p.nthreads, dsm, s>>>(p, o);
-            else raster_forward_kernel<false, false, true><<<grid, p.nthreads, dsm, s>>>(p, o);
-        }
+        if (p.channels == 3) rc = blur ? launch_fwd_inline<true, true, true>(grid, p, o, s) : launch_fwd_inline<true, false, true>(grid, p, o, s);
+        else rc = blur ? launch_fwd_inline<false, true, true>(grid, p, o, s) : launch_fwd_inline<false, false, true>(grid, p, o, s);
     } else if (p.channels == 3) {
-        if (blur) raster_forward_kernel<true, true><<<grid, p.nthreads, dsm, s>>>(p, o);
-        else raster_forward_kernel<true, false><<<grid, p.nthreads, dsm, s>>>(p, o);
+        rc = blur ? launch_fwd_queued<true, MODE_RENDER>(grid, p, o, nullptr, nullptr, s)
+                  : launch_fwd_queued<false, MODE_RENDER>(grid, p, o, nullptr, nullptr, s);
     } else {
-        if (blur) raster_forward_kernel<false, true><<<grid, p.nthreads, dsm, s>>>(p, o);
-        else raster_forward_kernel<false, false><<<grid, p.nthreads, dsm, s>>>(p, o);
+        rc = blur ? launch_fwd_inline<false, true, false>(grid, p, o, s) : launch_fwd_inline<false, false, false>(grid, p, o, s);
     }
+    if (rc != GSTEX_OK) return rc;
     GSTEX_LAUNCH_OK("raster_forward_kernel");
+    return GSTEX_OK;
+}
+
+// Blend masks of a finished forward pass from its saved state (phase 1 of the queued kernel): see MODE_MASKS above.
+int launch_raster_masks(const RasterCommon &p, const float *final_Ts, const int32_t *final_idx, int64_t mask_entries,
+                        const int32_t *d_count, cudaStream_t s) {
+    int rc = zero_masks(p, mask_entries, d_count, s);
+    if (rc != GSTEX_OK) return rc;
+    const dim3 grid(p.tiles_x, ceil_div(p.img_h, p.bw));
+    const bool blur = (p.settings & GSTEX_SET_BLUR) != 0;
+    ForwardOut o{};
+    rc = blur ? launch_fwd_queued<true, MODE_MASKS>(grid, p, o, final_Ts, final_idx, s)
+              : launch_fwd_queued<false, MODE_MASKS>(grid, p, o, final_Ts, final_idx, s);
+    if (rc != GSTEX_OK) return rc;
+    GSTEX_LAUNCH_OK("raster_forward_queued_kernel<MODE_MASKS>");
     return GSTEX_OK;
 }
 
@@ -347,7 +575,10 @@ int check_raster_args(const char *who, int img_height, int img_width, int block_
                   "%s: n = %d, texels = %lld", who, n, (long long)num_texels);
     GSTEX_REQUIRE(channels >= 1 && channels <= RASTER_MAX_C, GSTEX_E_INVALID,
                   "%s: texture channels must be in [1, %d] (got %d)", who, RASTER_MAX_C, channels);
-    GSTEX_REQUIRE((settings & ~supported_settings) == 0, GSTEX_E_UNSUPPORTED,
+    // Bits no reference kernel reads (0, 1 - texture_edit's blur / ndc when one settings word is shared -, 3-7, 11-14,
+    // 30, 31) are ignored, as upstream ignores them.  Only bits this build KNOWS but the entry point does not implement
+    // are an error: the visualisation bits 15-29 in a backward call.
+    GSTEX_REQUIRE((settings & GSTEX_SET_SUPPORTED_FORWARD & ~supported_settings) == 0, GSTEX_E_UNSUPPORTED,
                   "%s: settings 0x%x has bits this entry point does not implement (supported mask 0x%x); the "
                   "visualisation bits 15-29 are forward-only", who, settings, supported_settings);
     return GSTEX_OK;
@@ -384,7 +615,8 @@ extern "C" int gstex_texture_forward(int img_height, int img_width, int block_wi
     float4 *recs = (float4 *)(base + L.recs_off);
     float2 *mean2d = (float2 *)(base + L.mean2d_off);
     float4 *tex4 = (float4 *)(base + L.tex4_off);
-    uint32_t *masks = (uint32_t *)(base + L.masks_off);
+    // num_intersects == 0 also serves inference-only callers: no blend masks are kept (and none zero-filled)
+    uint32_t *masks = num_intersects > 0 ? (uint32_t *)(base + L.masks_off) : nullptr;
     rc = launch_pack(n, means, scales, glob_scale, quats, opacities, colors, uv0, umap, vmap, texture_dims, viewmat, c2w,
                      fx, fy, cx, cy, recs, mean2d, s);
     if (rc != GSTEX_OK) return rc;

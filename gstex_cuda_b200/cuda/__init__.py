@@ -144,10 +144,9 @@ def _forward_scratch(n, num_texels, channels, num_intersects, dev) -> torch.Tens
     return torch.empty((nbytes,), dtype=torch.uint8, device=dev)
 
 
-def texture_forward_ex(tile_bounds, block, img_size, texture_info, texture_dims, gaussian_ids_sorted, tile_bins,
-                       colors, opacities, means, scales, glob_scale, quats, uv0, umap, vmap, texture, viewmat, c2w, fx,
-                       fy, cx, cy, settings, background):
-    """texture_forward plus the forward scratch (packed records, padded texture, blend masks) the backward needs."""
+def _texture_forward(keep_scratch, tile_bounds, block, img_size, texture_info, texture_dims, gaussian_ids_sorted,
+                     tile_bins, colors, opacities, means, scales, glob_scale, quats, uv0, umap, vmap, texture, viewmat,
+                     c2w, fx, fy, cx, cy, settings, background):
     _check_raster_inputs(texture_dims, gaussian_ids_sorted, tile_bins, colors, opacities, means, scales, quats, uv0,
                          umap, vmap, texture, viewmat, c2w, background)
     dev = means.device
@@ -162,7 +161,8 @@ def texture_forward_ex(tile_bounds, block, img_size, texture_info, texture_dims,
     out_texture, out_normal = torch.empty((H, W, C), **f32), torch.empty((H, W, 3), **f32)
     final_Ts, final_idx, depth_idx = torch.empty((H, W), **f32), torch.empty((H, W), **i32), torch.empty((H, W), **i32)
     out_reg_s = torch.empty((H, W, 3), **f32)
-    M = gaussian_ids_sorted.shape[0]
+    # the blend masks (32 B per list entry) are only kept for a caller that will hand the scratch to the backward
+    M = gaussian_ids_sorted.shape[0] if keep_scratch else 0
     scratch = _forward_scratch(n, X, C, M, dev)
     with torch.cuda.device(dev):
         rc = _lib.load().gstex_texture_forward(
@@ -175,19 +175,27 @@ def texture_forward_ex(tile_bounds, block, img_size, texture_info, texture_dims,
     return (out_img, out_depth, out_reg, out_texture, out_normal, final_Ts, final_idx, depth_idx, out_reg_s), scratch
 
 
+def texture_forward_ex(*args):
+    """texture_forward plus the forward scratch (packed records, padded texture, blend masks): handing it to
+    ``texture_backward(..., _fwd_scratch=scratch)`` saves that call the re-derivation of the three."""
+    return _texture_forward(True, *args)
+
+
 def texture_forward(*args):
-    """texture_forward_tensor, texture.cu:766-901: returns the same 9-tuple."""
-    return texture_forward_ex(*args)[0]
+    """texture_forward_tensor, texture.cu:766-901: returns the same 9-tuple.  Keeps no state for the backward."""
+    return _texture_forward(False, *args)[0]
 
 
 def texture_backward(img_height, img_width, block_width, texture_info, texture_dims, gaussian_ids_sorted, tile_bins,
                      colors, opacities, means, scales, glob_scale, quats, uv0, umap, vmap, texture, viewmat, c2w, fx, fy,
                      cx, cy, settings, background, final_Ts, final_idx, depth_idx, final_s, v_output, v_output_depth,
                      v_output_reg, v_output_alpha, v_output_texture, v_output_normal, _fwd_scratch=None):
-    """texture_backward_tensor, texture.cu:915-1053: returns the same 9-tuple of gradients.
+    """texture_backward_tensor, texture.cu:915-1053: returns the same 9-tuple of gradients, a pure function of its
+    arguments like upstream.
 
     ``_fwd_scratch`` (keyword, optional, not in the reference signature) is the scratch tensor returned by
-    ``texture_forward_ex`` for the same inputs; without it the forward pass is run again first.
+    ``texture_forward_ex`` for the same inputs; with it the call skips re-packing the records / texture and re-deriving
+    the blend masks from ``final_Ts`` / ``final_idx`` (a cull + alpha walk over the lists, no second forward pass).
     """
     _check_raster_inputs(texture_dims, gaussian_ids_sorted, tile_bins, colors, opacities, means, scales, quats, uv0,
                          umap, vmap, texture, viewmat, c2w, background)
@@ -201,30 +209,38 @@ def texture_backward(img_height, img_width, block_width, texture_info, texture_d
     H, W, bw = int(img_height), int(img_width), int(block_width)
     n, X, C = means.shape[0], texture.shape[0], int(texture_info[2])
     nprob = int(texture_info[1])
+    M = gaussian_ids_sorted.shape[0]
     f32 = dict(dtype=torch.float32, device=dev)
     v_colors, v_opacity = torch.empty((n, 3), **f32), torch.empty((n, 1), **f32)
     v_means, v_scales, v_quats = torch.empty((n, 3), **f32), torch.empty((n, 3), **f32), torch.empty((n, 4), **f32)
-    v_uv0, v_umap, v_vmap = torch.empty((n, nprob, 2), **f32), torch.empty((n, nprob, 3), **f32), torch.empty((n, nprob, 3), **f32)
+    # (n, num_probs, k) zero-filled as upstream (texture.cu:1004-1006).  The reference kernels address these arrays
+    # (and uv0 / umap / vmap) flat, as float2 / float3 element g (texture.cu:743-756), whatever num_probs is: Gaussian
+    # g's gradient lands at flat element g, and so it does here
+    if nprob == 1:
+        v_uv0, v_umap, v_vmap = torch.empty((n, 1, 2), **f32), torch.empty((n, 1, 3), **f32), torch.empty((n, 1, 3), **f32)
+        o_uv0, o_umap, o_vmap = v_uv0, v_umap, v_vmap
+    else:
+        v_uv0, v_umap, v_vmap = torch.zeros((n, nprob, 2), **f32), torch.zeros((n, nprob, 3), **f32), torch.zeros((n, nprob, 3), **f32)
+        o_uv0, o_umap, o_vmap = torch.empty((n, 2), **f32), torch.empty((n, 3), **f32), torch.empty((n, 3), **f32)
     v_texture = torch.empty((X, C), **f32)
     lib = _lib.load()
     with torch.cuda.device(dev):
-        if _fwd_scratch is None:
-            # the reference's backward is a pure function of its arguments; ours differentiates the pairs recorded by
-            # the forward pass, so a caller that kept no scratch pays for one more forward here
-            _, _fwd_scratch = texture_forward_ex(
-                ((W + bw - 1) // bw, (H + bw - 1) // bw, 1), (bw, bw, 1), (W, H, 1), texture_info, texture_dims,
-                gaussian_ids_sorted, tile_bins, colors, opacities, means, scales, glob_scale, quats, uv0, umap, vmap,
-                texture, viewmat, c2w, fx, fy, cx, cy, settings, background)
-        temp = torch.empty((lib.gstex_texture_backward_temp_bytes(n, X, C),), dtype=torch.uint8, device=dev)
+        nbytes = (lib.gstex_texture_backward_temp_bytes(n, X, C) if _fwd_scratch is not None
+                  else lib.gstex_texture_backward_stateless_temp_bytes(n, X, C, M))
+        temp = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
         rc = lib.gstex_texture_backward(
-            H, W, bw, n, X, C, gaussian_ids_sorted.shape[0], _p(texture_dims), _p(gaussian_ids_sorted), _p(tile_bins), _p(colors), _p(opacities),
+            H, W, bw, n, X, C, M, _p(texture_dims), _p(gaussian_ids_sorted), _p(tile_bins), _p(colors), _p(opacities),
             _p(means), _p(scales), float(glob_scale), _p(quats), _p(uv0), _p(umap), _p(vmap), _p(texture), _p(viewmat),
             _p(c2w), float(fx), float(fy), float(cx), float(cy), int(settings), _p(background), _p(final_Ts),
             _p(final_idx), _p(depth_idx), _p(final_s), _p(v_output), _p(v_output_depth), _p(v_output_reg),
             _p(v_output_alpha), _p(v_output_texture), _p(v_output_normal), _p(v_colors), _p(v_opacity), _p(v_means),
-            _p(v_scales), _p(v_quats), _p(v_uv0), _p(v_umap), _p(v_vmap), _p(v_texture), 0, _p(_fwd_scratch), _p(temp),
+            _p(v_scales), _p(v_quats), _p(o_uv0), _p(o_umap), _p(o_vmap), _p(v_texture), 0, _p(_fwd_scratch), _p(temp),
             temp.numel(), _stream(dev))
     _lib.check(rc, "texture_backward")
+    if nprob != 1:
+        v_uv0.view(-1)[:2 * n] = o_uv0.view(-1)
+        v_umap.view(-1)[:3 * n] = o_umap.view(-1)
+        v_vmap.view(-1)[:3 * n] = o_vmap.view(-1)
     return v_colors, v_opacity, v_means, v_scales, v_quats, v_uv0, v_umap, v_vmap, v_texture
 
 

@@ -113,7 +113,9 @@ class _TextureGaussians(Function):
         # 4. same gaussian_ids_sorted / tile_bins as bin_and_sort_gaussians (utils.py:106-162 upstream), from the fused
         #    bucket-by-tile + per-tile sort (csrc/binning_tiles.cu) instead of the global 64-bit key sort
         gaussian_ids_sorted, tile_bins, _, _ = bin_tiles(centers, extents, depths, tile_bounds, bw, num_intersects)
-        masks = torch.empty((num_intersects, 8), **i32)  # blend masks: forward -> backward (csrc/raster.cuh)
+        # blend masks: forward -> backward (csrc/raster.cuh); not kept (nor zero-filled) for an inference-only call
+        need_grad = any(ctx.needs_input_grad)
+        masks = torch.empty((num_intersects, 8), **i32) if need_grad else None
         tex = tex4 if C == 3 else texture
         with torch.cuda.device(dev):
             rc = lib.gstex_raster_forward(H, W, bw, C, int(settings), _p(gaussian_ids_sorted), _p(tile_bins), _p(recs),
@@ -125,8 +127,9 @@ class _TextureGaussians(Function):
         ctx.img_width, ctx.img_height, ctx.block_width = W, H, bw
         ctx.texture_info, ctx.settings, ctx.glob_scale = texture_info, int(settings), float(glob_scale)
         ctx.intr = (fx, fy, cx, cy)
-        ctx.save_for_backward(gaussian_ids_sorted, tile_bins, means, scales, quats, umap, vmap, texture, viewmat, c2w,
-                              background, final_Ts, final_idx, depth_idx, out_reg_s, recs, mean2d, tex4, masks)
+        if need_grad:
+            ctx.save_for_backward(gaussian_ids_sorted, tile_bins, means, scales, quats, umap, vmap, texture, viewmat, c2w,
+                                  background, final_Ts, final_idx, depth_idx, out_reg_s, recs, mean2d, tex4, masks, uv0)
         out_alpha = 1 - final_Ts
         return out_img, out_depth, out_reg, out_alpha, out_texture, out_normal
 
@@ -138,7 +141,7 @@ class _TextureGaussians(Function):
             grads = [torch.zeros_like(t) for t in (colors, opacity, means, scales, quats, uv0, umap, vmap, texture)]
         else:
             (gaussian_ids_sorted, tile_bins, means, scales, quats, umap, vmap, texture, viewmat, c2w, background,
-             final_Ts, final_idx, depth_idx, out_reg_s, recs, mean2d, tex4, masks) = ctx.saved_tensors
+             final_Ts, final_idx, depth_idx, out_reg_s, recs, mean2d, tex4, masks, uv0) = ctx.saved_tensors
             lib = _lib.load()
             H, W, bw = ctx.img_height, ctx.img_width, ctx.block_width
             dev = means.device
@@ -160,7 +163,12 @@ class _TextureGaussians(Function):
             vtex4 = torch.zeros((X, 4), **f32) if C == 3 else None  # padded texel gradients
             v_colors, v_opacity = torch.empty((n, 3), **f32), torch.empty((n, 1), **f32)
             v_means, v_scales, v_quats = torch.empty((n, 3), **f32), torch.empty((n, 3), **f32), torch.empty((n, 4), **f32)
-            v_uv0, v_umap, v_vmap = torch.empty((n, 1, 2), **f32), torch.empty((n, 1, 3), **f32), torch.empty((n, 1, 3), **f32)
+            # shaped like the inputs ((n, num_probs, k) upstream, zero-filled: texture.cu:1004-1006); the kernels address
+            # them flat, Gaussian g at element g, exactly as the reference kernels do
+            if uv0.numel() == 2 * n:
+                v_uv0, v_umap, v_vmap = torch.empty_like(uv0), torch.empty_like(umap), torch.empty_like(vmap)
+            else:
+                v_uv0, v_umap, v_vmap = torch.zeros_like(uv0), torch.zeros_like(umap), torch.zeros_like(vmap)
             s = torch.cuda.current_stream(dev).cuda_stream
             tex = tex4 if C == 3 else texture
             vtex = vtex4 if C == 3 else v_texture

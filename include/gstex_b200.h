@@ -149,11 +149,15 @@ int gstex_bin_tiles(int n, const float *centers, const float *extents, const flo
  * the entry), which is what the backward pass differentiates. */
 size_t gstex_texture_forward_temp_bytes(int n, int64_t num_texels, int channels, int64_t num_intersects);
 size_t gstex_texture_backward_temp_bytes(int n, int64_t num_texels, int channels);
+/* temp size of a gstex_texture_backward call WITHOUT forward scratch (fwd_temp == NULL): the call then rebuilds the
+ * records, the padded texture and the blend masks from its own arguments, like the reference's stateless backward. */
+size_t gstex_texture_backward_stateless_temp_bytes(int n, int64_t num_texels, int channels, int64_t num_intersects);
 
 /* replaces texture_forward_tensor, texture.cu:766-901 (kernel :11-329).
  * Outputs (all fully written): out_img (H,W,3), out_depth (H,W), out_reg (H,W), out_texture (H,W,C),
  * out_normal (H,W,3), final_Ts (H,W), final_idx (H,W) int32, depth_idx (H,W) int32, out_reg_s (H,W,3).
- * background: 3 floats on the device. */
+ * background: 3 floats on the device.  num_intersects = 0 (with the matching temp size) renders without keeping blend
+ * masks - for inference-only callers and for callers that will use the stateless backward. */
 int gstex_texture_forward(int img_height, int img_width, int block_width, int n, int64_t num_texels,
                           int channels, int64_t num_intersects, const int32_t *texture_dims,
                           const int32_t *gaussian_ids_sorted, const int32_t *tile_bins, const float *colors,
@@ -166,9 +170,10 @@ int gstex_texture_forward(int img_height, int img_width, int block_width, int n,
                           size_t temp_bytes, gstex_stream_t stream);
 
 /* replaces texture_backward_tensor, texture.cu:915-1053 (kernel :331-760).
- * fwd_temp: the scratch the matching gstex_texture_forward call (same inputs) filled; the reference's backward is a
- * pure function of its arguments (texture.cuh:120-168), so a caller without that scratch runs the forward again
- * first (gstex_cuda_b200/cuda/__init__.py does).  Gradients (n,3) (n,1) (n,3) (n,3) (n,4) (n,1,2)
+ * fwd_temp: the scratch the matching gstex_texture_forward call (same inputs) filled, or NULL.  The reference's backward
+ * is a pure function of its arguments (texture.cuh:120-168); with fwd_temp == NULL this call is too: it re-packs the
+ * records, re-pads the texture and re-derives the blend masks from final_Ts / final_idx (a cull + alpha walk, no
+ * compositing), and `temp` must then hold gstex_texture_backward_stateless_temp_bytes().  Gradients (n,3) (n,1) (n,3) (n,3) (n,4) (n,1,2)
  * (n,1,3) (n,1,3) (X,C): if accumulate == 0 they are overwritten (no zero-fill needed), otherwise the
  * view's gradient is added to what they hold (multi-view accumulation). */
 int gstex_texture_backward(int img_height, int img_width, int block_width, int n, int64_t num_texels,
@@ -257,6 +262,14 @@ int gstex_raster_forward(int img_height, int img_width, int block_width, int cha
                          float *out_reg, float *out_texture, float *out_normal, float *final_Ts,
                          int32_t *final_idx, int32_t *depth_idx, float *out_reg_s, uint32_t *masks,
                          int64_t mask_entries, const int32_t *d_num_intersects, gstex_stream_t stream);
+/* Re-derives the blend masks of a finished forward pass from its saved state: pixel p composited list entry i iff
+ * i <= final_idx[p] and the pair passes the skip test (what the reference's backward re-evaluates, texture.cu:484-558).
+ * For callers that did not keep the masks gstex_raster_forward wrote. */
+int gstex_raster_masks(int img_height, int img_width, int block_width, int settings,
+                       const int32_t *gaussian_ids_sorted, const int32_t *tile_bins, const float *recs,
+                       const float *mean2d, const float *viewmat, const float *c2w, float fx, float fy, float cx,
+                       float cy, const float *final_Ts, const int32_t *final_idx, uint32_t *masks,
+                       int64_t mask_entries, const int32_t *d_num_intersects, gstex_stream_t stream);
 int gstex_raster_backward(int img_height, int img_width, int block_width, int channels, int settings,
                           const int32_t *gaussian_ids_sorted, const int32_t *tile_bins, const float *recs,
                           const float *mean2d, const float *tex, const float *viewmat, const float *c2w, float fx,

@@ -205,7 +205,8 @@ def test_visualisation_modes_vs_oracle(settings, C, seed):
 
 def test_visualisation_bits_are_forward_only():
     """The reference's backward ignores the viewer bits (it would differentiate a different image); here the backward
-    entry points reject them, and bits outside the reference's settings word are rejected everywhere."""
+    entry points reject them.  Bits no reference kernel reads (0, 1 - texture_edit's blur / ndc -, 30 ...) are ignored,
+    as upstream ignores them."""
     s = random_small_scene(10, 32, 32, seed=1, device=DEV)
     b = bin_cuda(s)
     ids, bins = b["gaussian_ids_sorted"], b["tile_bins"]
@@ -213,8 +214,42 @@ def test_visualisation_bits_are_forward_only():
     f, scratch = forward_cuda(s, ids, bins, settings=st)
     with pytest.raises(RuntimeError, match="settings"):
         backward_cuda(s, ids, bins, f, random_vout(s, 0), settings=st, scratch=scratch)
-    with pytest.raises(RuntimeError, match="settings"):
-        forward_cuda(s, ids, bins, settings=(1 << 8) | (1 << 30))
+    f0, _ = forward_cuda(s, ids, bins, settings=1 << 8)
+    f1, sc1 = forward_cuda(s, ids, bins, settings=(1 << 8) | (1 << 30) | 3)
+    for k in f0:
+        assert torch.equal(f0[k], f1[k]), k
+    backward_cuda(s, ids, bins, f1, random_vout(s, 0), settings=(1 << 8) | (1 << 30) | 3, scratch=sc1)
+
+
+@pytest.mark.parametrize("settings,C", [(1 << 8, 3), ((1 << 8) | (1 << 9), 3), (1 << 8, 5)])
+def test_stateless_backward_equals_backward_with_forward_scratch(settings, C):
+    """texture_backward without the forward's scratch (the reference's signature: a pure function of its arguments,
+    texture.cu:915-1053) re-derives records, padded texture and blend masks itself and must return what the call that
+    reuses the forward scratch returns (up to the order of the atomic sums).  Saturating scene: the stop rule matters."""
+    s = random_small_scene(1500, 96, 80, seed=41, channels=C, device=DEV, spread=5.0, scale_pow=0.1)
+    s["opacities"][::3] = 1.0
+    s["settings"] = settings
+    b = bin_cuda(s)
+    ids, bins = b["gaussian_ids_sorted"], b["tile_bins"]
+    f, scratch = forward_cuda(s, ids, bins)
+    assert float((f["final_Ts"] < 1e-3).float().mean()) > 0.05
+    vout = random_vout(s, 7)
+    g_a = backward_cuda(s, ids, bins, f, vout, scratch=scratch)
+    g_b = backward_cuda(s, ids, bins, f, vout, scratch=None)
+    for k in g_a:
+        a, bb = to_np(g_a[k]), to_np(g_b[k])
+        scale = float(np.abs(a).max()) + 1e-20
+        err = float(np.abs(a - bb).max()) / scale
+        print(f"  {k}: max|d|/max|g| = {err:.2e}")
+        assert err < 1e-4, k
+    # the plain texture_forward keeps no state either and returns the same images
+    from gstex_cuda_b200 import cuda as _C
+    from gpu_util import raster_args
+    a = raster_args(s, ids, bins)
+    tb = ((s["W"] + 15) // 16, (s["H"] + 15) // 16, 1)
+    outs = _C.texture_forward(tb, (16, 16, 1), (s["W"], s["H"], 1), s["texture_info"], *a["common"])
+    for got, k in zip(outs, f):
+        assert torch.equal(got, f[k]), k
 
 
 # ---- general cameras: every fixture above looks down +z with an identity rotation (as example.py does) -----------
