@@ -37,7 +37,7 @@ _PROTOS = {
     "gstex_sort_pairs": (c_i, [c_i64, c_fp, c_fp, c_fp, c_fp, c_i, c_fp, c_fp, c_sz, c_fp]),
     "gstex_get_tile_bin_edges": (c_i, [c_i64, c_fp, c_fp, c_fp, c_fp]),
     "gstex_bin_tiles_temp_bytes": (c_sz, [c_i, c_i64]),
-    "gstex_bin_tiles": (c_i, [c_i, c_fp, c_fp, c_fp, c_i, c_i, c_i, c_i64, c_fp, c_fp, c_fp, c_fp, c_fp, c_sz, c_fp]),
+    "gstex_bin_tiles": (c_i, [c_i, c_fp, c_fp, c_fp, c_i, c_i, c_i, c_i64, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_sz, c_fp]),
     "gstex_texture_forward_temp_bytes": (c_sz, [c_i, c_i64, c_i, c_i64]),
     "gstex_texture_backward_temp_bytes": (c_sz, [c_i, c_i64, c_i]),
     "gstex_texture_backward_stateless_temp_bytes": (c_sz, [c_i, c_i64, c_i, c_i64]),
@@ -55,7 +55,8 @@ _PROTOS = {
     "gstex_image_loss": (c_i, [c_i, c_i] + [c_fp] * 11 + [c_fp]),
     "gstex_pad_texture": (c_i, [c_i64, c_fp, c_fp, c_fp]),
     "gstex_unpad_texture_grad": (c_i, [c_i64, c_fp, c_fp, c_i, c_fp]),
-    "gstex_pack_records": (c_i, [c_i] + [c_fp] * 5 + [c_f] + [c_fp] * 6 + [c_f] * 4 + [c_fp, c_fp, c_fp]),
+    "gstex_pack_records": (c_i, [c_i] + [c_fp] * 5 + [c_f] + [c_fp] * 6 + [c_f] * 4 + [c_fp, c_fp, c_fp, c_fp]),
+    "gstex_fill_zero": (c_i, [c_fp, c_sz, c_fp]),
     "gstex_raster_forward": (c_i, [c_i] * 5 + [c_fp] * 7 + [c_f] * 4 + [c_fp] * 10 + [c_fp, c_i64, c_fp] + [c_fp]),
     "gstex_raster_masks": (c_i, [c_i] * 4 + [c_fp] * 6 + [c_f] * 4 + [c_fp] * 3 + [c_i64, c_fp] + [c_fp]),
     "gstex_raster_backward": (c_i, [c_i] * 5 + [c_fp] * 7 + [c_f] * 4 + [c_fp] * 11 + [c_fp, c_fp, c_fp] + [c_fp]),

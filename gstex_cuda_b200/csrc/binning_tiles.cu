@@ -47,7 +47,8 @@ __global__ void __launch_bounds__(256) tb_count_kernel(int n, const float2 *__re
 // one CTA of 1024 threads: exclusive scan of tile_count -> tile_start, tile_bins, total
 __global__ void __launch_bounds__(1024) tb_scan_kernel(int num_tiles, const int32_t *__restrict__ tile_count,
                                                        int32_t *__restrict__ tile_start, int2 *__restrict__ tile_bins,
-                                                       int32_t *__restrict__ num_intersects, int64_t cap) {
+                                                       int32_t *__restrict__ num_intersects, int64_t cap,
+                                                       int32_t *__restrict__ max_seen) {
     __shared__ int warp_sums[32];
     __shared__ int carry_s;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -86,7 +87,12 @@ __global__ void __launch_bounds__(1024) tb_scan_kernel(int num_tiles, const int3
         if (threadIdx.x == 1023) carry_s = carry + warp_sums[31];
         __syncthreads();
     }
-    if (threadIdx.x == 0) *num_intersects = carry_s;
+    if (threadIdx.x == 0) {
+        *num_intersects = carry_s;
+        // running maximum over the calls that share `max_seen` (same stream): what a no-host-sync caller compares with its
+        // capacity once in a while to detect dropped intersections
+        if (max_seen && carry_s > *max_seen) *max_seen = carry_s;
+    }
 }
 
 __global__ void __launch_bounds__(256) tb_scatter_kernel(int n, const float2 *__restrict__ centers,
@@ -303,8 +309,8 @@ extern "C" size_t gstex_bin_tiles_temp_bytes(int num_tiles, int64_t capacity) {
 
 extern "C" int gstex_bin_tiles(int n, const float *centers, const float *extents, const float *depths, int tiles_x,
                                int tiles_y, int block_width, int64_t capacity, int32_t *gaussian_ids_sorted,
-                               int64_t *isect_ids_sorted, int32_t *tile_bins, int32_t *num_intersects, void *temp,
-                               size_t temp_bytes, gstex_stream_t stream) {
+                               int64_t *isect_ids_sorted, int32_t *tile_bins, int32_t *num_intersects,
+                               int32_t *max_intersects_seen, void *temp, size_t temp_bytes, gstex_stream_t stream) {
     GSTEX_REQUIRE(n >= 0 && block_width > 0 && tiles_x > 0 && tiles_y > 0, GSTEX_E_INVALID,
                   "bin_tiles: n = %d, bw = %d, tiles = %dx%d", n, block_width, tiles_x, tiles_y);
     GSTEX_REQUIRE(capacity >= 0 && capacity < ((int64_t)1 << 31), GSTEX_E_INVALID, "bin_tiles: capacity = %lld",
@@ -325,7 +331,8 @@ extern "C" int gstex_bin_tiles(int n, const float *centers, const float *extents
                                                          tiles_y, fbw, tile_count);
         GSTEX_LAUNCH_OK("tb_count_kernel");
     }
-    tb_scan_kernel<<<1, 1024, 0, s>>>(num_tiles, tile_count, tile_start, (int2 *)tile_bins, num_intersects, capacity);
+    tb_scan_kernel<<<1, 1024, 0, s>>>(num_tiles, tile_count, tile_start, (int2 *)tile_bins, num_intersects, capacity,
+                                      max_intersects_seen);
     GSTEX_LAUNCH_OK("tb_scan_kernel");
     if (n == 0 || capacity == 0) return GSTEX_OK;
     tb_scatter_kernel<<<ceil_div(n, 256), 256, 0, s>>>(n, (const float2 *)centers, (const float2 *)extents, depths,

@@ -75,9 +75,15 @@ __global__ void __launch_bounds__(256, GSTEX_PACK_MINB) pack_kernel(int n, const
                                                    const int32_t *__restrict__ texture_dims,
                                                    const float *__restrict__ viewmat, const float *__restrict__ c2w,
                                                    float fx, float fy, float cx, float cy,
-                                                   float4 *__restrict__ recs, float2 *__restrict__ mean2d) {
+                                                   float4 *__restrict__ recs, float2 *__restrict__ mean2d,
+                                                   float4 *__restrict__ acc_to_zero) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n) return;
+    if (acc_to_zero) {  // the view's moment line starts from zero: cleared here instead of by a separate fill pass
+        float4 *a = acc_to_zero + (size_t)g * 8;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     PackCamera cam;
     load_camera(c2w, viewmat, cam);
     const Vec3 mean = ld3(means + 3 * g);
@@ -119,7 +125,8 @@ __global__ void __launch_bounds__(256, GSTEX_EPI_MINB) epilogue_kernel(
     const float *__restrict__ viewmat, const float *__restrict__ c2w, float fx, float fy, float cx, float cy,
     const float4 *__restrict__ acc, float *__restrict__ v_colors, float *__restrict__ v_opacity,
     float *__restrict__ v_means, float *__restrict__ v_scales, float4 *__restrict__ v_quats,
-    float2 *__restrict__ v_uv0, float *__restrict__ v_umap, float *__restrict__ v_vmap, int accumulate) {
+    float2 *__restrict__ v_uv0, float *__restrict__ v_umap, float *__restrict__ v_vmap, int accumulate_flags) {
+    const int accumulate = accumulate_flags & 1, accumulate_colors = (accumulate_flags >> 1) & 1;
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n) return;
     PackCamera cam;
@@ -189,9 +196,9 @@ __global__ void __launch_bounds__(256, GSTEX_EPI_MINB) epilogue_kernel(
     put(&v_vmap[3 * g + 0], v_vm.x, accumulate);
     put(&v_vmap[3 * g + 1], v_vm.y, accumulate);
     put(&v_vmap[3 * g + 2], v_vm.z, accumulate);
-    put(&v_colors[3 * g + 0], q5.x, accumulate);
-    put(&v_colors[3 * g + 1], q5.y, accumulate);
-    put(&v_colors[3 * g + 2], q5.z, accumulate);
+    put(&v_colors[3 * g + 0], q5.x, accumulate_colors);
+    put(&v_colors[3 * g + 1], q5.y, accumulate_colors);
+    put(&v_colors[3 * g + 2], q5.z, accumulate_colors);
     put(&v_opacity[g], q1.w, accumulate);
 }
 
@@ -217,11 +224,11 @@ __global__ void __launch_bounds__(256) unpad_texture_grad_kernel(int64_t num_tex
 int launch_pack(int n, const float *means, const float *scales, float glob_scale, const float *quats,
                 const float *opacities, const float *colors, const float *uv0, const float *umap, const float *vmap,
                 const int32_t *texture_dims, const float *viewmat, const float *c2w, float fx, float fy, float cx,
-                float cy, float4 *recs, float2 *mean2d, cudaStream_t s) {
+                float cy, float4 *recs, float2 *mean2d, cudaStream_t s, float4 *acc_to_zero) {
     if (n == 0) return GSTEX_OK;
     pack_kernel<<<ceil_div(n, 256), 256, 0, s>>>(n, means, scales, glob_scale, (const float4 *)quats, opacities,
                                                  colors, (const float2 *)uv0, umap, vmap, texture_dims, viewmat, c2w,
-                                                 fx, fy, cx, cy, recs, mean2d);
+                                                 fx, fy, cx, cy, recs, mean2d, acc_to_zero);
     GSTEX_LAUNCH_OK("pack_kernel");
     return GSTEX_OK;
 }

@@ -9,6 +9,12 @@
 
 using namespace gstex;
 
+extern "C" int gstex_fill_zero(void *ptr, size_t bytes, gstex_stream_t stream) {
+    GSTEX_REQUIRE(ptr != nullptr || bytes == 0, GSTEX_E_INVALID, "fill_zero: NULL pointer");
+    if (bytes) GSTEX_CUDA_OK(cudaMemsetAsync(ptr, 0, bytes, as_stream(stream)));
+    return GSTEX_OK;
+}
+
 extern "C" int gstex_pad_texture(int64_t num_texels, const float *texture, float *tex4, gstex_stream_t stream) {
     GSTEX_REQUIRE(num_texels >= 0, GSTEX_E_INVALID, "pad_texture: texels = %lld", (long long)num_texels);
     return launch_pad_texture(num_texels, texture, (float4 *)tex4, as_stream(stream));
@@ -24,10 +30,10 @@ extern "C" int gstex_pack_records(int n, const int32_t *texture_dims, const floa
                                   const float *means, const float *scales, float glob_scale, const float *quats,
                                   const float *uv0, const float *umap, const float *vmap, const float *viewmat,
                                   const float *c2w, float fx, float fy, float cx, float cy, float *recs,
-                                  float *mean2d, gstex_stream_t stream) {
+                                  float *mean2d, float *acc_to_zero, gstex_stream_t stream) {
     GSTEX_REQUIRE(n >= 0, GSTEX_E_INVALID, "pack_records: n = %d", n);
     return launch_pack(n, means, scales, glob_scale, quats, opacities, colors, uv0, umap, vmap, texture_dims, viewmat,
-                       c2w, fx, fy, cx, cy, (float4 *)recs, (float2 *)mean2d, as_stream(stream));
+                       c2w, fx, fy, cx, cy, (float4 *)recs, (float2 *)mean2d, as_stream(stream), (float4 *)acc_to_zero);
 }
 
 extern "C" int gstex_raster_forward(int img_height, int img_width, int block_width, int channels, int settings,

@@ -314,12 +314,12 @@ int launch_raster_backward(const RasterCommon &p, const BackwardIn &in, const Ba
 int launch_pack(int n, const float *means, const float *scales, float glob_scale, const float *quats,
                 const float *opacities, const float *colors, const float *uv0, const float *umap, const float *vmap,
                 const int32_t *texture_dims, const float *viewmat, const float *c2w, float fx, float fy, float cx,
-                float cy, float4 *recs, float2 *mean2d, cudaStream_t s);
+                float cy, float4 *recs, float2 *mean2d, cudaStream_t s, float4 *acc_to_zero = nullptr);
 int launch_epilogue(int n, const float *means, const float *scales, float glob_scale, const float *quats,
                     const float *umap, const float *vmap, const float *viewmat, const float *c2w, float fx, float fy,
                     float cx, float cy, const float4 *acc, float *v_colors, float *v_opacity, float *v_means,
                     float *v_scales, float *v_quats, float *v_uv0, float *v_umap, float *v_vmap, int accumulate,
-                    cudaStream_t s);
+                    cudaStream_t s);  // accumulate: 0 / 1 = overwrite / add everything; see gstex_raster_epilogue for bit 1
 int launch_pad_texture(int64_t num_texels, const float *tex, float4 *tex4, cudaStream_t s);
 int launch_unpad_texture_grad(int64_t num_texels, const float4 *g4, float *v_texture, int accumulate, cudaStream_t s);
 FwdLayout forward_layout(int n, int64_t num_texels, int channels, int64_t num_intersects);

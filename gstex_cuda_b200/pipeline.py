@@ -4,14 +4,19 @@ SH backward, for every view of the rank's share of a batch, with NO host synchro
 
 This is the host side of the hot path for BASELINE configs 4 and 5.  It replaces, per view,
 the ~60 torch/extension launches and the blocking ``.item()`` of the reference trainer (example.py:121-209,
-utils.py:58) with ~16 launches of libgstex_b200 kernels on one stream over preallocated buffers:
+utils.py:58) with ~15 launches of libgstex_b200 kernels over preallocated buffers.  Every device operation of the step
+goes through the C ABI - kernels are counted in ``launches``, the few stream-ordered memsets (texel-gradient buffer and
+loss once per step, tile counters once per view) in ``fills``; no torch op runs inside ``step()``:
 
 * binning is the fused bucket-by-tile + per-tile shared-memory sort of csrc/binning_tiles.cu (bit-identical ids and
   tile ranges, no cumulative sum, no global 64-bit sort); the intersection count never leaves the device, the id
-  buffer has a fixed capacity (``max_intersects``) and what does not fit is dropped - ``check_overflow()`` reports
-  it when the caller next synchronises anyway;
-* the texture is padded to float4 once per step, texel gradients of all views accumulate in one padded
-  buffer and are un-padded once per step;
+  buffer has a fixed capacity (``max_intersects``; by default n * tiles when that is small - which cannot overflow -
+  else 16 n) and what does not fit is dropped: the binning kernel keeps the running maximum of the count on the device
+  and ``check_overflow()`` (called by the trainer every ``check_every`` steps and by ``loss_value()``) raises if it
+  ever exceeded the capacity;
+* texels are read as one aligned float4: a (X,3) texture is padded once per step and its gradients un-padded once per
+  step; a texture stored as (X,4) (``texture_rgba=True``: channels r, g, b, unused) needs neither pass - the
+  rasterisers read it and accumulate its gradient in place;
 * parameter gradients of all views accumulate in ONE contiguous fp32 arena (``grad_arena``), which is what
   the data-parallel wrapper all-reduces over NCCL (one collective per step, SURVEY 8e);
 * the step is a two-stream software pipeline over the views: the two rasteriser kernels (instruction-issue bound, most
@@ -39,13 +44,15 @@ class FusedTrainStep:
                  *, intrins: Tuple[float, float, float, float], sh_degree: int = 3, block_width: int = 16,
                  settings: int = 1 << 8, glob_scale: float = 1.0, background: Optional[torch.Tensor] = None,
                  max_intersects: Optional[int] = None, grad_views: Optional[Dict[str, torch.Tensor]] = None,
-                 texture_is_raw: bool = False):
+                 texture_is_raw: bool = False, texture_rgba: bool = False):
         """``params`` holds the ACTIVATED parameters the rasteriser consumes.  Colours come from ``sh_coeffs``
         (N,K,3) through clamp(SH + 0.5, 0, 1) or, when ``params`` has ``colors`` (N,3) instead,
         are used as given (example.py:162).  ``grad_views`` places named gradients (e.g. ``v_means``,
         ``v_sh_coeffs``, ``v_texture``) in caller-owned tensors instead of this object's arena (trainer.py keeps
-        them in its raw-parameter gradient arena).  ``texture_is_raw``: ``params["texture"]`` holds pre-sigmoid
-        texels; the sigmoid and its VJP are fused into the padding / un-padding passes (example.py:171)."""
+        them in its raw-parameter gradient arena; ``loss`` places the loss accumulator).  ``texture_is_raw``:
+        ``params["texture"]`` holds pre-sigmoid texels; the sigmoid and its VJP are fused into the padding / un-padding
+        passes (example.py:171).  ``texture_rgba``: ``params["texture"]`` is (X,4) - three channels stored at a 16-byte
+        pitch - and so is its gradient ``v_texture``; no padding passes run."""
         self.lib = _lib.load()
         self.p = params
         dev = params["means"].device
@@ -54,6 +61,7 @@ class FusedTrainStep:
         self.dev = dev
         self.use_sh = "sh_coeffs" in params
         self.texture_is_raw = bool(texture_is_raw)
+        self.texture_rgba = bool(texture_rgba)
         for k in ("means", "scales", "quats", "opacities", "sh_coeffs" if self.use_sh else "colors", "uv0", "umap",
                   "vmap", "texture"):
             t = params[k]
@@ -62,6 +70,10 @@ class FusedTrainStep:
         self.texture_dims = texture_dims.contiguous()
         self.n = params["means"].shape[0]
         self.X, self.C = params["texture"].shape
+        if self.texture_rgba:
+            if self.C != 4 or self.texture_is_raw:
+                raise RuntimeError("texture_rgba needs an activated (X,4) texture")
+            self.C = 3  # three channels at a float4 pitch
         self.H, self.W, self.bw = int(img_height), int(img_width), int(block_width)
         self.intr = tuple(float(v) for v in intrins)
         self.sh_degree = int(sh_degree)
@@ -76,7 +88,9 @@ class FusedTrainStep:
         self.tiles_x, self.tiles_y = -(-self.W // self.bw), -(-self.H // self.bw)
         self.num_tiles = self.tiles_x * self.tiles_y
         self.end_bit = 32 + max(1, math.ceil(math.log2(max(2, self.num_tiles))))
-        self.cap = int(max_intersects if max_intersects is not None else 8 * self.n)
+        # default capacity: the exact bound n * tiles when that is small (cannot overflow), else 16 n
+        self.cap = int(max_intersects if max_intersects is not None
+                       else min(self.n * self.num_tiles, max(16 * self.n, 1 << 20)))
         f32 = dict(dtype=torch.float32, device=dev)
         i32 = dict(dtype=torch.int32, device=dev)
         n, X, C, H, W = self.n, self.X, self.C, self.H, self.W
@@ -85,7 +99,8 @@ class FusedTrainStep:
         # ---- gradient arena: [means 3 | scales 3 | quats 4 | opacity 1 | uv0 2 | umap 3 | vmap 3 | sh 3K | texture C*X/n]
         gv = dict(grad_views or {})
         col_name, col_shape = ("v_sh_coeffs", (n, self.K, 3)) if self.use_sh else ("v_colors", (n, 3))
-        shapes = [(name, (n, w)) for name, w in _GRAD_FIELDS] + [(col_name, col_shape), ("v_texture", (X, C))]
+        shapes = ([(name, (n, w)) for name, w in _GRAD_FIELDS] +
+                  [(col_name, col_shape), ("v_texture", (X, 4 if self.texture_rgba else C)), ("loss", (1,))])
         own = [(name, shp) for name, shp in shapes if name not in gv]
         # every field starts on a 256-byte boundary: the kernels use 8- and 16-byte vector accesses on some of them
         pad = lambda sz: -(-sz // 64) * 64  # noqa: E731
@@ -104,9 +119,15 @@ class FusedTrainStep:
                 self.grads[name] = t.view(*shp)
 
         # ---- per-step buffers
-        self.tex4 = torch.empty((X, 4), **f32) if C == 3 else None
-        self.vtex4 = torch.empty((X, 4), **f32) if C == 3 else None
-        self.loss = torch.zeros(1, **f32)
+        if self.texture_rgba:  # read and accumulated in place
+            self.tex4, self.vtex4 = params["texture"], self.grads["v_texture"]
+        else:
+            self.tex4 = torch.empty((X, 4), **f32) if C == 3 else None
+            self.vtex4 = torch.empty((X, 4), **f32) if C == 3 else None
+        # the loss accumulator is the last slot of the gradient arena: the data-parallel all-reduce sums it with the
+        # gradients in ONE collective
+        self.loss = self.grads["loss"]
+        self.has_grad_views = bool(gv)
         # ---- per-view buffers.  Everything the side stream produces for a view (and the moment lines it consumes)
         # exists twice, so that view k+1 can be prepared while view k is still being rasterised.
         self.sets = [self._make_view_set(f32, i32) for _ in range(2)]
@@ -125,7 +146,8 @@ class FusedTrainStep:
         self.launches = 0
         self.time_kernels = False
         self.kernel_events: List[Tuple[str, torch.cuda.Event, torch.cuda.Event]] = []
-        self._bin_launches = 5  # tile count, tile scan, scatter, two per-tile sort size classes
+        self._bin_launches = 5  # tile count, tile scan, scatter, two per-tile sort size classes (+ one memset)
+        self.fills = 0  # stream-ordered memsets issued through the C ABI (not kernels: not part of `launches`)
         # The rasterisers are issue-bound and leave most of the HBM bandwidth idle; the bandwidth-bound housekeeping that
         # does not depend on them (texture padding, zero-fills of the moment lines / texel-gradient buffer) runs on a
         # side stream underneath binning and the forward rasteriser and is joined with events where its result is needed.
@@ -200,20 +222,24 @@ class FusedTrainStep:
             raise RuntimeError(f"{name} must be contiguous (row-major); call .contiguous() on it")
         return m
 
+    def _zero(self, t: torch.Tensor) -> None:
+        """Stream-ordered zero fill through the C ABI (a cudaMemsetAsync, counted in `fills`)."""
+        self._ck(self.lib.gstex_fill_zero(t.data_ptr(), t.numel() * t.element_size(), self._s()), "fill_zero")
+        self.fills += 1
+
     def begin_step(self) -> None:
-        """Once per optimiser step: pad the texture, clear the texel-gradient buffer and the loss."""
+        """Once per optimiser step: pad the texture (unless it is stored padded), clear the texel-gradient buffer and the
+        loss."""
         lib = self.lib
         main = torch.cuda.current_stream(self.dev)
         self.side.wait_stream(main)  # the parameters (and last step's consumers of tex4 / vtex4) are settled on `main`
         with torch.cuda.stream(self.side):
-            if self.C == 3:
+            if self.C == 3 and not self.texture_rgba:
                 pad = lib.gstex_sigmoid_pad_texture if self.texture_is_raw else lib.gstex_pad_texture
                 self._ck(pad(self.X, self.p["texture"].data_ptr(), self.tex4.data_ptr(), self._s()), "pad_texture")
                 self.launches += 1
-                self.vtex4.zero_()
-            else:
-                self.grads["v_texture"].zero_()
-        self.loss.zero_()
+            self._zero(self.vtex4 if self.C == 3 else self.grads["v_texture"])
+        self._zero(self.loss)
         self._first_view = True
 
     def _prepare(self, v, viewmat: torch.Tensor, c2w: torch.Tensor, first: bool) -> None:
@@ -223,9 +249,6 @@ class FusedTrainStep:
         n, H, W, bw = self.n, self.H, self.W, self.bw
         fx, fy, cx, cy = self.intr
         P = lambda t: t.data_ptr()  # noqa: E731
-        v.acc.zero_()
-        if self.use_sh and not first:
-            v.v_colors.zero_()  # SH colours are per view (they feed this view's SH backward), never accumulated
         if self.use_sh:
             self._ck(lib.gstex_sh_colors_forward(n, self.sh_degree, self.sh_degree, P(p["means"]), P(c2w),
                                                  P(p["sh_coeffs"]), P(v.colors), P(v.mask), s), "sh_colors_forward")
@@ -235,12 +258,11 @@ class FusedTrainStep:
         # fused tile binning: bucket by tile + per-tile shared-memory sort; the intersection count stays on the device
         self._ck(lib.gstex_bin_tiles(n, P(v.centers), P(v.extents), P(v.depths), self.tiles_x, self.tiles_y, bw,
                                      self.cap, P(v.ids_sorted), 0, P(v.tile_bins), P(v.num_isect),
-                                     P(v.bin_temp), v.bin_temp.numel(), s), "bin_tiles")
-        torch.maximum(self.max_count_seen, v.num_isect, out=self.max_count_seen)
+                                     P(self.max_count_seen), P(v.bin_temp), v.bin_temp.numel(), s), "bin_tiles")
         self._ck(lib.gstex_pack_records(n, P(self.texture_dims), P(v.colors), P(p["opacities"]), P(p["means"]),
                                         P(p["scales"]), self.glob_scale, P(p["quats"]), P(p["uv0"]), P(p["umap"]),
-                                        P(p["vmap"]), P(viewmat), P(c2w), fx, fy, cx, cy, P(v.recs), P(v.mean2d), s),
-                 "pack_records")
+                                        P(p["vmap"]), P(viewmat), P(c2w), fx, fy, cx, cy, P(v.recs), P(v.mean2d),
+                                        P(v.acc), s), "pack_records")  # also clears the view's moment lines
         v.prep_done.record(torch.cuda.current_stream(self.dev))
         self.launches += int(self.use_sh) + 1 + self._bin_launches + 1  # sh, project, binning, pack
 
@@ -286,7 +308,9 @@ class FusedTrainStep:
         lib, s, p, g = self.lib, self._s(), self.p, self.grads
         fx, fy, cx, cy = self.intr
         P = lambda t: t.data_ptr()  # noqa: E731
-        acc_flag = 0 if first else 1
+        # geometry gradients accumulate over the views (bit 0); the colour gradient too when colours are parameters, but a
+        # view's SH colour gradient feeds only this view's SH backward and is overwritten (bit 1 clear)
+        acc_flag = 0 if first else (1 if self.use_sh else 3)
         self._ck(lib.gstex_raster_epilogue(self.n, P(p["means"]), P(p["scales"]), self.glob_scale, P(p["quats"]),
                                            P(p["umap"]), P(p["vmap"]), P(viewmat), P(c2w), fx, fy, cx, cy, P(v.acc),
                                            P(v.v_colors), P(g["v_opacity"]), P(g["v_means"]), P(g["v_scales"]),
@@ -294,7 +318,7 @@ class FusedTrainStep:
                  "raster_epilogue")
         if self.use_sh:
             self._ck(lib.gstex_sh_colors_backward(self.n, self.sh_degree, self.sh_degree, P(p["means"]), P(c2w),
-                                                  P(v.v_colors), P(v.mask), P(g["v_sh_coeffs"]), acc_flag, s),
+                                                  P(v.v_colors), P(v.mask), P(g["v_sh_coeffs"]), acc_flag & 1, s),
                      "sh_colors_backward")
         self.launches += 1 + int(self.use_sh)
 
@@ -329,8 +353,8 @@ class FusedTrainStep:
         self._first_view = False
 
     def end_step(self) -> None:
-        """Once per step: un-pad the texel gradients into the arena."""
-        if self.C == 3:
+        """Once per step: un-pad the texel gradients into the arena (nothing to do for a (X,4) texture)."""
+        if self.C == 3 and not self.texture_rgba:
             if self.texture_is_raw:  # gradient w.r.t. the pre-sigmoid texels: g * t (1 - t), fused into the un-padding
                 self._ck(self.lib.gstex_unpad_texture_grad_sigmoid(self.X, self.vtex4.data_ptr(), self.tex4.data_ptr(),
                                                                    self.grads["v_texture"].data_ptr(), 0, self._s()),
@@ -367,9 +391,23 @@ class FusedTrainStep:
                 side.wait_event(v.bwd_done)
                 self._tail(v, viewmat, c2w, k == 0)
         main.wait_stream(side)
+        if nv == 0:
+            # a rank without views (fewer views than ranks, short last batch) contributes zeros: nothing above has
+            # overwritten last step's gradients
+            self._zero(self.grad_arena)
+            for name, t in self.grads.items():
+                if t.data_ptr() < self.grad_arena.data_ptr() or t.data_ptr() >= self.grad_arena.data_ptr() + 4 * max(1, self.grad_arena.numel()):
+                    self._zero(t)
+            return self.loss
         self._first_view = False
         self.end_step()
         return self.loss
+
+    def loss_value(self) -> float:
+        """Host value of the loss of the last step (synchronises); raises if any view so far overflowed the capacity."""
+        val = float(self.loss.item())
+        self.check_overflow()
+        return val
 
     def check_overflow(self) -> int:
         """Largest intersection count seen so far (synchronises); raises if it exceeded the buffers."""
@@ -386,7 +424,12 @@ class DataParallelTrainStep:
     sharding logic)."""
 
     def __init__(self, inner, rank: int, world_size: int, group=None):
+        if getattr(inner, "has_grad_views", False):
+            raise RuntimeError("DataParallelTrainStep all-reduces inner.grad_arena: gradients placed in caller-owned "
+                               "grad_views would be left out (GStexTrainStep reduces its own arena)")
         self.inner, self.rank, self.world_size, self.group = inner, int(rank), int(world_size), group
+        self.time_collective = False
+        self.collective_events = []
 
     @staticmethod
     def shard(num_views: int, rank: int, world_size: int) -> List[int]:
@@ -398,6 +441,13 @@ class DataParallelTrainStep:
         if self.world_size > 1:
             import torch.distributed as dist
 
+            # ONE collective per step: the loss accumulator is the last slot of the arena
+            if self.time_collective:
+                a = torch.cuda.Event(enable_timing=True)
+                a.record()
             dist.all_reduce(self.inner.grad_arena, op=dist.ReduceOp.SUM, group=self.group)
-            dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=self.group)
+            if self.time_collective:
+                b = torch.cuda.Event(enable_timing=True)
+                b.record()
+                self.collective_events.append((a, b))
         return loss

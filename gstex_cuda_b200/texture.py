@@ -94,7 +94,7 @@ class _TextureGaussians(Function):
             if n > 0:
                 _lib.check(lib.gstex_pack_records(n, _p(texture_dims), _p(colors), _p(opacity), _p(means), _p(scales),
                                                   float(glob_scale), _p(quats), _p(uv0), _p(umap), _p(vmap), _p(viewmat),
-                                                  _p(c2w), fx, fy, cx, cy, _p(recs), _p(mean2d), s), "pack_records")
+                                                  _p(c2w), fx, fy, cx, cy, _p(recs), _p(mean2d), 0, s), "pack_records")
             if C == 3 and X > 0:
                 _lib.check(lib.gstex_pad_texture(X, _p(texture), _p(tex4), s), "pad_texture")
             # 3. the count (the reference's one sync per call)

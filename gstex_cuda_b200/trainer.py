@@ -36,9 +36,13 @@ class GStexTrainStep:
     def __init__(self, raw: Dict[str, torch.Tensor], texture_dims: torch.Tensor, img_height: int, img_width: int, *,
                  intrins: Tuple[float, float, float, float], sh_degree: int = 3, lr: float = 0.01,
                  betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8, grad_scale: float = 1.0,
-                 train_mapping: bool = False, rank: int = 0, world_size: int = 1, group=None, **fused_kwargs):
+                 train_mapping: bool = False, rank: int = 0, world_size: int = 1, group=None, check_every: int = 100,
+                 **fused_kwargs):
         """``raw``: the leaf parameters (copied into this object's arena; ``self.raw`` are views of it).
-        ``train_mapping``: example.py:118 freezes the uv mapping (its gradient is computed, the update skipped)."""
+        ``train_mapping``: example.py:118 freezes the uv mapping (its gradient is computed, the update skipped).
+        ``check_every``: every that many steps (and in ``loss_value()``) the running maximum of the intersection count
+        is read back and compared with the preallocated capacity - an overflow would otherwise drop intersections
+        silently, also under CUDA-graph replay (0 disables the periodic check)."""
         self.lib = _lib.load()
         dev = raw["means"].device
         if dev.type != "cuda":
@@ -51,10 +55,12 @@ class GStexTrainStep:
             raise RuntimeError("GStexTrainStep trains 3-channel textures (example.py:95)")
         K = (int(sh_degree) + 1) ** 2
         col = ("sh_coeffs", (n, K, 3)) if self.use_sh else ("rgbs", (n, 3))
-        # the mapping sits last so that a frozen mapping is simply left out of the Adam range
+        # the mapping sits after the trained fields so that a frozen mapping is simply left out of the Adam range; the last
+        # slot is the loss accumulator (no parameter: only its gradient-arena twin is used), so that the data-parallel
+        # all-reduce of the gradient arena sums the loss in the same collective
         self.fields: List[Tuple[str, Tuple[int, ...]]] = [
             ("means", (n, 3)), ("scales", (n, 3)), ("quats", (n, 4)), ("opacities", (n, 1)), col, ("texture", (X, 3)),
-            ("mapping", (n, 1, 4))]
+            ("mapping", (n, 1, 4)), ("loss", (1,))]
         pad = lambda sz: -(-sz // 64) * 64  # noqa: E731  (fields start on 256-byte boundaries: vector accesses)
         total = sum(pad(math.prod(shp)) for _, shp in self.fields)
         f32 = dict(dtype=torch.float32, device=dev)
@@ -65,13 +71,15 @@ class GStexTrainStep:
         off = 0
         for name, shp in self.fields:
             sz = math.prod(shp)
-            if tuple(raw[name].shape) != shp:
-                raise RuntimeError(f"raw[{name!r}] must have shape {shp}, got {tuple(raw[name].shape)}")
-            self.raw[name] = self.param_arena[off:off + sz].view(*shp)
-            self.raw[name].copy_(raw[name])
             self.raw_grads[name] = self.grad_arena[off:off + sz].view(*shp)
+            if name != "loss":
+                if tuple(raw[name].shape) != shp:
+                    raise RuntimeError(f"raw[{name!r}] must have shape {shp}, got {tuple(raw[name].shape)}")
+                self.raw[name] = self.param_arena[off:off + sz].view(*shp)
+                self.raw[name].copy_(raw[name])
             off += pad(sz)
-        self.n_train = total if train_mapping else total - pad(n * 4)
+        self.n_train = total - pad(1) - (0 if train_mapping else pad(n * 4))
+        self.check_every = int(check_every)
         self.n, self.X = n, X
         self.lr, self.betas, self.eps, self.grad_scale = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(grad_scale)
         self.rank, self.world_size, self.group = int(rank), int(world_size), group
@@ -85,7 +93,7 @@ class GStexTrainStep:
                         opacities=torch.empty((n, 1), **f32), uv0=torch.empty((n, 1, 2), **f32),
                         umap=torch.empty((n, 1, 3), **f32), vmap=torch.empty((n, 1, 3), **f32))
         params = dict(self.act, means=self.raw["means"], texture=self.raw["texture"])
-        grad_views = dict(v_means=self.raw_grads["means"], v_texture=self.raw_grads["texture"])
+        grad_views = dict(v_means=self.raw_grads["means"], v_texture=self.raw_grads["texture"], loss=self.raw_grads["loss"])
         if self.use_sh:
             params["sh_coeffs"] = self.raw["sh_coeffs"]
             grad_views["v_sh_coeffs"] = self.raw_grads["sh_coeffs"]
@@ -134,8 +142,7 @@ class GStexTrainStep:
         if self.world_size > 1:
             import torch.distributed as dist
 
-            dist.all_reduce(self.grad_arena, op=dist.ReduceOp.SUM, group=self.group)
-            dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=self.group)
+            dist.all_reduce(self.grad_arena, op=dist.ReduceOp.SUM, group=self.group)  # the loss rides in its last slot
         return loss
 
     def optimizer_step(self) -> None:
@@ -151,7 +158,17 @@ class GStexTrainStep:
     def step(self, cameras, targets) -> torch.Tensor:
         loss = self.forward_backward(cameras, targets)
         self.optimizer_step()
+        self._periodic_check()
         return loss
+
+    def _periodic_check(self) -> None:
+        if self.check_every > 0 and self.step_count % self.check_every == 0 and not torch.cuda.is_current_stream_capturing():
+            self.fused.check_overflow()
+
+    def loss_value(self) -> float:
+        """Host value of the last step's loss (synchronises) after checking that no view overflowed the capacity."""
+        self.fused.check_overflow()
+        return float(self.raw_grads["loss"].item())
 
     # ---- CUDA graph of one whole optimiser step ------------------------------------------------------------------
     def capture(self, cameras: Sequence[Tuple[torch.Tensor, torch.Tensor]], targets: Sequence[torch.Tensor]) -> None:
@@ -182,6 +199,7 @@ class GStexTrainStep:
             raise RuntimeError("GStexTrainStep.replay() before capture()")
         self._graph.replay()
         self.step_count += 1
+        self._periodic_check()
         return self._graph_loss
 
     @property

@@ -112,6 +112,6 @@ def bin_tiles(centers: Tensor, extents: Tensor, depths: Tensor, tile_bounds: Tup
     with torch.cuda.device(dev):
         rc = lib.gstex_bin_tiles(n, centers.data_ptr(), extents.data_ptr(), depths.data_ptr(), tx, ty, int(block_size),
                                  int(capacity), ids.data_ptr(), isect.data_ptr() if isect is not None else 0,
-                                 bins.data_ptr(), count.data_ptr(), temp.data_ptr(), temp.numel(), _stream(dev))
+                                 bins.data_ptr(), count.data_ptr(), 0, temp.data_ptr(), temp.numel(), _stream(dev))
     _lib.check(rc, "bin_tiles")
     return ids, bins, count, isect

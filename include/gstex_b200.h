@@ -131,12 +131,13 @@ int gstex_get_tile_bin_edges(int64_t m, const int64_t *isect_ids_sorted, int32_t
  * capacity: length of gaussian_ids_sorted / isect_ids_sorted; intersections past it are dropped and tile_bins is
  * clipped to it.  isect_ids_sorted may be NULL.  tile_bins (num_tiles,2) is fully written ((0,0) for empty tiles).
  * num_intersects: one int32 on the device = the true number of intersections (compare with capacity to detect
- * overflow). */
+ * overflow).  max_intersects_seen (may be NULL): one int32 on the device, raised to num_intersects when that is larger -
+ * a running maximum over the calls of a no-host-sync loop. */
 size_t gstex_bin_tiles_temp_bytes(int num_tiles, int64_t capacity);
 int gstex_bin_tiles(int n, const float *centers, const float *extents, const float *depths, int tiles_x, int tiles_y,
                     int block_width, int64_t capacity, int32_t *gaussian_ids_sorted, int64_t *isect_ids_sorted,
-                    int32_t *tile_bins, int32_t *num_intersects, void *temp, size_t temp_bytes,
-                    gstex_stream_t stream);
+                    int32_t *tile_bins, int32_t *num_intersects, int32_t *max_intersects_seen, void *temp,
+                    size_t temp_bytes, gstex_stream_t stream);
 
 /* ======================================================================================== *
  * (3) rasterise forward / (4) rasterise backward
@@ -243,7 +244,8 @@ int gstex_image_loss(int img_height, int img_width, const float *out_texture, co
 /* ---- staged entry points (host side: gstex_cuda_b200/pipeline.py) ---------------------------------------
  * The stages gstex_texture_forward / gstex_texture_backward run internally, exposed so that a multi-view step
  * pads the texture once, packs records per view and accumulates all views into one gradient arena.
- * recs: n x 32 floats, mean2d: n x 2 floats, acc: n x 32 floats (zero-filled by the caller per view),
+ * recs: n x 32 floats, mean2d: n x 2 floats, acc: n x 32 floats (zero-filled per view: gstex_pack_records does it in
+ * the same pass when given acc_to_zero, else the caller),
  * masks: mask_entries x 8 uint32 blend masks written by gstex_raster_forward (which first zeroes the words of the first
  * min(*d_num_intersects, mask_entries) entries; d_num_intersects NULL = all) and read by gstex_raster_backward,
  * tex / vtex: (X,4) padded when channels == 3, else the caller's (X,C) layout; vtex is accumulated into. */
@@ -254,7 +256,7 @@ int gstex_pack_records(int n, const int32_t *texture_dims, const float *colors, 
                        const float *means, const float *scales, float glob_scale, const float *quats,
                        const float *uv0, const float *umap, const float *vmap, const float *viewmat,
                        const float *c2w, float fx, float fy, float cx, float cy, float *recs, float *mean2d,
-                       gstex_stream_t stream);
+                       float *acc_to_zero, gstex_stream_t stream);
 int gstex_raster_forward(int img_height, int img_width, int block_width, int channels, int settings,
                          const int32_t *gaussian_ids_sorted, const int32_t *tile_bins, const float *recs,
                          const float *mean2d, const float *tex, const float *viewmat, const float *c2w, float fx,
@@ -283,6 +285,12 @@ int gstex_raster_epilogue(int n, const float *means, const float *scales, float 
                           float fy, float cx, float cy, const float *acc, float *v_colors, float *v_opacity,
                           float *v_means, float *v_scales, float *v_quats, float *v_uv0, float *v_umap,
                           float *v_vmap, int accumulate, gstex_stream_t stream);
+/* accumulate bit 0: add to the geometry gradients (means ... vmap, opacity) instead of overwriting them; bit 1: the same
+ * for v_colors alone (per-view colour gradients that feed an SH backward are overwritten while the rest accumulates). */
+
+/* cudaMemsetAsync(ptr, 0, bytes) on the stream: lets a host layer that owns no CUDA runtime binding (ctypes) clear
+ * its buffers in stream order. */
+int gstex_fill_zero(void *ptr, size_t bytes, gstex_stream_t stream);
 
 /* Fused view-dependent colour around the SH op: colors = clamp(SH(means - camera origin) + 0.5, 0, 1);
  * mask (n bytes) records which channels were not clamped and gates the backward. */

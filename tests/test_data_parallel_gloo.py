@@ -11,19 +11,20 @@ from gstex_cuda_b200.pipeline import DataParallelTrainStep
 
 
 class _FakeInner:
-    """Mimics FusedTrainStep.step: accumulates a known gradient per view into one flat arena."""
+    """Mimics FusedTrainStep.step: accumulates a known gradient per view into one flat arena whose LAST slot is the loss
+    accumulator (the all-reduce sums gradients and loss in one collective), and zero-fills when given no views."""
 
     def __init__(self, size):
-        self.grad_arena = torch.zeros(size)
+        self.grad_arena = torch.zeros(size + 1)
+        self.loss = self.grad_arena[-1:]
 
     def step(self, cameras, targets):
         self.grad_arena.zero_()
-        loss = torch.zeros(1)
         for (vm, _), tgt in zip(cameras, targets):
             v = float(vm[0, 0])
-            self.grad_arena += v * torch.arange(1, self.grad_arena.numel() + 1, dtype=torch.float32)
-            loss += v + float(tgt.sum())
-        return loss
+            self.grad_arena[:-1] += v * torch.arange(1, self.grad_arena.numel(), dtype=torch.float32)
+            self.loss += v + float(tgt.sum())
+        return self.loss
 
 
 def _worker(rank, world, port, nviews, out):
@@ -45,8 +46,12 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def test_two_rank_gloo_allreduce_equals_single_rank(tmp_path):
-    nviews, world = 7, 2
+import pytest
+
+
+@pytest.mark.parametrize("nviews", [7, 1])  # 1 view on 2 ranks: rank 1's shard is empty and must contribute zeros
+def test_two_rank_gloo_allreduce_equals_single_rank(tmp_path, nviews):
+    world = 2
     mp.spawn(_worker, args=(world, _free_port(), nviews, str(tmp_path)), nprocs=world, join=True)
     res = [torch.load(os.path.join(tmp_path, f"r{r}.pt")) for r in range(world)]
     # shards partition the views
@@ -59,6 +64,14 @@ def test_two_rank_gloo_allreduce_equals_single_rank(tmp_path):
     for r in res:
         torch.testing.assert_close(r["arena"], single.inner.grad_arena)
         torch.testing.assert_close(r["loss"], loss1)
+
+
+def test_wrapper_rejects_caller_owned_gradient_views():
+    """Gradients placed outside inner.grad_arena would be left out of the all-reduce."""
+    inner = _FakeInner(4)
+    inner.has_grad_views = True
+    with pytest.raises(RuntimeError, match="grad_views"):
+        DataParallelTrainStep(inner, 0, 2)
 
 
 def test_shard_partitions():

@@ -72,6 +72,31 @@ def test_fused_step_matches_api_path(nviews):
     assert abs(loss2 - float(loss)) <= 1e-5 * abs(loss2) + 1e-7
 
 
+def test_rgba_texture_layout_equals_padded_path_and_empty_shard_is_zero():
+    """texture_rgba=True: the (X,4) texture is read, and its gradient accumulated, in place - no padding passes - and
+    gives what the (X,3) path gives.  A step without views (a rank whose shard is empty) leaves zero gradients."""
+    s = synthetic_scene(20000, 256, 160, seed=11, device=DEV)
+    cams = [(s["viewmat"], s["c2w"])] + [(a.to(DEV), b.to(DEV)) for a, b in arc_cameras(5)[:2]]
+    g = torch.Generator().manual_seed(2)
+    targets = [torch.rand(s["H"], s["W"], 3, generator=g).to(DEV) for _ in range(3)]
+    kw = dict(intrins=s["intrins"], sh_degree=s["sh_degree"], background=s["background"])
+    f3 = FusedTrainStep({k: s[k] for k in PARAMS}, s["texture_dims"], s["H"], s["W"], **kw)
+    p4 = {k: s[k] for k in PARAMS}
+    p4["texture"] = torch.cat([s["texture"], torch.zeros_like(s["texture"][:, :1])], 1).contiguous()
+    f4 = FusedTrainStep(p4, s["texture_dims"], s["H"], s["W"], texture_rgba=True, **kw)
+    l3, l4 = float(f3.step(cams, targets)), float(f4.step(cams, targets))
+    assert f3.check_overflow() > 0 and f4.launches < f3.launches  # no pad / un-pad kernels
+    assert abs(l3 - l4) <= 1e-6 * abs(l3)
+    for k in f3.grads:
+        a, b = to_np(f3.grads[k]), to_np(f4.grads[k])
+        if k == "v_texture":
+            assert float(np.abs(b[:, 3]).max()) == 0.0
+            b = b[:, :3]
+        assert_close_frac(k, b.reshape(a.shape), a, 1e-3, 1e-9 + 2e-5 * float(np.abs(a).max()), 1e-4, 12, 0.05)
+    f4.step([], [])
+    assert float(f4.grad_arena.abs().max()) == 0.0 and float(f4.loss) == 0.0
+
+
 def test_sh_colors_fused_matches_oracle():
     from gstex_cuda_b200 import _lib
     s = synthetic_scene(5000, 64, 64, seed=3, device=DEV)
