@@ -53,6 +53,12 @@ def parse_args():
                     help="multiplies the C4 scene's Gaussian scales (SURVEY 8d: a denser second data point at 2.0)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-cuda", action="store_true",
+                    help="skip timing the unmodified reference CUDA extension (oracle/_ref) beside our path at N=1")
+    ap.add_argument("--no-scale-base", action="store_true",
+                    help="skip the 64-view C5 batch at N=1 (the 1-GPU point of the scaling curve)")
+    ap.add_argument("--texture-layout", default="rgba", choices=["rgba", "rgb"],
+                    help="rgba: texels stored (X,4) at a 16-byte pitch, read / accumulated in place; rgb: (X,3), padded per step")
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the frame in the CPU sample (0 = auto)")
     return ap.parse_args()
 
@@ -201,6 +207,90 @@ def run_reference(args, rank: int):
 
 
 # --------------------------------------------------------------------------------------------------
+# The unmodified reference CUDA extension beside our path (SURVEY 8d "Reference CUDA beside it"): a REPORTED comparison,
+# timed after our timed region on the same GPU, same inputs.  oracle/_ref is checker infrastructure: nothing of it is on
+# the measured path of `value` / `e2e`.
+# --------------------------------------------------------------------------------------------------
+def time_reference_cuda(scene, H, W, steps=5, warmup=2):
+    import importlib.util
+
+    import torch
+
+    so = os.path.join(ROOT, "oracle", "_ref", "gstex_ref_C.so")
+    if not os.path.exists(so):
+        return {"unavailable": "oracle/_ref/gstex_ref_C.so not built (python oracle/build_ref.py in the build container)"}
+    spec = importlib.util.spec_from_file_location("gstex_ref_C", so)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    s, N, bw = scene, scene["num_points"], 16
+    dev = s["means"].device
+    fx, fy, cx, cy = s["intrins"]
+    tb = ((W + bw - 1) // bw, (H + bw - 1) // bw, 1)
+    vm, c2w, gt, P = s["viewmat"], s["c2w"], s["target"], H * W
+
+    def ev():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def step(times):
+        """the reference pipeline: example.py:146-152 + texture.py:195-289 + example.py:189-209, torch glue as upstream"""
+        t = [ev()]
+        dirs = (s["means"] - c2w[:3, 3]).contiguous()
+        colors = torch.clamp(ref.compute_sh_forward(N, 3, 3, dirs, s["sh_coeffs"]) + 0.5, 0, 1).contiguous()
+        t.append(ev())
+        depths = (s["means"] @ vm[:3, :3].T + vm[:3, 3])[:, 2].contiguous()
+        centers, extents = ref.get_aabb_2d(s["means"], s["scales"], 1.0, s["quats"], vm, fx, fy, cx, cy)
+        tl = torch.floor((centers - extents) / bw).to(torch.int32)
+        br = torch.floor((centers + extents) / bw + 1).to(torch.int32)
+        tmin = torch.stack([tl[:, 0].clamp(0, tb[0]), tl[:, 1].clamp(0, tb[1])], -1)
+        tmax = torch.stack([br[:, 0].clamp(0, tb[0]), br[:, 1].clamp(0, tb[1])], -1)
+        nth = ((tmax - tmin)[:, 0] * (tmax - tmin)[:, 1]).to(torch.int32)
+        t.append(ev())
+        cum = torch.cumsum(nth, 0, dtype=torch.int32)
+        m = int(cum[-1].item())
+        isect, gids = ref.map_gaussian_to_intersects(N, m, centers, extents, depths, cum, tb, bw, False)
+        isect_s, perm = torch.sort(isect)
+        gids_s = torch.gather(gids, 0, perm)
+        bins = ref.get_tile_bin_edges(m, isect_s, tb)
+        t.append(ev())
+        outs = ref.texture_forward(tb, (bw, bw, 1), (W, H, 1), (N, 1, 3), s["texture_dims"], gids_s, bins, colors,
+                                   s["opacities"], s["means"], s["scales"], 1.0, s["quats"], s["uv0"], s["umap"],
+                                   s["vmap"], s["texture"], vm, c2w, fx, fy, cx, cy, 1 << 8, s["background"])
+        t.append(ev())
+        out_tex, out_n = outs[3], outs[4]
+        v_tex = (2.0 / (3 * P)) * (out_tex - gt)
+        v_n = torch.stack([2 * out_n[..., 0], 2 * out_n[..., 1], -2 * (1 - out_n[..., 2])], -1) / P
+        z = torch.zeros(H, W, device=dev)
+        v_reg = torch.full((H, W), 1.0 / P, device=dev)
+        t.append(ev())
+        g = ref.texture_backward(H, W, bw, (N, 1, 3), s["texture_dims"], gids_s, bins, colors, s["opacities"], s["means"],
+                                 s["scales"], 1.0, s["quats"], s["uv0"], s["umap"], s["vmap"], s["texture"], vm, c2w, fx,
+                                 fy, cx, cy, 1 << 8, s["background"], outs[5], outs[6], outs[7], outs[8],
+                                 torch.zeros(H, W, 3, device=dev), z, v_reg, z, v_tex.contiguous(), v_n.contiguous())
+        t.append(ev())
+        ref.compute_sh_backward(N, 3, 3, dirs, g[0].contiguous())
+        t.append(ev())
+        torch.cuda.synchronize()
+        names = ["sh_fwd", "project+aabb+count", "bin+sort", "raster_fwd", "loss_grad", "raster_bwd", "sh_bwd"]
+        for n_, a, b in zip(names, t[:-1], t[1:]):
+            times.setdefault(n_, []).append(a.elapsed_time(b))
+        times.setdefault("total", []).append(t[0].elapsed_time(t[-1]))
+        return m
+
+    for _ in range(warmup):
+        step({})
+    times = {}
+    for _ in range(steps):
+        m = step(times)
+    avg = {k: sum(v) / len(v) for k, v in times.items()}
+    return {"what": "UNMODIFIED reference CUDA extension (gstex_cuda @ abdc217, its JIT flags -O3, sm_100) through its own "
+                    "Python-level pipeline, same GPU, same scene, after our timed region; reported comparison only",
+            "steps": steps, "intersections": m, "ms": avg, "ms_per_step": avg["total"],
+            "mpixel_per_s": H * W / (avg["total"] * 1e-3) / 1e6}
+
+
+# --------------------------------------------------------------------------------------------------
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -210,11 +300,10 @@ def main():
         run_reference(args, rank)
         return
 
-    # rank 0 prints exactly one JSON line on stdout: NCCL writes its version banner and logs to stdout at any
-    # NCCL_DEBUG level >= VERSION, so the variable is cleared unless GSTEX_NCCL_DEBUG asks for logs, which then go to stderr
-    os.environ.pop("NCCL_DEBUG", None)
-    if os.environ.get("GSTEX_NCCL_DEBUG"):
-        os.environ["NCCL_DEBUG"] = os.environ["GSTEX_NCCL_DEBUG"]
+    # rank 0 prints exactly one JSON line on stdout.  NCCL writes its banner and logs to stdout at any NCCL_DEBUG level
+    # >= VERSION: when the caller asks for NCCL logs they are sent to stderr instead, so that the rank count can be read
+    # from them without breaking the one-line contract.
+    if os.environ.get("NCCL_DEBUG"):
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
@@ -235,25 +324,34 @@ def main():
     scene = synthetic_scene(N, W, H, seed=1234, device=dev, scale_lo=0.004 * args.scale_mult,
                             scale_hi=0.04 * args.scale_mult)
     params = {k: scene[k] for k in ("means", "scales", "quats", "opacities", "sh_coeffs", "uv0", "umap", "vmap", "texture")}
+    rgba = args.texture_layout == "rgba"
+    if rgba:  # the same texels at a 16-byte pitch: read and differentiated in place, no per-step padding passes
+        params["texture"] = torch.cat([scene["texture"], torch.zeros_like(scene["texture"][:, :1])], 1).contiguous()
     views = args.views or (1 if world == 1 else 64)
-    if views == 1:
-        cams = [(scene["viewmat"], scene["c2w"])]
-        workload = "C4: 1 view/step, front camera" + (f" (Gaussian scales x{args.scale_mult:g})" if args.scale_mult != 1.0 else "")
-    else:
-        cams = [(a.to(dev), b.to(dev)) for a, b in arc_cameras(views)]
-        workload = (f"C5: {views} views/step on a +-30 degree arc around the C4 camera, sharded over {world} GPU(s), "
-                    f"one NCCL all-reduce of the gradient arena per step")
-    mine = DataParallelTrainStep.shard(views, rank, world)
-    gen = torch.Generator().manual_seed(99)
-    targets_host = {}
-    for v in range(views):
-        t = torch.rand(H, W, 3, generator=gen)
-        if v in mine:
-            targets_host[v] = t.pin_memory()
-    targets = [targets_host[v].to(dev) if v in targets_host else None for v in range(views)]
 
+    def make_batch(nviews):
+        """cameras, host targets of this rank's shard, device targets, workload label"""
+        if nviews == 1:
+            cams = [(scene["viewmat"], scene["c2w"])]
+            label = "C4: 1 view/step, front camera" + (f" (Gaussian scales x{args.scale_mult:g})" if args.scale_mult != 1.0 else "")
+        else:
+            cams = [(a.to(dev), b.to(dev)) for a, b in arc_cameras(nviews)]
+            label = (f"C5: {nviews} views/step on a +-30 degree arc around the C4 camera, sharded over {world} GPU(s), "
+                     f"one NCCL all-reduce of the gradient arena per step")
+        mine = DataParallelTrainStep.shard(nviews, rank, world)
+        g2 = torch.Generator().manual_seed(99)
+        th = {}
+        for v in range(nviews):
+            t = torch.rand(H, W, 3, generator=g2)
+            if v in mine:
+                th[v] = t.pin_memory()
+        tg = [th[v].to(dev) if v in th else None for v in range(nviews)]
+        return cams, mine, th, tg, label
+
+    cams, mine, targets_host, targets, workload = make_batch(views)
     fused = FusedTrainStep(params, scene["texture_dims"], H, W, intrins=scene["intrins"], sh_degree=scene["sh_degree"],
-                           background=scene["background"], max_intersects=int(12 * N * max(1.0, args.scale_mult ** 2)))
+                           background=scene["background"], max_intersects=int(12 * N * max(1.0, args.scale_mult ** 2)),
+                           texture_rgba=rgba)
     dp = DataParallelTrainStep(fused, rank, world)
 
     def barrier():
@@ -261,39 +359,42 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up --------------------------------------------------------------------------------
-    sampler.wait_first()
-    barrier()
-    load_start = sampler.mark()
-    for _ in range(args.warmup):
-        dp.step(cams, targets)
-    barrier()
-    m_max = fused.check_overflow()
+    def timed_run(cams_, targets_, nviews, steps, warmup, per_kernel):
+        """W untimed steps, then exactly K steps between barrier + synchronize on both sides, CUDA events, max over ranks."""
+        barrier()
+        for _ in range(warmup):
+            dp.step(cams_, targets_)
+        barrier()
+        m_max_ = fused.check_overflow()
+        fused.time_kernels, fused.kernel_events = per_kernel, []
+        dp.time_collective, dp.collective_events = world > 1, []
+        launches0 = fused.launches
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss_ = dp.step(cams_, targets_)
+        e1.record()
+        barrier()
+        el = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        lc = torch.tensor([fused.launches - launches0], device=dev, dtype=torch.float64)
+        ar = [a.elapsed_time(b) for a, b in dp.collective_events]
+        arm = torch.tensor([sum(ar) / len(ar) if ar else 0.0], device=dev, dtype=torch.float64)
+        fused.time_kernels, dp.time_collective = False, False
+        if world > 1:
+            dist.all_reduce(el, op=dist.ReduceOp.MAX)
+            dist.all_reduce(lc, op=dist.ReduceOp.SUM)
+            dist.all_reduce(arm, op=dist.ReduceOp.MAX)
+        ms = float(el.item()) / steps
+        return dict(ms_per_step=ms, value=nviews * H * W / (ms * 1e-3) / 1e6, launches=int(lc.item()),
+                    loss=float(loss_.item()), m_max=m_max_, allreduce_ms=float(arm.item()) if world > 1 else None)
 
-    # ---- timed region: exactly K steps ----------------------------------------------------------------
-    fused.time_kernels = True
-    fused.kernel_events = []
-    launches0 = fused.launches
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        loss = dp.step(cams, targets)
-    e1.record()
-    barrier()
+    # ---- the headline run: W warm-up steps, exactly K timed steps ---------------------------------------------
+    sampler.wait_first()
+    load_start = sampler.mark()
+    head = timed_run(cams, targets, views, args.steps, args.warmup, True)
     clocks = sampler.stop(load_start)
-    elapsed_ms = e0.elapsed_time(e1)
-    launches = fused.launches - launches0
-    fused.time_kernels = False
-    el = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
-    lc = torch.tensor([launches], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(el, op=dist.ReduceOp.MAX)
-        dist.all_reduce(lc, op=dist.ReduceOp.SUM)
-    elapsed_ms = float(el.item())
-    ms_per_step = elapsed_ms / args.steps
-    value = views * H * W / (ms_per_step * 1e-3) / 1e6
-    loss_val = float(loss.item())
+    ms_per_step, value = head["ms_per_step"], head["value"]
 
     # per-kernel device time inside the timed region (CUDA events on the launching stream)
     ktime = {}
@@ -313,14 +414,17 @@ def main():
     dom_bytes = bytes_bwd if dom == "raster_backward" else bytes_fwd
     dom_ms = kavg.get(dom, float("nan"))
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms == dom_ms and dom_ms > 0 else None
-    traffic = None
+    traffic, traffic_src = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")) as f:
-            traffic = json.load(f).get(dom)
+            tj = json.load(f)
+            traffic = tj.get(dom)
+            traffic_src = "static: " + tj.get("_source", "profiles/dominant_kernel_traffic.json") + " - read from the committed capture, not measured in this run"
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_ms,
                 "share_of_step": (dom_ms * len(mine) / ms_per_step) if dom_ms == dom_ms else None,
                 "step": {"algorithmic_bytes_per_view": bytes_step,
@@ -328,10 +432,30 @@ def main():
                          "frac": bytes_step * len(mine) / (ms_per_step * 1e-3) / 1e9 / peak},
                 "kernel_ms": kavg}
 
+    # ---- N = 1: the 64-view C5 batch as well, so that the 1 -> 8 GPU curve is ONE workload --------------------------
+    scale_base = None
+    if world == 1 and views == 1 and not args.no_scale_base and args.scale_mult == 1.0:
+        c5 = make_batch(64)
+        sb = timed_run(c5[0], c5[3], 64, 3, 1, False)
+        scale_base = {"workload": c5[4], "views_per_step": 64, "steps": 3, "warmup": 1, "ms_per_step": sb["ms_per_step"],
+                      "value": sb["value"], "unit": UNIT, "max_intersections_seen": sb["m_max"],
+                      "note": "the N>1 lines of this bench run this 64-view batch (strong scaling); this is its 1-GPU point"}
+        del c5
+
     # ---- end to end through the public (reference-shaped) API, host buffers -------------------------------
     e2e = None
     if not args.no_e2e:
         e2e = run_e2e(args, scene, cams, mine, targets_host, dev, world, views)
+
+    # ---- the reference's own CUDA kernels beside it (N = 1, rank 0; reported comparison) ----------------------------
+    ref_cuda = None
+    if rank == 0 and world == 1 and views == 1 and not args.no_reference_cuda:
+        try:
+            ref_cuda = time_reference_cuda(scene, H, W)
+            if "ms_per_step" in ref_cuda:
+                ref_cuda["ours_over_reference"] = ref_cuda["ms_per_step"] / ms_per_step
+        except Exception as e:  # the comparison must never cost the bench line
+            ref_cuda = {"unavailable": f"{type(e).__name__}: {e}"}
 
     # ---- CPU baseline (oracle port) on a bounded crop, rank 0 at N=1 only -----------------------------------
     cpu = None
@@ -351,11 +475,13 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload, "gaussians": N, "sh_degree": 3, "texels_per_gaussian": 16,
-                       "texture_channels": 3, "width": W, "height": H, "views_per_step": views, "block_width": 16,
-                       "settings": 256, "intersections_last_view": M, "max_intersections_seen": m_max,
+                       "texture_channels": 3, "texture_layout": "(X,4) fp32: r, g, b at a 16-byte pitch" if rgba else "(X,3) fp32",
+                       "width": W, "height": H, "views_per_step": views, "block_width": 16,
+                       "settings": 256, "intersections_last_view": M, "max_intersections_seen": head["m_max"],
                        "l2": "inputs (0.9 GB of parameters, records and textures per view) are larger than the 126 MB L2",
-                       "loss": loss_val},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(lc.item()), "roofline": roofline, "cpu_baseline": cpu,
+                       "loss": head["loss"]},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": head["launches"], "roofline": roofline, "cpu_baseline": cpu,
+            "allreduce_ms": head["allreduce_ms"], "scale_base": scale_base, "reference_cuda": ref_cuda,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -377,6 +503,14 @@ def run_e2e(args, scene, cams, mine, targets_host, dev, world, views):
     H, W, bw, intr = args.height, args.width, 16, scene["intrins"]
     leaves = {k: scene[k].clone().requires_grad_(True) for k in
               ("means", "scales", "quats", "opacities", "sh_coeffs", "uv0", "umap", "vmap", "texture")}
+    # the leaves' gradients are views of ONE flat buffer (autograd accumulates into them in place), so that the
+    # data-parallel reduction is one collective, as in the fused step
+    flat = torch.zeros(sum(t.numel() for t in leaves.values()), device=dev)
+    off = 0
+    for t in leaves.values():
+        t.grad = flat[off:off + t.numel()].view_as(t)
+        off += t.numel()
+    cap = int(12 * args.points * max(1.0, args.scale_mult ** 2))
     cams_host = [(a.cpu().pin_memory(), b.cpu().pin_memory()) for a, b in cams]
     h2d = sum(targets_host[v].numel() * 4 + 2 * 64 for v in mine)
 
@@ -420,14 +554,13 @@ def run_e2e(args, scene, cams, mine, targets_host, dev, world, views):
             outs = texture_gaussians(scene["texture_info"], scene["texture_dims"], centers, extents, depths, nth, colors,
                                      leaves["opacities"], leaves["means"], leaves["scales"], 1.0, leaves["quats"],
                                      leaves["uv0"], leaves["umap"], leaves["vmap"], leaves["texture"], vm, c2w, *intr, H,
-                                     W, bw, 1 << 8, scene["background"])
+                                     W, bw, 1 << 8, scene["background"], max_intersects=cap)
             loss = image_loss(outs[4], outs[2], outs[5], gt)  # example.py:189-209, one kernel (csrc/loss.cu)
             loss.backward()
             loader.release()
             total = loss.detach() if total is None else total + loss.detach()
         if world > 1:
-            for t in leaves.values():
-                dist.all_reduce(t.grad)
+            dist.all_reduce(flat)
         # device -> host read of the step's result, every step: an asynchronous copy into pinned memory that is
         # consumed one step later, so that reading the loss of step k does not drain the queue before step k+1 is
         # enqueued (the usual way a training loop logs its loss); read_pending() collects the last one
@@ -436,11 +569,10 @@ def run_e2e(args, scene, cams, mine, targets_host, dev, world, views):
         loss_ready[k].record()
         val = read_pending()
         state["pending"], state["k"] = k, state["k"] + 1
-        for t in leaves.values():
-            t.grad = None
+        flat.zero_()
         return val
 
-    steps = max(3, min(args.steps, 10 if views == 1 else 3))
+    steps = max(3, min(args.steps, 10))
     loader_steps = [0]
     for _ in range(2):
         one_step()
@@ -467,7 +599,8 @@ def run_e2e(args, scene, cams, mine, targets_host, dev, world, views):
     ms = float(ms.item())
     return {"value": views * H * W / (ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
             "d2h_bytes_per_step": 4, "ms_per_step": ms, "steps": steps,
-            "api": "spherical_harmonics_colors + project_points + get_aabb_2d + get_num_tiles_hit_2d + texture_gaussians + "
+            "api": "spherical_harmonics_colors + project_points + get_aabb_2d + get_num_tiles_hit_2d + texture_gaussians "
+                   "(max_intersects capacity: no host sync per call) + "
                    "image_loss (the example.py loss), all autograd ops of the package; inputs staged by gstex_cuda_b200.prefetch.ViewPrefetcher "
                    "(pinned host -> device on a copy stream, one view ahead); the loss of every step is read back through "
                    "an asynchronous copy into pinned memory, consumed one step later",

@@ -21,9 +21,15 @@ def texture_gaussians(texture_info: Tuple[int, int, int], texture_dims: Tensor, 
                       scales: Tensor, glob_scale, quats: Tensor, uv0: Tensor, umap: Tensor, vmap: Tensor,
                       texture: Tensor, viewmat: Tensor, c2w: Tensor, fx: float, fy: float, cx: float, cy: float,
                       img_height: int, img_width: int, block_width: int, settings: int,
-                      background: Optional[Tensor] = None, use_torch_impl: bool = False):
+                      background: Optional[Tensor] = None, use_torch_impl: bool = False,
+                      max_intersects: Optional[int] = None):
     """Rasterise textured 2D Gaussians; differentiable w.r.t. colors, opacity, means, scales, quats, uv0,
-    umap, vmap and texture.  Arguments, defaults and outputs as in the reference (texture.py:14-150)."""
+    umap, vmap and texture.  Arguments, defaults and outputs as in the reference (texture.py:14-150).
+
+    ``max_intersects`` (extension, opt-in): a capacity for the sorted intersection list.  The reference synchronises
+    the host once per call to read the intersection count (``cum_tiles_hit[-1].item()``, utils.py:58) because its
+    buffers are sized by it; with a capacity the count stays on the device and the call never waits for the GPU.
+    Intersections beyond the capacity are dropped: ``last_intersect_count()`` returns the count of the last call."""
     assert block_width > 1 and block_width <= 16, "block_width must be between 2 and 16"
     if colors.dtype == torch.uint8:
         colors = colors.float() / 255
@@ -42,7 +48,18 @@ def texture_gaussians(texture_info: Tuple[int, int, int], texture_dims: Tensor, 
         num_tiles_hit.contiguous(), colors.contiguous(), opacity.contiguous(), means.contiguous(), scales.contiguous(),
         glob_scale, quats.contiguous(), uv0.contiguous(), umap.contiguous(), vmap.contiguous(), texture.contiguous(),
         viewmat.contiguous(), c2w.contiguous(), fx, fy, cx, cy, img_height, img_width, block_width, settings,
-        background.contiguous())
+        background.contiguous(), None if max_intersects is None else int(max_intersects))
+
+
+_LAST_COUNT = {}
+
+
+def last_intersect_count(device=None) -> int:
+    """Intersection count of the last ``texture_gaussians(..., max_intersects=...)`` call on the device (synchronises).
+    Compare it with the capacity passed: a larger count means intersections were dropped."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    t = _LAST_COUNT.get(dev.index if dev.index is not None else torch.cuda.current_device())
+    return -1 if t is None else int(t.item())
 
 
 def _p(t) -> int:
@@ -60,7 +77,7 @@ class _TextureGaussians(Function):
     @staticmethod
     def forward(ctx, texture_info, texture_dims, centers, extents, depths, num_tiles_hit, colors, opacity, means,
                 scales, glob_scale, quats, uv0, umap, vmap, texture, viewmat, c2w, fx, fy, cx, cy, img_height,
-                img_width, block_width, settings, background):
+                img_width, block_width, settings, background, max_intersects=None):
         lib = _lib.load()
         H, W, bw = int(img_height), int(img_width), int(block_width)
         tile_bounds = ((W + bw - 1) // bw, (H + bw - 1) // bw, 1)
@@ -78,7 +95,7 @@ class _TextureGaussians(Function):
         with torch.cuda.device(dev):
             # 1. inclusive scan of the tile counts; its last element starts travelling to the host
             count_host, count_ready = None, None
-            if n > 0:
+            if n > 0 and max_intersects is None:
                 cum = cumsum_i32(num_tiles_hit.reshape(-1))
                 count_host = torch.empty((1,), dtype=torch.int32, pin_memory=True)
                 count_host.copy_(cum[-1:], non_blocking=True)
@@ -102,6 +119,8 @@ class _TextureGaussians(Function):
             if count_ready is not None:
                 count_ready.synchronize()
                 num_intersects = int(count_host[0])
+        if max_intersects is not None:
+            num_intersects = max(int(max_intersects), 1)  # a capacity: the true count stays on the device
         ctx.num_intersects = num_intersects
         if num_intersects < 1:
             # upstream leaves several outputs undefined in this branch (texture.py:197-205, :254-289);
@@ -112,7 +131,9 @@ class _TextureGaussians(Function):
             return (out_img, zeros, zeros.clone(), zeros.clone(), torch.zeros(H, W, C, **f32), torch.zeros(H, W, 3, **f32))
         # 4. same gaussian_ids_sorted / tile_bins as bin_and_sort_gaussians (utils.py:106-162 upstream), from the fused
         #    bucket-by-tile + per-tile sort (csrc/binning_tiles.cu) instead of the global 64-bit key sort
-        gaussian_ids_sorted, tile_bins, _, _ = bin_tiles(centers, extents, depths, tile_bounds, bw, num_intersects)
+        gaussian_ids_sorted, tile_bins, count_dev, _ = bin_tiles(centers, extents, depths, tile_bounds, bw, num_intersects)
+        if max_intersects is not None:
+            _LAST_COUNT[dev.index] = count_dev
         # blend masks: forward -> backward (csrc/raster.cuh); not kept (nor zero-filled) for an inference-only call
         need_grad = any(ctx.needs_input_grad)
         masks = torch.empty((num_intersects, 8), **i32) if need_grad else None
@@ -122,7 +143,7 @@ class _TextureGaussians(Function):
                                           _p(mean2d), _p(tex), _p(viewmat), _p(c2w), fx, fy, cx, cy, _p(background),
                                           _p(out_img), _p(out_depth), _p(out_reg), _p(out_texture), _p(out_normal),
                                           _p(final_Ts), _p(final_idx), _p(depth_idx), _p(out_reg_s), _p(masks),
-                                          num_intersects, 0, s)
+                                          num_intersects, _p(count_dev) if max_intersects is not None else 0, s)
         _lib.check(rc, "raster_forward")
         ctx.img_width, ctx.img_height, ctx.block_width = W, H, bw
         ctx.texture_info, ctx.settings, ctx.glob_scale = texture_info, int(settings), float(glob_scale)
@@ -135,7 +156,7 @@ class _TextureGaussians(Function):
 
     @staticmethod
     def backward(ctx, v_out_img, v_out_depth, v_out_reg, v_out_alpha, v_out_texture, v_out_normal):
-        none18 = [None] * 27
+        none18 = [None] * 28
         if ctx.num_intersects < 1:
             colors, opacity, means, scales, quats, uv0, umap, vmap, texture = ctx.saved_tensors
             grads = [torch.zeros_like(t) for t in (colors, opacity, means, scales, quats, uv0, umap, vmap, texture)]

@@ -51,7 +51,7 @@ def test_gpu_arm_prints_one_contract_line():
     d = json.loads(lines[0])
     assert d["n_gpus"] == 1 and d["steps"] == 3 and d["warmup"] == 3 and d["unit"] == "Mpixel/s" and d["value"] > 0
     assert d["scaling"] in ("weak", "strong") and d["vs_baseline"] is None and d["dtype"] == "f32"
-    assert d["gpu_launches"] >= 3 * 15  # every step launches the ~17 kernels of the path
+    assert d["gpu_launches"] >= 3 * 13  # every step launches the ~14 kernels of the path
     e = d["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] >= 320 * 192 * 3 * 4 and e["d2h_bytes_per_step"] == 4
     assert e["h2d_bytes_measured_per_step"] == e["h2d_bytes_per_step"]
@@ -62,3 +62,9 @@ def test_gpu_arm_prints_one_contract_line():
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] > 0
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
     assert "workload" in d["config"] and "l2" in d["config"]
+    # the 1-GPU point of the scaling workload and the reference's own CUDA kernels beside our path
+    sb = d["scale_base"]
+    assert sb["views_per_step"] == 64 and sb["value"] > 0 and sb["ms_per_step"] > 0
+    rc = d["reference_cuda"]
+    assert rc is not None and ("unavailable" in rc or (rc["ms_per_step"] > 0 and rc["ms"]["raster_bwd"] > 0))
+    assert d["allreduce_ms"] is None and "traffic_source" in rf
