@@ -60,7 +60,7 @@ _PROTOS = {
     "gstex_raster_forward": (c_i, [c_i] * 5 + [c_fp] * 7 + [c_f] * 4 + [c_fp] * 10 + [c_fp, c_i64, c_fp] + [c_fp]),
     "gstex_raster_masks": (c_i, [c_i] * 4 + [c_fp] * 6 + [c_f] * 4 + [c_fp] * 3 + [c_i64, c_fp] + [c_fp]),
     "gstex_raster_backward": (c_i, [c_i] * 5 + [c_fp] * 7 + [c_f] * 4 + [c_fp] * 11 + [c_fp, c_fp, c_fp] + [c_fp]),
-    "gstex_raster_epilogue": (c_i, [c_i, c_fp, c_fp, c_f] + [c_fp] * 5 + [c_f] * 4 + [c_fp] * 9 + [c_i, c_fp]),
+    "gstex_raster_epilogue": (c_i, [c_i, c_fp, c_fp, c_f] + [c_fp] * 5 + [c_f] * 4 + [c_fp] * 10 + [c_i, c_fp]),
     "gstex_sh_colors_forward": (c_i, [c_i, c_i, c_i] + [c_fp] * 5 + [c_fp]),
     "gstex_sh_colors_backward": (c_i, [c_i, c_i, c_i] + [c_fp] * 5 + [c_i, c_fp]),
     "gstex_preprocess_forward": (c_i, [c_i] + [c_fp] * 12 + [c_fp]),
@@ -92,7 +92,7 @@ def load() -> C.CDLL:
         if not os.path.exists(LIB_PATH):
             from .build import build  # builds with nvcc; raises with the compiler output on failure
 
-            build()
+            build()  # takes an inter-process lock: the ranks of a torchrun launch must not compile into the same files
         lib = C.CDLL(LIB_PATH)
         for name, (res, args) in _PROTOS.items():
             try:

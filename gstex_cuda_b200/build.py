@@ -41,10 +41,26 @@ def _deps_mtime() -> float:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    """Compile and link in-tree.  Safe to call from several processes at once (all ranks of a torchrun launch import the
+    package together): an exclusive file lock serialises them, the library is linked under a temporary name and renamed
+    into place, and whoever gets the lock second finds the library up to date."""
+    import fcntl
+
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _deps_mtime():
         return LIB
     os.makedirs(BUILD, exist_ok=True)
+    with open(os.path.join(BUILD, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force: bool, verbose: bool) -> str:
+    srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _deps_mtime():
+        return LIB
     nvcc = _nvcc()
     hdr_mtime = max(os.path.getmtime(os.path.join(CSRC, f)) for f in os.listdir(CSRC) if f.endswith(".cuh"))
     hdr_mtime = max(hdr_mtime, os.path.getmtime(os.path.join(os.path.dirname(HERE), "include", "gstex_b200.h")))
@@ -65,14 +81,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = [o for o, _ in results]
     log = "".join(l for _, l in results)
     if log:
-        with open(os.path.join(BUILD, "ptxas.log"), "a") as f:
+        with open(os.path.join(BUILD, "ptxas.log"), "w") as f:  # the log of the LAST build (git-ignored)
             f.write(log)
         if verbose:
             print(log)
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    tmp = LIB + f".tmp{os.getpid()}"
+    cmd = [nvcc, "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, LIB)  # atomic: no process ever dlopens a half-written library
     return LIB
 
 

@@ -66,6 +66,8 @@ __device__ __forceinline__ Vec3 form_vector(const SurfelFrame &f, Vec3 a, float 
 #ifndef GSTEX_PACK_MINB
 #define GSTEX_PACK_MINB 1
 #endif
+// |c3| below which a surfel counts as grazing (its normal within ~3 degrees of perpendicular to the centre ray)
+constexpr float GRAZING_C3 = 0.05f;
 __global__ void __launch_bounds__(256, GSTEX_PACK_MINB) pack_kernel(int n, const float *__restrict__ means,
                                                    const float *__restrict__ scales, float glob_scale,
                                                    const float4 *__restrict__ quats,
@@ -99,13 +101,62 @@ __global__ void __launch_bounds__(256, GSTEX_PACK_MINB) pack_kernel(int n, const
     const float c3 = dot3(h3, f.rc);
     const float2 t0 = uv0[g];
     float4 *r = recs + (size_t)g * 8;
-    r[0] = make_float4(fmaf(fx, f.rc.x, cx), fmaf(fy, f.rc.y, cy), f.c0, opacities[g]);
-    r[1] = make_float4(f.k1 * h1.x * ifx, f.k1 * h1.y * ify, c1, c3);
-    r[2] = make_float4(f.k2 * h2.x * ifx, f.k2 * h2.y * ify, c2, __int_as_float(g));
-    r[3] = make_float4(h3.x * ifx, h3.y * ify, __int_as_float(texture_dims[3 * g]),
-                       __int_as_float(texture_dims[3 * g + 1]));
-    r[4] = make_float4(hu.x * ifx, hu.y * ify, cu, t0.x);
-    r[5] = make_float4(hv.x * ifx, hv.y * ify, cv, t0.y);
+    const float xc = fmaf(fx, f.rc.x, cx), yc = fmaf(fy, f.rc.y, cy);
+    float4 r0 = make_float4(xc, yc, f.c0, opacities[g]);
+    float4 r1 = make_float4(f.k1 * h1.x * ifx, f.k1 * h1.y * ify, c1, c3);
+    float4 r2 = make_float4(f.k2 * h2.x * ifx, f.k2 * h2.y * ify, c2, __int_as_float(g));
+    float4 r3 = make_float4(h3.x * ifx, h3.y * ify, __int_as_float(texture_dims[3 * g]),
+                            __int_as_float(texture_dims[3 * g + 1]));
+    float4 r4 = make_float4(hu.x * ifx, hu.y * ify, cu, t0.x);
+    float4 r5 = make_float4(hv.x * ifx, hv.y * ify, cv, t0.y);
+    // Grazing surfels.  c3 = a3 . R(centre ray) is the cosine-like plane denominator at the Gaussian's centre: a sum of
+    // O(1) products, so its fp32 value carries ~1e-7 ABSOLUTE error - a relative error of 1e-7 / |c3| that every 1/D and
+    // 1/D^2 factor of the pair evaluation and its gradients inherits (the reference's dot(ray, ax3), texture_helpers.cuh:
+    // 302-313, has the same conditioning; at |c3| ~ 1e-3 either evaluation is only good to 1e-4).  For the few surfels seen
+    // nearly edge-on the form coefficients are therefore recomputed in double, with the constants evaluated at the
+    // ROUNDED expansion centre (xc, yc) the kernels subtract from the pixel - so that N(p) = c + P.(p - centre) holds to
+    // fp32 rounding of the result instead of to fp32 rounding of its O(1) terms.
+    if (fabsf(c3) < GRAZING_C3) {
+        const double qw = quats[g].x, qx = quats[g].y, qy = quats[g].z, qz = quats[g].w;
+        const double a1[3] = {1.0 - 2.0 * (qy * qy + qz * qz), 2.0 * (qx * qy + qw * qz), 2.0 * (qx * qz - qw * qy)};
+        const double a2[3] = {2.0 * (qx * qy - qw * qz), 1.0 - 2.0 * (qx * qx + qz * qz), 2.0 * (qy * qz + qw * qx)};
+        const double a3[3] = {2.0 * (qx * qz + qw * qy), 2.0 * (qy * qz - qw * qx), 1.0 - 2.0 * (qx * qx + qy * qy)};
+        const double um[3] = {(double)umap[3 * g], (double)umap[3 * g + 1], (double)umap[3 * g + 2]};
+        const double vm[3] = {(double)vmap[3 * g], (double)vmap[3 * g + 1], (double)vmap[3 * g + 2]};
+        const double d[3] = {(double)mean.x - (double)cam.o.x, (double)mean.y - (double)cam.o.y, (double)mean.z - (double)cam.o.z};
+        auto dotd = [](const double *a, const double *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; };
+        const double c0d = dotd(a3, d);
+        // centre ray through the rounded expansion centre, camera frame
+        const double rr[3] = {((double)xc - (double)cx) / (double)fx, ((double)yc - (double)cy) / (double)fy, 1.0};
+        // h = Rc^T (c0 a - (a.d) a3): coefficients of the linear form in the camera-frame ray; h3 = Rc^T a3
+        auto form = [&](const double *a, double kappa, bool plane, float &px, float &py, float &c) {
+            double w[3];
+            const double b = plane ? 0.0 : dotd(a, d);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) w[k] = plane ? a[k] : c0d * a[k] - b * a3[k];
+            double h[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                h[k] = (double)cam.Rc[k] * w[0] + (double)cam.Rc[4 + k] * w[1] + (double)cam.Rc[8 + k] * w[2];
+            px = (float)(kappa * h[0] / (double)fx);
+            py = (float)(kappa * h[1] / (double)fy);
+            c = (float)(kappa * dotd(h, rr));
+        };
+        const double k1d = (double)K_SIGMA / ((double)scales[3 * g] * (double)glob_scale);
+        const double k2d = (double)K_SIGMA / ((double)scales[3 * g + 1] * (double)glob_scale);
+        r0.z = (float)c0d;
+        form(a1, k1d, false, r1.x, r1.y, r1.z);
+        form(a2, k2d, false, r2.x, r2.y, r2.z);
+        form(a3, 1.0, true, r3.x, r3.y, r1.w);
+        form(um, 1.0, false, r4.x, r4.y, r4.z);
+        form(vm, 1.0, false, r5.x, r5.y, r5.z);
+    }
+    r[0] = r0;
+    r[1] = r1;
+    r[2] = r2;
+    r[3] = r3;
+    r[4] = r4;
+    r[5] = r5;
     // colours are optional: texture_edit walks the same records without them
     const Vec3 col = colors ? ld3(colors + 3 * g) : mk3(0.f, 0.f, 0.f);
     r[6] = make_float4(col.x, col.y, col.z, __int_as_float(texture_dims[3 * g + 2]));
@@ -123,7 +174,8 @@ __global__ void __launch_bounds__(256, GSTEX_EPI_MINB) epilogue_kernel(
     int n, const float *__restrict__ means, const float *__restrict__ scales, float glob_scale,
     const float4 *__restrict__ quats, const float *__restrict__ umap, const float *__restrict__ vmap,
     const float *__restrict__ viewmat, const float *__restrict__ c2w, float fx, float fy, float cx, float cy,
-    const float4 *__restrict__ acc, float *__restrict__ v_colors, float *__restrict__ v_opacity,
+    const float4 *__restrict__ acc, const float4 *__restrict__ recs, float *__restrict__ v_colors,
+    float *__restrict__ v_opacity,
     float *__restrict__ v_means, float *__restrict__ v_scales, float4 *__restrict__ v_quats,
     float2 *__restrict__ v_uv0, float *__restrict__ v_umap, float *__restrict__ v_vmap, int accumulate_flags) {
     const int accumulate = accumulate_flags & 1, accumulate_colors = (accumulate_flags >> 1) & 1;
@@ -173,11 +225,20 @@ __global__ void __launch_bounds__(256, GSTEX_EPI_MINB) epilogue_kernel(
         const Vec3 v_pv = mk3(gx * rw, gy * rw, -(gx * pv.x + gy * pv.y) * rw * rw);
         v_d = add3(v_d, rot_apply_t(cam.vm, v_pv));
     }
-    // scales: kappa_i = K/(s_i*glob)  =>  dL/ds_i = -(F_i . G_i)/s_i with F_i the record's form coefficients
-    const Vec3 h1 = form_vector(f, f.a1, f.b1, cam), h2 = form_vector(f, f.a2, f.b2, cam);
-    const float c1 = f.exact ? 0.f : f.k1 * dot3(h1, f.rc), c2 = f.exact ? 0.f : f.k2 * dot3(h2, f.rc);
-    const float fg1 = fmaf(f.k1 * h1.x * ifx, q0.x, fmaf(f.k1 * h1.y * ify, q0.y, c1 * q0.z));
-    const float fg2 = fmaf(f.k2 * h2.x * ifx, q1.x, fmaf(f.k2 * h2.y * ify, q1.y, c2 * q1.z));
+    // scales: kappa_i = K/(s_i*glob)  =>  dL/ds_i = -(F_i . G_i)/s_i with F_i the record's form coefficients - read back
+    // from the record the rasterisers used when the caller has it (for grazing surfels pack_kernel computes them in
+    // double; F . G = sum over pairs of g * N is a sum of small N's there, and must use the same coefficients)
+    float fg1, fg2;
+    if (recs) {
+        const float4 F1 = recs[(size_t)g * 8 + 1], F2 = recs[(size_t)g * 8 + 2];
+        fg1 = fmaf(F1.x, q0.x, fmaf(F1.y, q0.y, F1.z * q0.z));
+        fg2 = fmaf(F2.x, q1.x, fmaf(F2.y, q1.y, F2.z * q1.z));
+    } else {
+        const Vec3 h1 = form_vector(f, f.a1, f.b1, cam), h2 = form_vector(f, f.a2, f.b2, cam);
+        const float c1 = f.exact ? 0.f : f.k1 * dot3(h1, f.rc), c2 = f.exact ? 0.f : f.k2 * dot3(h2, f.rc);
+        fg1 = fmaf(f.k1 * h1.x * ifx, q0.x, fmaf(f.k1 * h1.y * ify, q0.y, c1 * q0.z));
+        fg2 = fmaf(f.k2 * h2.x * ifx, q1.x, fmaf(f.k2 * h2.y * ify, q1.y, c2 * q1.z));
+    }
     const float4 vq = surfel_axes_vjp(quat, v_a1, v_a2, v_a3);
 
     put(&v_means[3 * g + 0], v_d.x, accumulate);
@@ -237,10 +298,10 @@ int launch_epilogue(int n, const float *means, const float *scales, float glob_s
                     const float *umap, const float *vmap, const float *viewmat, const float *c2w, float fx, float fy,
                     float cx, float cy, const float4 *acc, float *v_colors, float *v_opacity, float *v_means,
                     float *v_scales, float *v_quats, float *v_uv0, float *v_umap, float *v_vmap, int accumulate,
-                    cudaStream_t s) {
+                    cudaStream_t s, const float4 *recs) {
     if (n == 0) return GSTEX_OK;
     epilogue_kernel<<<ceil_div(n, 256), 256, 0, s>>>(n, means, scales, glob_scale, (const float4 *)quats, umap, vmap,
-                                                     viewmat, c2w, fx, fy, cx, cy, acc, v_colors, v_opacity, v_means,
+                                                     viewmat, c2w, fx, fy, cx, cy, acc, recs, v_colors, v_opacity, v_means,
                                                      v_scales, (float4 *)v_quats, (float2 *)v_uv0, v_umap, v_vmap,
                                                      accumulate);
     GSTEX_LAUNCH_OK("epilogue_kernel");

@@ -94,11 +94,11 @@ extern "C" int gstex_raster_backward(int img_height, int img_width, int block_wi
 extern "C" int gstex_raster_epilogue(int n, const float *means, const float *scales, float glob_scale,
                                      const float *quats, const float *umap, const float *vmap, const float *viewmat,
                                      const float *c2w, float fx, float fy, float cx, float cy, const float *acc,
-                                     float *v_colors, float *v_opacity, float *v_means, float *v_scales,
+                                     const float *recs, float *v_colors, float *v_opacity, float *v_means, float *v_scales,
                                      float *v_quats, float *v_uv0, float *v_umap, float *v_vmap, int accumulate,
                                      gstex_stream_t stream) {
     GSTEX_REQUIRE(n >= 0, GSTEX_E_INVALID, "raster_epilogue: n = %d", n);
     return launch_epilogue(n, means, scales, glob_scale, quats, umap, vmap, viewmat, c2w, fx, fy, cx, cy,
                            (const float4 *)acc, v_colors, v_opacity, v_means, v_scales, v_quats, v_uv0, v_umap, v_vmap,
-                           accumulate, as_stream(stream));
+                           accumulate, as_stream(stream), (const float4 *)recs);
 }

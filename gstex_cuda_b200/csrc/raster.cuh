@@ -319,7 +319,7 @@ int launch_epilogue(int n, const float *means, const float *scales, float glob_s
                     const float *umap, const float *vmap, const float *viewmat, const float *c2w, float fx, float fy,
                     float cx, float cy, const float4 *acc, float *v_colors, float *v_opacity, float *v_means,
                     float *v_scales, float *v_quats, float *v_uv0, float *v_umap, float *v_vmap, int accumulate,
-                    cudaStream_t s);  // accumulate: 0 / 1 = overwrite / add everything; see gstex_raster_epilogue for bit 1
+                    cudaStream_t s, const float4 *recs = nullptr);  // accumulate: see gstex_raster_epilogue; recs: the view's records
 int launch_pad_texture(int64_t num_texels, const float *tex, float4 *tex4, cudaStream_t s);
 int launch_unpad_texture_grad(int64_t num_texels, const float4 *g4, float *v_texture, int accumulate, cudaStream_t s);
 FwdLayout forward_layout(int n, int64_t num_texels, int channels, int64_t num_intersects);

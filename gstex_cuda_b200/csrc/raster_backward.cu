@@ -638,7 +638,7 @@ extern "C" int gstex_texture_backward(
         if (rc != GSTEX_OK) return rc;
     }
     rc = launch_epilogue(n, means, scales, glob_scale, quats, umap, vmap, viewmat, c2w, fx, fy, cx, cy, acc, v_colors,
-                         v_opacity, v_means, v_scales, v_quats, v_uv0, v_umap, v_vmap, accumulate, s);
+                         v_opacity, v_means, v_scales, v_quats, v_uv0, v_umap, v_vmap, accumulate, s, p.recs);
     if (rc != GSTEX_OK) return rc;
     if (channels == 3) {
         rc = launch_unpad_texture_grad(num_texels, vtex4, v_texture, accumulate, s);

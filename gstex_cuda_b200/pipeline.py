@@ -313,7 +313,7 @@ class FusedTrainStep:
         acc_flag = 0 if first else (1 if self.use_sh else 3)
         self._ck(lib.gstex_raster_epilogue(self.n, P(p["means"]), P(p["scales"]), self.glob_scale, P(p["quats"]),
                                            P(p["umap"]), P(p["vmap"]), P(viewmat), P(c2w), fx, fy, cx, cy, P(v.acc),
-                                           P(v.v_colors), P(g["v_opacity"]), P(g["v_means"]), P(g["v_scales"]),
+                                           P(v.recs), P(v.v_colors), P(g["v_opacity"]), P(g["v_means"]), P(g["v_scales"]),
                                            P(g["v_quats"]), P(g["v_uv0"]), P(g["v_umap"]), P(g["v_vmap"]), acc_flag, s),
                  "raster_epilogue")
         if self.use_sh:

@@ -201,7 +201,7 @@ class _TextureGaussians(Function):
                                                _p(vtex), s)
                 _lib.check(rc, "raster_backward")
                 rc = lib.gstex_raster_epilogue(n, _p(means), _p(scales), ctx.glob_scale, _p(quats), _p(umap), _p(vmap),
-                                               _p(viewmat), _p(c2w), fx, fy, cx, cy, _p(acc), _p(v_colors), _p(v_opacity),
+                                               _p(viewmat), _p(c2w), fx, fy, cx, cy, _p(acc), _p(recs), _p(v_colors), _p(v_opacity),
                                                _p(v_means), _p(v_scales), _p(v_quats), _p(v_uv0), _p(v_umap), _p(v_vmap),
                                                0, s)
                 _lib.check(rc, "raster_epilogue")

@@ -282,9 +282,11 @@ int gstex_raster_backward(int img_height, int img_width, int block_width, int ch
                           const uint32_t *masks, float *acc, float *vtex, gstex_stream_t stream);
 int gstex_raster_epilogue(int n, const float *means, const float *scales, float glob_scale, const float *quats,
                           const float *umap, const float *vmap, const float *viewmat, const float *c2w, float fx,
-                          float fy, float cx, float cy, const float *acc, float *v_colors, float *v_opacity,
-                          float *v_means, float *v_scales, float *v_quats, float *v_uv0, float *v_umap,
-                          float *v_vmap, int accumulate, gstex_stream_t stream);
+                          float fy, float cx, float cy, const float *acc, const float *recs, float *v_colors,
+                          float *v_opacity, float *v_means, float *v_scales, float *v_quats, float *v_uv0,
+                          float *v_umap, float *v_vmap, int accumulate, gstex_stream_t stream);
+/* recs (may be NULL): the records gstex_pack_records wrote for this view; the scale gradients then use the very form
+ * coefficients the rasterisers used (they are computed in double for grazing surfels). */
 /* accumulate bit 0: add to the geometry gradients (means ... vmap, opacity) instead of overwriting them; bit 1: the same
  * for v_colors alone (per-view colour gradients that feed an SH backward are overwritten while the rest accumulates). */
 

@@ -60,11 +60,11 @@ def test_baseline_config_vs_oracle(name, N, H, W, num_texels, texdim):
     g_c = backward_cuda(s, ids, bins, f_c, vout, scratch=scratch)
     g_o = backward_oracle(s, to_np(ids), to_np(bins), f_c, vout)
     # example.py draws uniformly random orientations, so at 10 000 Gaussians a few surfels are seen edge-on (C3: Gaussian
-    # 950 has cos(normal, ray) = 0.0015).  Their plane denominator is a difference of O(1) terms and every fp32
-    # evaluation of it - the reference kernel's dot(ray, ax3), the oracle's, the affine form here - carries ~1e-4
-    # relative error that the 1/D^2 factors of the quaternion / mean gradients amplify: measured on this scene, the
-    # oracle differs from the reference CUDA kernel by 2.1 % of max|g| on such entries and this path by 7 %, on
-    # 3e-4 of the entries.  The number of outliers keeps its bound; their size is bounded at 15 % of max|g| for C3.
+    # 950 has cos(normal, ray) = 0.0015).  Their plane denominator is a difference of O(1) terms: an fp32 evaluation of
+    # it - the reference kernel's dot(ray, ax3), the oracle's - carries ~1e-4 relative error that the 1/D^2 factors of the
+    # quaternion / mean gradients amplify (the oracle differs from the reference CUDA kernel by 2.1 % of max|g| on such
+    # entries).  Here the form coefficients of grazing surfels are computed in double (csrc/pack.cu), so what remains is
+    # the oracle's own noise: the standard outlier bound applies to C3 like to every other case.
     uv_keys = ("v_uv0", "v_umap", "v_vmap")
     if texdim == 1:
         # 1x1 textures: all four bilinear corners are the same texel, so d(out)/d(uv) vanishes identically; both sides
@@ -73,4 +73,4 @@ def test_baseline_config_vs_oracle(name, N, H, W, num_texels, texdim):
             assert float(g_c[k].abs().max()) <= 1e-4 and float(abs(g_o[k]).max()) <= 1e-4
         g_c = {k: (torch.zeros_like(v) if k in uv_keys else v) for k, v in g_c.items()}
         g_o = {k: (0 * v if k in uv_keys else v) for k, v in g_o.items()}
-    compare_backward(g_c, g_o, max_bad_frac=2e-3, outlier_bound=0.15 if name == "C3" else 0.05)
+    compare_backward(g_c, g_o, max_bad_frac=2e-3, outlier_bound=0.05)

@@ -30,11 +30,11 @@ fi
 if has variants; then bash tools/gpu_variants.sh; fi
 if has ncu; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
-      --log-file gpurun_out/launches_$tag.csv python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline \
+      --log-file gpurun_out/launches_$tag.csv python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --no-scale-base --no-reference-cuda \
       > gpurun_out/ncu_launch_$tag.log 2>&1
   echo "== ncu launches exit=$?" | tee -a gpurun_out/summary.txt
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:raster_ -s 2 -c 2 \
-      -f -o gpurun_out/prof_raster_$tag python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline \
+      -f -o gpurun_out/prof_raster_$tag python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --no-scale-base --no-reference-cuda \
       > gpurun_out/ncu_full_$tag.log 2>&1
   echo "== ncu full exit=$?" | tee -a gpurun_out/summary.txt
 fi

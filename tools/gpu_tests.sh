@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/smi.txt 2>&1
 nproc > gpurun_out/nproc.txt
 rc_all=0
-for f in ${@:-tests/test_gpu_sh_sample.py tests/test_gpu_binning.py tests/test_gpu_raster.py tests/test_gpu_api.py tests/test_gpu_pipeline.py tests/test_gpu_vs_reference_cuda.py tests/test_gpu_texture_edit.py tests/test_gpu_train_ops.py tests/test_gpu_full_size.py tests/test_gpu_baseline_configs.py}; do
+for f in ${@:-tests/test_gpu_reference_python.py tests/test_gpu_sh_sample.py tests/test_gpu_binning.py tests/test_gpu_raster.py tests/test_gpu_api.py tests/test_gpu_pipeline.py tests/test_gpu_vs_reference_cuda.py tests/test_gpu_texture_edit.py tests/test_gpu_train_ops.py tests/test_gpu_full_size.py tests/test_gpu_baseline_configs.py}; do
   name=$(basename $f .py)
   timeout 900 python -m pytest $f -m gpu -q -s --timeout 600 > gpurun_out/$name.log 2>&1
   rc=$?

@@ -7,7 +7,7 @@ for so in /tmp/lib_prod.so experiments/_variants/lib_*.so; do
   cp $so gstex_cuda_b200/libgstex_b200.so
   n=$(basename $so .so)
   if [[ "$1" == test ]]; then timeout 300 python -m pytest tests/test_gpu_raster.py tests/test_gpu_vs_reference_cuda.py -m gpu -q -x 2>&1 | tail -1; fi
-  timeout 300 python bench.py --steps 20 --warmup 5 --no-e2e --no-cpu-baseline > gpurun_out/var_$n.json 2> gpurun_out/var_$n.err
+  timeout 300 python bench.py --steps 20 --warmup 5 --no-e2e --no-cpu-baseline --no-scale-base --no-reference-cuda > gpurun_out/var_$n.json 2> gpurun_out/var_$n.err
   python - "$n" <<'P'
 import json,sys
 n=sys.argv[1]
