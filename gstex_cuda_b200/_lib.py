@@ -28,7 +28,7 @@ _PROTOS = {
     "gstex_num_tiles_hit_2d": (c_i, [c_i, c_fp, c_fp, c_i, c_i, c_i, c_fp, c_fp]),
     "gstex_project_points": (c_i, [c_i, c_fp, c_fp, c_f, c_f, c_f, c_f, c_fp, c_fp, c_fp]),
     "gstex_project_aabb_count": (c_i, [c_i, c_fp, c_fp, c_f, c_fp, c_fp, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_fp,
-                                       c_fp, c_fp, c_fp, c_fp]),
+                                       c_fp, c_fp, c_fp, c_fp, c_fp]),
     "gstex_scan_temp_bytes": (c_sz, [c_i]),
     "gstex_cumsum_i32": (c_i, [c_i, c_fp, c_fp, c_fp, c_sz, c_fp]),
     "gstex_map_gaussian_to_intersects": (c_i, [c_i, c_i64, c_fp, c_fp, c_fp, c_fp, c_i, c_i, c_i, c_fp, c_fp, c_fp]),
@@ -69,6 +69,8 @@ _PROTOS = {
     "gstex_unpad_texture_grad_sigmoid": (c_i, [c_i64, c_fp, c_fp, c_fp, c_i, c_fp]),
     "gstex_adam_step": (c_i, [c_i64, c_fp, c_fp, c_fp, c_fp] + [C.c_double] * 4 + [c_i, c_f, c_fp]),
     "gstex_adam_state_bytes": (c_sz, []),
+    "gstex_adam_prepare_device": (c_i, [c_fp, C.c_double, C.c_double, C.c_double, C.c_double, c_f, c_fp]),
+    "gstex_adam_apply_rows_device": (c_i, [c_i64, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_i, c_fp, c_fp]),
     "gstex_adam_step_device": (c_i, [c_i64, c_fp, c_fp, c_fp, c_fp, C.c_double, C.c_double, C.c_double, C.c_double, c_fp,
                                      c_f, c_fp]),
 }

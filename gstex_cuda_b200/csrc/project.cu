@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(256) project_aabb_count_kernel(
     int n, const float *__restrict__ means, const float *__restrict__ scales, float glob_scale,
     const float4 *__restrict__ quats, const float *__restrict__ viewmat, float fx, float fy, float cx, float cy,
     int tiles_x, int tiles_y, float fbw, float2 *__restrict__ centers, float2 *__restrict__ extents,
-    float *__restrict__ depths, int32_t *__restrict__ num_tiles_hit) {
+    float *__restrict__ depths, int32_t *__restrict__ num_tiles_hit, float *__restrict__ visible_count) {
     __shared__ float vm[12];
     if (threadIdx.x < 12) vm[threadIdx.x] = viewmat[threadIdx.x];
     __syncthreads();
@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(256) project_aabb_count_kernel(
         cnt = (x1 - x0) * (y1 - y0);
     }
     num_tiles_hit[i] = cnt;
+    if (visible_count && cnt > 0) visible_count[i] += 1.f;  // one thread per Gaussian, views in stream order: no atomic
 }
 
 }  // namespace gstex
@@ -197,14 +198,14 @@ extern "C" int gstex_project_aabb_count(int n, const float *means, const float *
                                         const float *quats, const float *viewmat, float fx, float fy, float cx,
                                         float cy, int img_height, int img_width, int block_width,
                                         float *centers, float *extents, float *depths,
-                                        int32_t *num_tiles_hit, gstex_stream_t stream) {
+                                        int32_t *num_tiles_hit, float *visible_count, gstex_stream_t stream) {
     GSTEX_REQUIRE(n >= 0 && block_width > 0, GSTEX_E_INVALID, "project_aabb_count: n = %d, bw = %d", n,
                   block_width);
     if (n == 0) return GSTEX_OK;
     const int tx = ceil_div(img_width, block_width), ty = ceil_div(img_height, block_width);
     project_aabb_count_kernel<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(
         n, means, scales, glob_scale, (const float4 *)quats, viewmat, fx, fy, cx, cy, tx, ty, (float)block_width,
-        (float2 *)centers, (float2 *)extents, depths, num_tiles_hit);
+        (float2 *)centers, (float2 *)extents, depths, num_tiles_hit, visible_count);
     GSTEX_LAUNCH_OK("project_aabb_count_kernel");
     return GSTEX_OK;
 }

@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, GSTEX_FWD_MINB) raster_for
     asm volatile("" : "+r"(queue_off));
 #endif
     uint8_t *__restrict__ my_list = surv_base + list_off;
-    float *__restrict__ q_alpha = reinterpret_cast<float *>(surv_base + FWD_WARPS * FWD_BATCH) + queue_off;
+    float *__restrict__ q_val = reinterpret_cast<float *>(surv_base + FWD_WARPS * FWD_BATCH) + queue_off;
     uint8_t *__restrict__ q_ent = surv_base + FWD_WARPS * FWD_BATCH + sizeof(float) * FWD_WARPS * FWD_Q * 32 + queue_off;
     const int tile = blockIdx.y * p.tiles_x + blockIdx.x;
     int lx, ly;
@@ -172,15 +172,17 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, GSTEX_FWD_MINB) raster_for
         const int qmax = __reduce_max_sync(0xffffffffu, qn);
         for (int k = 0; k < qmax; ++k) {
             if (k < qn && !done) {
-                const float qa = q_alpha[k * 32];
+                const float qa = q_val[k * 32];
                 const int i = q_ent[k * 32];
-                const float alpha = fabsf(qa);
+                const float4 *__restrict__ R = S + i * REC_PITCH;
+                const float4 q0 = R[0];
+                // the same operations as eval_pair(): alpha is bit-identical to what the backward pass recomputes
+                const float alpha = BLUR ? fabsf(qa) : fminf(ALPHA_CAP, __fmul_rn(q0.w, fast_exp2(-fabsf(qa))));
                 const float next_T = __fmul_rn(T, __fsub_rn(1.f, alpha));
                 if (next_T <= T_STOP) {  // tested before the skip is honoured (reference texture.cu:216-221)
                     done = true;
-                } else if (qa > 0.f) {   // sign bit: skipped for its ray distance (texture.cu:213)
-                    const float4 *__restrict__ R = S + i * REC_PITCH;
-                    const float4 q0 = R[0], q3 = R[3], q4 = R[4], q5 = R[5], q6 = R[6], q7 = R[7];
+                } else if (__float_as_int(qa) >= 0) {   // sign bit: skipped for its ray distance (texture.cu:213)
+                    const float4 q3 = R[3], q4 = R[4], q5 = R[5], q6 = R[6], q7 = R[7];
                     const float c3 = R[1].w;
                     // the same operations, in the same order, as eval_pair(): t, u and v come out bit-identical to what
                     // phase 1 tested and to what the backward pass recomputes for this pair
@@ -233,6 +235,7 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, GSTEX_FWD_MINB) raster_for
         const int cnt = min(FWD_BATCH, range.y - first);
         if (!fwd_stage_advance(stage, p, range, b, nbatch, tr, done)) break;
         const float4 *__restrict__ S = stage[b % FWD_STAGES];
+        uint32_t *__restrict__ mask_row = p.masks + ((size_t)first * MASK_WARPS + warp);  // this warp's word of entry `first`
         if (RENDER && tr < cnt) {  // one thread per staged record: start fetching its texture block
             const float4 q3 = S[quad_slot(tr, 3)], q6 = S[quad_slot(tr, 6)];
             prefetch_texture_block(p.tex4, __float_as_int(q6.w), __float_as_int(q3.z), __float_as_int(q3.w));
@@ -243,18 +246,39 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, GSTEX_FWD_MINB) raster_for
             const int i = my_list[si];
             const float4 *__restrict__ R = S + i * REC_PITCH;
             const float4 q0 = R[0], q1 = R[1], q2 = R[2], q3 = R[3];
-            PairEval pe;
-            eval_pair<BLUR>(q0, q1, q2, q3, pc, p.mean2d, pe);
+            // alpha >= 1/255  <=>  l1'^2 + l2'^2 <= log2(255 opac) = the record's R_QMAX: the walk needs no exponential (the
+            // drain computes alpha, for the pairs that pass); with the blur floor alpha is not a function of q alone and
+            // the full evaluation stays
+            float qv;    // what the queue carries: q = l1'^2 + l2'^2 (BLUR: alpha)
+            bool pass, tskip;
+            if (BLUR) {
+                PairEval pe;
+                eval_pair<true>(q0, q1, q2, q3, pc, p.mean2d, pe);
+                qv = pe.alpha;
+                pass = pe.alpha >= ALPHA_MIN;
+                tskip = pe.t < T_NEAR || pe.t > T_FAR;
+            } else {
+                const float ex = __fsub_rn(pc.px, q0.x), ey = __fsub_rn(pc.py, q0.y);
+                const float n1 = fmaf(q1.x, ex, fmaf(q1.y, ey, q1.z));
+                const float n2 = fmaf(q2.x, ex, fmaf(q2.y, ey, q2.z));
+                float d = fmaf(q3.x, ex, fmaf(q3.y, ey, q1.w));
+                if (fabsf(d) < pc.eps) d = copysignf(pc.eps, d);
+                const float rD = fast_rcp(d);
+                const float l1 = __fmul_rn(n1, rD), l2 = __fmul_rn(n2, rD);
+                qv = fmaf(l1, l1, __fmul_rn(l2, l2));
+                const float t = __fmul_rn(__fmul_rn(q0.z, rD), pc.rn);
+                pass = qv <= R[7].w;
+                tskip = t < T_NEAR || t > T_FAR;
+            }
             if (!RENDER) done = done || first + i > my_last;
-            const bool cand = !done && pe.alpha >= ALPHA_MIN;
-            const bool tskip = pe.t < T_NEAR || pe.t > T_FAR;
+            const bool cand = !done && pass;
             const unsigned bm = __ballot_sync(0xffffffffu, cand && !tskip);
-            if (p.masks && bm != 0u && lane == 0) p.masks[(size_t)(first + i) * MASK_WARPS + warp] = bm;
+            if (p.masks && bm != 0u && lane == 0) mask_row[(size_t)i * MASK_WARPS] = bm;
             if (!RENDER) {
                 if (__all_sync(0xffffffffu, done)) break;
             } else {
-                if (cand) {
-                    q_alpha[qn * 32] = tskip ? -pe.alpha : pe.alpha;
+                if (cand) {  // sign bit: skipped for its ray distance, but it still takes part in the stop rule
+                    q_val[qn * 32] = __int_as_float(__float_as_int(qv) | (tskip ? 0x80000000 : 0));
                     q_ent[qn * 32] = (uint8_t)i;
                     ++qn;
                 }

@@ -248,6 +248,46 @@ extern "C" int gstex_unpad_texture_grad_sigmoid(int64_t num_texels, const float 
     return GSTEX_OK;
 }
 
+// Visible-only ("selective") Adam over one field of the arena: element e belongs to unit e / unit_width, the unit to row
+// owner[unit] (or to row `unit` itself), and only rows with visible[row] > 0 are touched - parameters AND both moments of
+// an unseen Gaussian stay as they are, so a Gaussian outside every view of the step neither drifts on stale momentum nor
+// has its second moment decayed.  The bias corrections use the global step counter, as torch.optim.SparseAdam's dense
+// twin and gsplat's SelectiveAdam do.
+__global__ void __launch_bounds__(256) adam_rows_kernel(int64_t count, float *__restrict__ p, const float *__restrict__ g,
+                                                        float *__restrict__ m, float *__restrict__ v,
+                                                        const AdamDeviceState *__restrict__ st,
+                                                        const float *__restrict__ visible, int unit_width,
+                                                        const int32_t *__restrict__ owner) {
+    const AdamArgs a = st->args;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += stride) {
+        const int64_t unit = e / unit_width;
+        const int64_t row = owner ? (int64_t)owner[unit] : unit;
+        if (visible[row] > 0.f) adam_one(p[e], g[e], m[e], v[e], a);
+    }
+}
+
+extern "C" int gstex_adam_prepare_device(void *state, double lr, double beta1, double beta2, double eps, float grad_scale,
+                                         gstex_stream_t stream) {
+    GSTEX_REQUIRE(state != nullptr, GSTEX_E_INVALID, "adam_prepare_device: state is NULL");
+    adam_prepare_kernel<<<1, 1, 0, as_stream(stream)>>>((AdamDeviceState *)state, lr, beta1, beta2, eps, grad_scale);
+    GSTEX_LAUNCH_OK("adam_prepare_kernel");
+    return GSTEX_OK;
+}
+
+extern "C" int gstex_adam_apply_rows_device(int64_t count, float *params, const float *grads, float *exp_avg,
+                                            float *exp_avg_sq, const void *state, const float *visible, int unit_width,
+                                            const int32_t *owner, gstex_stream_t stream) {
+    GSTEX_REQUIRE(count >= 0 && state != nullptr && visible != nullptr && unit_width >= 1, GSTEX_E_INVALID,
+                  "adam_apply_rows_device: count = %lld, unit_width = %d", (long long)count, unit_width);
+    if (count == 0) return GSTEX_OK;
+    const int blocks = (int)min((int64_t)148 * 8, ceil_div64(count, 256));
+    adam_rows_kernel<<<blocks, 256, 0, as_stream(stream)>>>(count, params, grads, exp_avg, exp_avg_sq,
+                                                            (const AdamDeviceState *)state, visible, unit_width, owner);
+    GSTEX_LAUNCH_OK("adam_rows_kernel");
+    return GSTEX_OK;
+}
+
 extern "C" int gstex_adam_step(int64_t count, float *params, const float *grads, float *exp_avg, float *exp_avg_sq,
                                double lr, double beta1, double beta2, double eps, int step, float grad_scale,
                                gstex_stream_t stream) {

@@ -76,11 +76,13 @@ int gstex_project_points(int n, const float *means, const float *viewmat, float 
 /* fused replacement of example.py:148-152 (project_points + get_aabb_2d + get_num_tiles_hit_2d):
  * one pass over the Gaussians.  Tile counts use the same truncation rule as the key emitter
  * (helpers.cuh:37-51), which equals the floor rule after clamping for power-of-two block widths.
- * Gaussians whose extents are both <= 1e-4 (clipped, forward.cu:32) count 0 tiles. */
+ * Gaussians whose extents are both <= 1e-4 (clipped, forward.cu:32) count 0 tiles.
+ * visible_count (may be NULL): n floats; += 1 for every Gaussian that hits at least one tile (the per-step visibility the
+ * visible-only Adam update gates on; the caller zero-fills it once per optimiser step). */
 int gstex_project_aabb_count(int n, const float *means, const float *scales, float glob_scale,
                              const float *quats, const float *viewmat, float fx, float fy, float cx, float cy,
                              int img_height, int img_width, int block_width, float *centers, float *extents,
-                             float *depths, int32_t *num_tiles_hit, gstex_stream_t stream);
+                             float *depths, int32_t *num_tiles_hit, float *visible_count, gstex_stream_t stream);
 
 /* ======================================================================================== *
  * (2) tile binning
@@ -347,6 +349,17 @@ size_t gstex_adam_state_bytes(void);
 int gstex_adam_step_device(int64_t count, float *params, const float *grads, float *exp_avg, float *exp_avg_sq,
                            double lr, double beta1, double beta2, double eps, void *state, float grad_scale,
                            gstex_stream_t stream);
+/* Visible-only Adam ("sparse / visible-only update"): gstex_adam_prepare_device advances the
+ * device-resident step counter once per optimiser step; gstex_adam_apply_rows_device then updates one field of the
+ * arena, touching only the elements whose row has visible[row] > 0 (parameters and both moments of unseen rows are
+ * left alone).  Element e belongs to unit e / unit_width and the unit to row owner[unit] (owner == NULL: row = unit) -
+ * e.g. unit_width 3 and owner = texel -> Gaussian for a jagged texture.  visible: one float per row, e.g. the number of
+ * views of the step whose tile count for the Gaussian was non-zero (gstex_project_aabb_count fills it). */
+int gstex_adam_prepare_device(void *state, double lr, double beta1, double beta2, double eps, float grad_scale,
+                              gstex_stream_t stream);
+int gstex_adam_apply_rows_device(int64_t count, float *params, const float *grads, float *exp_avg, float *exp_avg_sq,
+                                 const void *state, const float *visible, int unit_width, const int32_t *owner,
+                                 gstex_stream_t stream);
 
 #ifdef __cplusplus
 }
