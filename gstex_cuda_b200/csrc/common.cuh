@@ -159,7 +159,7 @@ enum RecSlot : int {
     R_PUX = 16, R_PUY = 17, R_CU = 18, R_U0 = 19,  // u = u0 + (cu + PU.e)/D
     R_PVX = 20, R_PVY = 21, R_CV = 22, R_V0 = 23,
     R_CR = 24, R_CG = 25, R_CB = 26, R_TEX0 = 27,  // colour, first texel (int bits)
-    R_NX = 28, R_NY = 29, R_NZ = 30, R_QMAX = 31,  // world normal ; log2(255 opac): alpha >= 1/255 <=> l1'^2 + l2'^2 <= it
+    R_NX = 28, R_NY = 29, R_NZ = 30, R_PAD = 31,   // world normal
 };
 
 // Per-view, per-Gaussian gradient moments written by the backward rasteriser (32 floats, 8 quads).

@@ -160,8 +160,7 @@ __global__ void __launch_bounds__(256, GSTEX_PACK_MINB) pack_kernel(int n, const
     // colours are optional: texture_edit walks the same records without them
     const Vec3 col = colors ? ld3(colors + 3 * g) : mk3(0.f, 0.f, 0.f);
     r[6] = make_float4(col.x, col.y, col.z, __int_as_float(texture_dims[3 * g + 2]));
-    // R_QMAX: the forward walk's candidate test alpha >= 1/255 without an exponential (opacity <= 0: never a candidate)
-    r[7] = make_float4(f.a3.x, f.a3.y, f.a3.z, r0.w > 0.f ? log2f(255.f * r0.w) : -1.f);
+    r[7] = make_float4(f.a3.x, f.a3.y, f.a3.z, 0.f);
     mean2d[g] = pinhole(fx, fy, cx, cy, xform_point(cam.vm, mean));
 }
 

@@ -178,7 +178,7 @@ __device__ __forceinline__ void stage_records(float4 *__restrict__ dst, const fl
 // approximate ex2 / rounding) is skipped by every pixel of the warp (reference texture.cu:213), so the
 // warp never evaluates it.  Survivor indices are compacted per warp, order preserved.
 // The reference tests the stop rule T(1-alpha) <= 1e-4 even for Gaussians it skips; a culled Gaussian (alpha < 1/255) is
-// never evaluated here.  That cannot change any output: see the monotonicity argument at the top of raster_forward.cu.
+// never evaluated here.  That cannot change any output: see the monotonicity argument in raster_forward.cu.
 // ------------------------------------------------------------------------------------------
 struct WarpRect {
     float cx, cy, hx, hy;  // centre and half extents (pixel centres) of the warp's live pixels
@@ -268,11 +268,10 @@ struct RasterCommon {
     const float *tex;          // caller's texture (X x C), generic channel count
     const float *viewmat, *c2w, *background;
     float fx, fy, cx, cy;
-    // One 32-bit word per (sorted-list entry, warp of the tile's CTA): the lanes (pixels) whose pair passed the skip test
-    // (alpha >= 1/255, ray distance in range) while the pixel was not known to have stopped.  Pixel p BLENDED entry i iff
-    // its bit is set and i <= final_idx[p].  Written by the forward rasteriser, read (and filtered) by the backward one,
-    // which therefore differentiates exactly the pairs the forward pass composited without re-evaluating the skip rule
-    // or running a culling pass.
+    // One 32-bit word per (sorted-list entry, warp of the tile's CTA): the lanes (pixels) that BLENDED the entry in the
+    // forward pass.  Written by the forward rasteriser (or re-derived from final_Ts / final_idx by raster_masks_kernel),
+    // read by the backward one, which therefore differentiates exactly the pairs the forward pass composited (no
+    // re-evaluation of the skip / stop rules, no culling pass).
     uint32_t *masks;
 };
 constexpr int MASK_WARPS = RASTER_MAX_THREADS / 32;  // mask words per list entry
@@ -307,7 +306,7 @@ RasterCommon make_raster_common(int img_height, int img_width, int block_width, 
 // then rasterises
 int launch_raster_forward(const RasterCommon &p, const ForwardOut &o, int64_t mask_entries, const int32_t *d_count,
                           cudaStream_t s);
-// rebuilds the blend masks from a finished forward pass's final_Ts / final_idx (raster_forward.cu: MODE_MASKS)
+// rebuilds the blend masks from a finished forward pass's final_Ts / final_idx (raster_forward.cu: raster_masks_kernel)
 int launch_raster_masks(const RasterCommon &p, const float *final_Ts, const int32_t *final_idx, int64_t mask_entries,
                         const int32_t *d_count, cudaStream_t s);
 int launch_raster_backward(const RasterCommon &p, const BackwardIn &in, const BackwardOut &o, cudaStream_t s);

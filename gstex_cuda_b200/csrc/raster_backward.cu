@@ -269,11 +269,6 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, GSTEX_BWD_MINB) raster_bac
     const int nbatch = (hi - range.x + BWD_BATCH - 1) / BWD_BATCH;
 
     float T = in.final_Ts[me.pix];
-    // The forward pass's mask words are a superset of what was composited: they also carry the bits of candidates that
-    // come after a pixel's stop (raster_forward.cu).  Pixel p composited entry i iff its bit is set and
-    // i <= final_idx[p].  Entries up to the smallest final_idx among the warp's pixels that composited anything need no
-    // filtering; in the tail beyond it the bits of the pixels that had already stopped are cleared as the words are fetched.
-    const int filter_from = __reduce_min_sync(full, (inside && T < 1.f) ? bfinal : 0x7fffffff);
     me.Sf0 = in.final_s[3 * me.pix]; me.Sf1 = in.final_s[3 * me.pix + 1]; me.Sf2 = in.final_s[3 * me.pix + 2];
     me.dfinal = in.depth_idx[me.pix];
     me.vi0 = in.v_img[3 * me.pix]; me.vi1 = in.v_img[3 * me.pix + 1]; me.vi2 = in.v_img[3 * me.pix + 2];
@@ -310,17 +305,6 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, GSTEX_BWD_MINB) raster_bac
         nx_g0 = r0 < cnt ? __ldg(p.ids + first + r0) : 0;
         nx_m1 = r1 < cnt ? __ldg(p.masks + (size_t)(first + r1) * MASK_WARPS + warp) : 0u;
         nx_g1 = r1 < cnt ? __ldg(p.ids + first + r1) : 0;
-        if (first + cnt - 1 > filter_from) {  // warp-uniform: only the tail of the walk
-            unsigned v0 = 0u, v1 = 0u;
-#pragma unroll 4
-            for (int pl = 0; pl < 32; ++pl) {
-                const int bp = __shfl_sync(full, bfinal, pl);
-                v0 |= (bp >= first + r0 ? 1u : 0u) << pl;
-                v1 |= (bp >= first + r1 ? 1u : 0u) << pl;
-            }
-            nx_m0 &= v0;
-            nx_m1 &= v1;
-        }
     };
     fetch_batch(0);
     for (int b = 0; b < nbatch; ++b) {
@@ -610,7 +594,7 @@ extern "C" int gstex_texture_backward(
 
     // Forward state: the caller's scratch when it kept one, else rebuilt here from the call's own arguments - the
     // reference's texture_backward_tensor is a pure function of them (texture.cu:915-1053): records and padded texture
-    // are re-packed, and the blend masks are re-derived from final_Ts / final_idx by the MODE_MASKS walk (no second
+    // are re-packed, and the blend masks are re-derived from final_Ts / final_idx by raster_masks_kernel (no second
     // forward pass: no compositing, no texel fetch, no outputs).
     const char *fbase = stateless ? base + L.fwd_off : (const char *)fwd_temp;
     RasterCommon p = make_raster_common(

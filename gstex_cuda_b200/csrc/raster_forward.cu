@@ -39,61 +39,49 @@ __device__ __forceinline__ float outline_distance(const float4 q0, const float4 
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Two kernel bodies.
+// raster_forward_kernel<C3, BLUR, VIS>  the forward pass.  The warp walks the survivors of a stage in lock step, one
+//   record per iteration, every lane evaluating ITS pixel from the broadcast record: the record reads are broadcasts, the
+//   four texel loads of the blending lanes fall into the two cache lines of one Gaussian's texture block, and the blend
+//   decision of the 32 pixels is one ballot - the mask word the backward pass reads.
+//   C3 = false: runtime channel count (<= 64, texels read from the caller's (X,C) array).  VIS = true: the viewer-only
+//   settings bits 15-29 (texture.cu:58-63, :201-241, :269-274; no culling - its bound assumes alpha = opac*exp(-sigma) -,
+//   no masks, forward only).
+// raster_masks_kernel<BLUR>  re-derives the blend masks of a FINISHED forward pass from its saved state, for callers of
+//   the stateless reference-shaped backward (texture_backward_tensor, texture.cu:915-1053, is a pure function of its
+//   arguments): pixel p composited list entry i iff i <= final_idx[p] and the pair passes the skip test - exactly what the
+//   reference's backward re-evaluates (texture.cu:484-558); the stop rule needs no replay because final_idx bounds the
+//   walk.  Same staging, culling and pair evaluation as the forward pass, no compositing, no texel fetch, no outputs.
 //
-// raster_forward_queued_kernel - 3-channel textures, training / inference (the hot path) and MODE_MASKS.
-//   Walk (phase 1).  The warp walks the survivors of the stage together, one record per iteration, every lane
-//   evaluating ITS pixel's alpha and ray distance from the broadcast record.  Nothing in this phase depends on the
-//   transmittance: a lane whose alpha reaches 1/255 appends (entry, alpha) to its own queue in shared memory
-//   (slot-major: queue[slot][lane], conflict free), and the ballot of the lanes that may blend the entry is the mask
-//   word the backward pass reads - one plain store per (entry, warp).  No divergent code.
-//   Drain (phase 2).  When a pixel's queue is full, and at the end of every stage, every lane composites ITS OWN queue
-//   front to back: stop rule, transmittance, colour / normal / depth / distortion sums, texture coordinate, the four
-//   16-byte texel loads, out_texture.  The lanes of a warp work on different Gaussians at the same time, so the ~135
-//   instructions of a blended pair run with 62-69 % of the lanes active (measured on the C4 masks, tools/sim_masks.py)
-//   instead of the 36 % (11.5 of 32 pixels) a per-Gaussian lock-step walk gets.
-//   Per pixel the candidates are composited in list order with the reference's rules, so the outputs are what the
-//   lock-step evaluation gives.  Two things need an argument:
-//   * The reference tests the stop rule T(1-alpha) <= 1e-4 on EVERY Gaussian, including those it skips for
-//     alpha < 1/255 (texture.cu:213-222), which never enter a queue here (nor survive the warp-level cull).  That
-//     cannot change any output: if such a Gaussian (alpha_s < 1/255) trips the rule at transmittance T, then for the
-//     next candidate (alpha_c >= 1/255 > alpha_s) fl(T * fl(1-alpha_c)) <= fl(T * fl(1-alpha_s)) <= 1e-4 by monotonicity
-//     of rounding, so that candidate trips the rule too and nothing is composited after the point where the reference
-//     stopped; T, final_idx and every sum are identical.  Candidates skipped for their ray distance (t < 0.01 or
-//     t > 1000) can have any alpha, so they ARE queued (sign bit set) and take part in the stop rule.
-//   * The mask word is a superset of the composited pixels: it also has the bits of candidates that come after the
-//     pixel's stop.  Pixel p composited entry i iff its bit is set and i <= final_idx[p]; the backward pass applies
-//     that filter (raster_backward.cu).  MODE_MASKS - re-deriving the masks for the stateless reference-shaped
-//     backward (texture.cu:915-1053 is a pure function of its arguments) - is therefore phase 1 alone.
+// Measured and rejected this round (experiments/README.md): composing each pixel's candidates from a per-pixel queue
+// (lanes working on different Gaussians at once, 62-69 % of the lanes busy in the blend instead of 36 %).  The
+// instruction count came out the same, but lanes on different Gaussians touch 21 cache lines per texel load instead of 2
+// and read their records without broadcast; the L1 tag / LSU pipes went from 56 % to 80 % busy and the kernel from 1.31
+// to 1.41-1.61 ms.
 //
-// raster_forward_inline_kernel - runtime channel count (<= 64, texels read from the caller's (X,C) array) and the
-//   viewer-only settings bits 15-29 (texture.cu:58-63, :201-241, :269-274; no culling - its bound assumes
-//   alpha = opac * exp(-sigma) -, no masks, forward only): the lock-step walk with the blend in line.
+// The reference tests the stop rule T(1-alpha) <= 1e-4 on EVERY Gaussian, including those it skips for alpha < 1/255
+// (texture.cu:213-222); a Gaussian removed by the warp-level cull (alpha < 0.0039 on the whole patch) is never evaluated
+// here.  That cannot change any output: if such a Gaussian (alpha_s < 1/255) trips the rule at transmittance T, then for
+// the next Gaussian that could blend (alpha_c >= 1/255 > alpha_s) fl(T * fl(1-alpha_c)) <= fl(T * fl(1-alpha_s)) <= 1e-4 by
+// monotonicity of rounding, so it trips the rule too: nothing is composited after the point where the reference stopped,
+// and T, final_idx and every sum are identical.
 // ------------------------------------------------------------------------------------------------------------------
 #ifndef GSTEX_FWD_BATCH
-#define GSTEX_FWD_BATCH 88
-#endif
-#ifndef GSTEX_FWD_Q
-#define GSTEX_FWD_Q 12
+#define GSTEX_FWD_BATCH 128
 #endif
 #ifndef GSTEX_FWD_MINB
 #define GSTEX_FWD_MINB 4
 #endif
 constexpr int FWD_BATCH = GSTEX_FWD_BATCH;  // records per shared-memory stage (<= 256: uint8 indices)
-constexpr int FWD_Q = GSTEX_FWD_Q;          // queue slots per pixel
 constexpr int FWD_STAGES = 3;
 constexpr int FWD_WARPS = RASTER_MAX_THREADS / 32;
-enum FwdMode : int { MODE_RENDER = 0, MODE_MASKS = 1 };
 
-constexpr size_t fwd_smem_bytes(bool queued) {
-    return sizeof(float4) * FWD_STAGES * FWD_BATCH * REC_PITCH + (size_t)FWD_WARPS * FWD_BATCH +
-           (queued ? (size_t)FWD_WARPS * FWD_Q * 32 * (sizeof(float) + 1) : 0);
-}
-static_assert(fwd_smem_bytes(true) + 1024 <= 227 * 1024 / GSTEX_FWD_MINB, "forward stage buffers + queues exceed the per-CTA shared memory budget");
+constexpr size_t fwd_smem_bytes() { return sizeof(float4) * FWD_STAGES * FWD_BATCH * REC_PITCH + (size_t)FWD_WARPS * FWD_BATCH; }
+static_assert(fwd_smem_bytes() + 1024 <= 227 * 1024 / GSTEX_FWD_MINB, "forward stage buffers exceed the per-CTA shared memory budget");
 static_assert(FWD_BATCH % 4 == 0 && FWD_BATCH <= 256, "stage size");
 
 // Shared prologue of one stage iteration: issue stage b+1, wait for stage b, CTA barrier.  Returns false when every
-// pixel of the CTA is finished.
+// pixel of the CTA is finished.  Three stage buffers: stage b+1 is filled into the buffer last read two iterations ago,
+// which every warp has left by the time it passed this iteration's barrier, so ONE barrier per stage suffices.
 __device__ __forceinline__ bool fwd_stage_advance(float4 (*stage)[FWD_BATCH * REC_PITCH], const RasterCommon &p, int2 range,
                                                   int b, int nbatch, int tr, bool done) {
     const int first = range.x + b * FWD_BATCH;
@@ -111,32 +99,15 @@ __device__ __forceinline__ bool fwd_stage_advance(float4 (*stage)[FWD_BATCH * RE
     return __syncthreads_count(done) < p.nthreads;
 }
 
-template <bool BLUR, int MODE>
-__global__ void __launch_bounds__(RASTER_MAX_THREADS, GSTEX_FWD_MINB) raster_forward_queued_kernel(const RasterCommon p, const ForwardOut o,
-                                                                                                   const float *__restrict__ final_Ts_in,
-                                                                                                   const int32_t *__restrict__ final_idx_in) {
-    constexpr bool RENDER = MODE == MODE_RENDER;
-    // dynamic shared memory: three stage buffers (stage b+1 is filled into the buffer last read two iterations ago,
-    // which every warp has left by the time it passed this iteration's barrier, so ONE barrier per stage suffices),
-    // the per-warp survivor lists, and the per-pixel queues
+template <bool BLUR>
+__global__ void __launch_bounds__(RASTER_MAX_THREADS, GSTEX_FWD_MINB) raster_masks_kernel(const RasterCommon p,
+                                                                                          const float *__restrict__ final_Ts,
+                                                                                          const int32_t *__restrict__ final_idx) {
     extern __shared__ __align__(16) unsigned char fwd_smem[];
     float4 (*stage)[FWD_BATCH * REC_PITCH] = reinterpret_cast<float4 (*)[FWD_BATCH * REC_PITCH]>(fwd_smem);
     uint8_t *const surv_base = fwd_smem + sizeof(float4) * FWD_STAGES * FWD_BATCH * REC_PITCH;
-
-    const int tr = threadIdx.x, warp = tr >> 5;
-    // Under the 64-register cap ptxas re-derives the lane and this warp's shared-memory offsets from S2R SR_TID.X inside
-    // the hot loops; passing them through an empty asm makes them opaque, so they stay in registers (the same cure as in
-    // raster_backward.cu).
-    int lane = tr & 31;
-    unsigned list_off = (unsigned)warp * FWD_BATCH, queue_off = (unsigned)warp * (FWD_Q * 32) + (unsigned)lane;
-#ifndef GSTEX_FWD_NO_OPAQUE
-    asm volatile("" : "+r"(lane));
-    asm volatile("" : "+r"(list_off));
-    asm volatile("" : "+r"(queue_off));
-#endif
-    uint8_t *__restrict__ my_list = surv_base + list_off;
-    float *__restrict__ q_val = reinterpret_cast<float *>(surv_base + FWD_WARPS * FWD_BATCH) + queue_off;
-    uint8_t *__restrict__ q_ent = surv_base + FWD_WARPS * FWD_BATCH + sizeof(float) * FWD_WARPS * FWD_Q * 32 + queue_off;
+    const int tr = threadIdx.x, lane = tr & 31, warp = tr >> 5;
+    uint8_t *__restrict__ my_list = surv_base + warp * FWD_BATCH;
     const int tile = blockIdx.y * p.tiles_x + blockIdx.x;
     int lx, ly;
     tile_pixel(p.bw, tr, lx, ly);
@@ -144,182 +115,42 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, GSTEX_FWD_MINB) raster_for
     const bool inside = (tr < p.bw * p.bw) && col < p.img_w && row < p.img_h;
     const PixelConsts pc = make_pixel(col, row, p.c2w, p.viewmat, p.fx, p.fy, p.cx, p.cy);
     const WarpRect wr = make_warp_rect(col, row, inside);
-    const bool use_ndc = (p.settings & GSTEX_SET_NDC) != 0;
-    const bool bilinear = !(p.settings & GSTEX_SET_NEAREST);
-
     const int2 range = p.bins[tile];
     const int total = range.y - range.x;
     const int nbatch = (total + FWD_BATCH - 1) / FWD_BATCH;
-
-    float T = 1.f;
-    float acc_c0 = 0.f, acc_c1 = 0.f, acc_c2 = 0.f;
-    float acc_n0 = 0.f, acc_n1 = 0.f, acc_n2 = 0.f;
-    float acc_t0 = 0.f, acc_t1 = 0.f, acc_t2 = 0.f;
-    float depth = 0.f, reg = 0.f, S0 = 0.f, S1 = 0.f, S2 = 0.f;
-    int last = 0, dlast = -1;
-    int qn = 0;  // candidates queued for this pixel
-    bool done = !inside;
-    // MODE_MASKS: the saved state bounds the walk - a pixel's candidates end at the last entry it composited (a pixel
-    // that composited nothing has final_T == 1 exactly; its final_idx of 0 would be ambiguous)
+    // the saved state bounds the walk: a pixel's blends end at the last entry it composited (a pixel that composited
+    // nothing has final_T == 1 exactly; its final_idx of 0 would be ambiguous)
     int my_last = -1;
-    if (!RENDER && inside) {
+    if (inside) {
         const int pix = row * p.img_w + col;
-        my_last = final_Ts_in[pix] < 1.f ? final_idx_in[pix] : -1;
+        my_last = final_Ts[pix] < 1.f ? final_idx[pix] : -1;
     }
-
-    // phase 2: every lane composites its own queue against stage buffer S (the records the queued entries index)
-    auto drain = [&](const float4 *__restrict__ S, int first) {
-        const int qmax = __reduce_max_sync(0xffffffffu, qn);
-        for (int k = 0; k < qmax; ++k) {
-            if (k < qn && !done) {
-                const float qa = q_val[k * 32];
-                const int i = q_ent[k * 32];
-                const float4 *__restrict__ R = S + i * REC_PITCH;
-                const float4 q0 = R[0];
-                // the same operations as eval_pair(): alpha is bit-identical to what the backward pass recomputes
-                const float alpha = BLUR ? fabsf(qa) : fminf(ALPHA_CAP, __fmul_rn(q0.w, fast_exp2(-fabsf(qa))));
-                const float next_T = __fmul_rn(T, __fsub_rn(1.f, alpha));
-                if (next_T <= T_STOP) {  // tested before the skip is honoured (reference texture.cu:216-221)
-                    done = true;
-                } else if (__float_as_int(qa) >= 0) {   // sign bit: skipped for its ray distance (texture.cu:213)
-                    const float4 q3 = R[3], q4 = R[4], q5 = R[5], q6 = R[6], q7 = R[7];
-                    const float c3 = R[1].w;
-                    // the same operations, in the same order, as eval_pair(): t, u and v come out bit-identical to what
-                    // phase 1 tested and to what the backward pass recomputes for this pair
-                    const float ex = __fsub_rn(pc.px, q0.x), ey = __fsub_rn(pc.py, q0.y);
-                    float d = fmaf(q3.x, ex, fmaf(q3.y, ey, c3));
-                    if (fabsf(d) < pc.eps) d = copysignf(pc.eps, d);
-                    const float rD = fast_rcp(d);
-                    const float t = __fmul_rn(__fmul_rn(q0.z, rD), pc.rn);
-                    const float vis = alpha * T;
-                    acc_c0 = fmaf(q6.x, vis, acc_c0);
-                    acc_c1 = fmaf(q6.y, vis, acc_c1);
-                    acc_c2 = fmaf(q6.z, vis, acc_c2);
-                    acc_n0 = fmaf(q7.x, vis, acc_n0);
-                    acc_n1 = fmaf(q7.y, vis, acc_n1);
-                    acc_n2 = fmaf(q7.z, vis, acc_n2);
-                    const float nu = fmaf(q4.x, ex, fmaf(q4.y, ey, q4.z));
-                    const float nv = fmaf(q5.x, ex, fmaf(q5.y, ey, q5.z));
-                    const float u = clamp01(fmaf(nu, rD, q4.w)), v = clamp01(fmaf(nv, rD, q5.w));
-                    TexFetch tf;
-                    texel_setup(__float_as_int(q3.z), __float_as_int(q3.w), __float_as_int(q6.w), u, v, bilinear, tf);
-                    const float4 t0 = __ldg(p.tex4 + tf.idx[0]), t1 = __ldg(p.tex4 + tf.idx[1]);
-                    const float4 t2 = __ldg(p.tex4 + tf.idx[2]), t3 = __ldg(p.tex4 + tf.idx[3]);
-                    const float t_view = t * pc.vdep;
-                    if (T > 0.5f) {  // median depth (reference texture.cu:286-291)
-                        depth = t_view;
-                        dlast = first + i;
-                    }
-                    float tv = t;
-                    if (use_ndc) tv = (T_FAR * t_view - T_FAR * T_NEAR) / ((T_FAR - T_NEAR) * t_view);
-                    reg += vis * (tv * tv * S0 + S2 - 2.f * tv * S1);  // helpers.cuh:259-264
-                    S0 += vis;
-                    S1 += vis * tv;
-                    S2 += vis * tv * tv;
-                    T = next_T;
-                    last = first + i;
-                    const float w0 = tf.w[0] * vis, w1 = tf.w[1] * vis, w2 = tf.w[2] * vis, w3 = tf.w[3] * vis;
-                    acc_t0 += w0 * t0.x + w1 * t1.x + w2 * t2.x + w3 * t3.x;
-                    acc_t1 += w0 * t0.y + w1 * t1.y + w2 * t2.y + w3 * t3.y;
-                    acc_t2 += w0 * t0.z + w1 * t1.z + w2 * t2.z + w3 * t3.z;
-                }
-            }
-        }
-        qn = 0;
-    };
-
+    bool done = my_last < range.x;
     if (nbatch > 0) stage_records(stage[0], p.recs, p.ids, range.x, min(FWD_BATCH, total), tr, p.nthreads);
-
     for (int b = 0; b < nbatch; ++b) {
         const int first = range.x + b * FWD_BATCH;
         const int cnt = min(FWD_BATCH, range.y - first);
         if (!fwd_stage_advance(stage, p, range, b, nbatch, tr, done)) break;
         const float4 *__restrict__ S = stage[b % FWD_STAGES];
-        uint32_t *__restrict__ mask_row = p.masks + ((size_t)first * MASK_WARPS + warp);  // this warp's word of entry `first`
-        if (RENDER && tr < cnt) {  // one thread per staged record: start fetching its texture block
-            const float4 q3 = S[quad_slot(tr, 3)], q6 = S[quad_slot(tr, 6)];
-            prefetch_texture_block(p.tex4, __float_as_int(q6.w), __float_as_int(q3.z), __float_as_int(q3.w));
-        }
-        // warp-level culling: the warp walks only the records that can reach alpha >= 1/255 on its patch
         const int nsurv = __all_sync(0xffffffffu, done) ? 0 : build_survivors<BLUR, true>(S, 0, cnt, wr, p.mean2d, my_list, lane);
         for (int si = 0; si < nsurv; ++si) {
             const int i = my_list[si];
             const float4 *__restrict__ R = S + i * REC_PITCH;
-            const float4 q0 = R[0], q1 = R[1], q2 = R[2], q3 = R[3];
-            // alpha >= 1/255  <=>  l1'^2 + l2'^2 <= log2(255 opac) = the record's R_QMAX: the walk needs no exponential (the
-            // drain computes alpha, for the pairs that pass); with the blur floor alpha is not a function of q alone and
-            // the full evaluation stays
-            float qv;    // what the queue carries: q = l1'^2 + l2'^2 (BLUR: alpha)
-            bool pass, tskip;
-            if (BLUR) {
-                PairEval pe;
-                eval_pair<true>(q0, q1, q2, q3, pc, p.mean2d, pe);
-                qv = pe.alpha;
-                pass = pe.alpha >= ALPHA_MIN;
-                tskip = pe.t < T_NEAR || pe.t > T_FAR;
-            } else {
-                const float ex = __fsub_rn(pc.px, q0.x), ey = __fsub_rn(pc.py, q0.y);
-                const float n1 = fmaf(q1.x, ex, fmaf(q1.y, ey, q1.z));
-                const float n2 = fmaf(q2.x, ex, fmaf(q2.y, ey, q2.z));
-                float d = fmaf(q3.x, ex, fmaf(q3.y, ey, q1.w));
-                if (fabsf(d) < pc.eps) d = copysignf(pc.eps, d);
-                const float rD = fast_rcp(d);
-                const float l1 = __fmul_rn(n1, rD), l2 = __fmul_rn(n2, rD);
-                qv = fmaf(l1, l1, __fmul_rn(l2, l2));
-                const float t = __fmul_rn(__fmul_rn(q0.z, rD), pc.rn);
-                pass = qv <= R[7].w;
-                tskip = t < T_NEAR || t > T_FAR;
-            }
-            if (!RENDER) done = done || first + i > my_last;
-            const bool cand = !done && pass;
-            const unsigned bm = __ballot_sync(0xffffffffu, cand && !tskip);
-            if (p.masks && bm != 0u && lane == 0) mask_row[(size_t)i * MASK_WARPS] = bm;
-            if (!RENDER) {
-                if (__all_sync(0xffffffffu, done)) break;
-            } else {
-                if (cand) {  // sign bit: skipped for its ray distance, but it still takes part in the stop rule
-                    q_val[qn * 32] = __int_as_float(__float_as_int(qv) | (tskip ? 0x80000000 : 0));
-                    q_ent[qn * 32] = (uint8_t)i;
-                    ++qn;
-                }
-                if (__any_sync(0xffffffffu, qn >= FWD_Q)) {
-                    drain(S, first);
-                    if (__all_sync(0xffffffffu, done)) break;
-                }
-            }
+            PairEval pe;
+            eval_pair<BLUR>(R[0], R[1], R[2], R[3], pc, p.mean2d, pe);
+            done = done || first + i > my_last;
+            if (__all_sync(0xffffffffu, done)) break;
+            const unsigned bm = __ballot_sync(0xffffffffu, !done && !pair_skipped(pe));
+            if (bm != 0u && lane == 0) p.masks[(size_t)(first + i) * MASK_WARPS + warp] = bm;
         }
-        // the queued entries index this stage's records: drain before the buffer can be refilled
-        if (RENDER && __any_sync(0xffffffffu, qn > 0)) drain(S, first);
     }
     __pipeline_wait_prior(0);
-
-    if (RENDER && inside) {
-        const int pix = row * p.img_w + col;
-        const float bg0 = p.background[0], bg1 = p.background[1], bg2 = p.background[2];
-        o.final_Ts[pix] = T;
-        o.final_idx[pix] = last;
-        o.depth_idx[pix] = dlast;
-        o.out_img[3 * pix + 0] = fmaf(T, bg0, acc_c0);
-        o.out_img[3 * pix + 1] = fmaf(T, bg1, acc_c1);
-        o.out_img[3 * pix + 2] = fmaf(T, bg2, acc_c2);
-        o.out_normal[3 * pix + 0] = acc_n0;
-        o.out_normal[3 * pix + 1] = acc_n1;
-        o.out_normal[3 * pix + 2] = acc_n2;
-        o.out_depth[pix] = depth;
-        o.out_reg[pix] = reg;
-        o.out_reg_s[3 * pix + 0] = S0;
-        o.out_reg_s[3 * pix + 1] = S1;
-        o.out_reg_s[3 * pix + 2] = S2;
-        o.out_texture[3 * pix + 0] = acc_t0;
-        o.out_texture[3 * pix + 1] = acc_t1;
-        o.out_texture[3 * pix + 2] = acc_t2;
-    }
 }
 
-// C3 = true : 3-channel texture read through the padded float4 copy (VIS builds only; the non-VIS 3-channel case is the
-//             queued kernel above).  C3 = false: runtime channel count (<= 64) read from the caller's (X,C) array.
+// C3 = true : 3-channel texture read through the padded float4 copy, accumulators in registers.
+// C3 = false: runtime channel count (<= 64) read from the caller's (X,C) array (slow generic path).
 template <bool C3, bool BLUR, bool VIS>
-__global__ void __launch_bounds__(RASTER_MAX_THREADS, GSTEX_FWD_MINB) raster_forward_inline_kernel(const RasterCommon p, const ForwardOut o) {
+__global__ void __launch_bounds__(RASTER_MAX_THREADS, GSTEX_FWD_MINB) raster_forward_kernel(const RasterCommon p, const ForwardOut o) {
     extern __shared__ __align__(16) unsigned char fwd_smem[];
     float4 (*stage)[FWD_BATCH * REC_PITCH] = reinterpret_cast<float4 (*)[FWD_BATCH * REC_PITCH]>(fwd_smem);
     uint8_t *const surv_base = fwd_smem + sizeof(float4) * FWD_STAGES * FWD_BATCH * REC_PITCH;
@@ -365,6 +196,10 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, GSTEX_FWD_MINB) raster_for
         const int cnt = min(FWD_BATCH, range.y - first);
         if (!fwd_stage_advance(stage, p, range, b, nbatch, tr, done)) break;
         const float4 *__restrict__ S = stage[b % FWD_STAGES];
+        if (C3 && tr < cnt) {  // one thread per staged record: start fetching its texture block
+            const float4 q3 = S[quad_slot(tr, 3)], q6 = S[quad_slot(tr, 6)];
+            prefetch_texture_block(p.tex4, __float_as_int(q6.w), __float_as_int(q3.z), __float_as_int(q3.w));
+        }
         const int nsurv = __all_sync(0xffffffffu, done) ? 0 : build_survivors<BLUR, !VIS>(S, 0, cnt, wr, p.mean2d, my_list, lane);
         // The survivor walk is warp-uniform: finished pixels stay in the loop (predicated off) so that the blend
         // decision of all 32 pixels is one ballot - the mask word the backward pass reads.
@@ -510,24 +345,12 @@ __global__ void __launch_bounds__(256) zero_masks_kernel(uint4 *__restrict__ mas
         masks[q] = make_uint4(0u, 0u, 0u, 0u);
 }
 
-template <bool BLUR, int MODE>
-static int launch_fwd_queued(const dim3 grid, const RasterCommon &p, const ForwardOut &o, const float *final_Ts_in,
-                             const int32_t *final_idx_in, cudaStream_t s) {
-    constexpr size_t smem = fwd_smem_bytes(MODE == MODE_RENDER);
-    static SmemOnceFlags once;  // one per template instantiation
-    const int rc = configure_dynamic_smem((const void *)raster_forward_queued_kernel<BLUR, MODE>, smem, true, once);
-    if (rc != GSTEX_OK) return rc;
-    raster_forward_queued_kernel<BLUR, MODE><<<grid, p.nthreads, smem, s>>>(p, o, final_Ts_in, final_idx_in);
-    return GSTEX_OK;
-}
-
 template <bool C3, bool BLUR, bool VIS>
-static int launch_fwd_inline(const dim3 grid, const RasterCommon &p, const ForwardOut &o, cudaStream_t s) {
-    constexpr size_t smem = fwd_smem_bytes(false);
-    static SmemOnceFlags once;
-    const int rc = configure_dynamic_smem((const void *)raster_forward_inline_kernel<C3, BLUR, VIS>, smem, true, once);
+static int launch_fwd_variant(const dim3 grid, const RasterCommon &p, const ForwardOut &o, cudaStream_t s) {
+    static SmemOnceFlags once;  // one per template instantiation
+    const int rc = configure_dynamic_smem((const void *)raster_forward_kernel<C3, BLUR, VIS>, fwd_smem_bytes(), true, once);
     if (rc != GSTEX_OK) return rc;
-    raster_forward_inline_kernel<C3, BLUR, VIS><<<grid, p.nthreads, smem, s>>>(p, o);
+    raster_forward_kernel<C3, BLUR, VIS><<<grid, p.nthreads, fwd_smem_bytes(), s>>>(p, o);
     return GSTEX_OK;
 }
 
@@ -547,31 +370,35 @@ int launch_raster_forward(const RasterCommon &p, const ForwardOut &o, int64_t ma
     const dim3 grid(p.tiles_x, ceil_div(p.img_h, p.bw));
     const bool blur = (p.settings & GSTEX_SET_BLUR) != 0;
     if (p.settings & GSTEX_SET_VIS_ALL) {  // viewer-only modes: one generic build per channel layout, forward only
-        if (p.channels == 3) rc = blur ? launch_fwd_inline<true, true, true>(grid, p, o, s) : launch_fwd_inline<true, false, true>(grid, p, o, s);
-        else rc = blur ? launch_fwd_inline<false, true, true>(grid, p, o, s) : launch_fwd_inline<false, false, true>(grid, p, o, s);
+        if (p.channels == 3) rc = blur ? launch_fwd_variant<true, true, true>(grid, p, o, s) : launch_fwd_variant<true, false, true>(grid, p, o, s);
+        else rc = blur ? launch_fwd_variant<false, true, true>(grid, p, o, s) : launch_fwd_variant<false, false, true>(grid, p, o, s);
     } else if (p.channels == 3) {
-        rc = blur ? launch_fwd_queued<true, MODE_RENDER>(grid, p, o, nullptr, nullptr, s)
-                  : launch_fwd_queued<false, MODE_RENDER>(grid, p, o, nullptr, nullptr, s);
+        rc = blur ? launch_fwd_variant<true, true, false>(grid, p, o, s) : launch_fwd_variant<true, false, false>(grid, p, o, s);
     } else {
-        rc = blur ? launch_fwd_inline<false, true, false>(grid, p, o, s) : launch_fwd_inline<false, false, false>(grid, p, o, s);
+        rc = blur ? launch_fwd_variant<false, true, false>(grid, p, o, s) : launch_fwd_variant<false, false, false>(grid, p, o, s);
     }
     if (rc != GSTEX_OK) return rc;
     GSTEX_LAUNCH_OK("raster_forward_kernel");
     return GSTEX_OK;
 }
 
-// Blend masks of a finished forward pass from its saved state (phase 1 of the queued kernel): see MODE_MASKS above.
+// Blend masks of a finished forward pass from its saved state: see raster_masks_kernel.
 int launch_raster_masks(const RasterCommon &p, const float *final_Ts, const int32_t *final_idx, int64_t mask_entries,
                         const int32_t *d_count, cudaStream_t s) {
     int rc = zero_masks(p, mask_entries, d_count, s);
     if (rc != GSTEX_OK) return rc;
     const dim3 grid(p.tiles_x, ceil_div(p.img_h, p.bw));
-    const bool blur = (p.settings & GSTEX_SET_BLUR) != 0;
-    ForwardOut o{};
-    rc = blur ? launch_fwd_queued<true, MODE_MASKS>(grid, p, o, final_Ts, final_idx, s)
-              : launch_fwd_queued<false, MODE_MASKS>(grid, p, o, final_Ts, final_idx, s);
-    if (rc != GSTEX_OK) return rc;
-    GSTEX_LAUNCH_OK("raster_forward_queued_kernel<MODE_MASKS>");
+    static SmemOnceFlags once[2];
+    if (p.settings & GSTEX_SET_BLUR) {
+        rc = configure_dynamic_smem((const void *)raster_masks_kernel<true>, fwd_smem_bytes(), true, once[1]);
+        if (rc != GSTEX_OK) return rc;
+        raster_masks_kernel<true><<<grid, p.nthreads, fwd_smem_bytes(), s>>>(p, final_Ts, final_idx);
+    } else {
+        rc = configure_dynamic_smem((const void *)raster_masks_kernel<false>, fwd_smem_bytes(), true, once[0]);
+        if (rc != GSTEX_OK) return rc;
+        raster_masks_kernel<false><<<grid, p.nthreads, fwd_smem_bytes(), s>>>(p, final_Ts, final_idx);
+    }
+    GSTEX_LAUNCH_OK("raster_masks_kernel");
     return GSTEX_OK;
 }
 

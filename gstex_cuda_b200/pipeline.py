@@ -128,6 +128,11 @@ class FusedTrainStep:
         # gradients in ONE collective
         self.loss = self.grads["loss"]
         self.has_grad_views = bool(gv)
+        # optional per-step visibility counts (n floats, caller-owned): += 1 per view in which the Gaussian hits a tile
+        self.visible = gv.get("visible")
+        if self.visible is not None and not (self.visible.is_cuda and self.visible.dtype == torch.float32
+                                             and self.visible.numel() == n and self.visible.is_contiguous()):
+            raise RuntimeError("grad_views['visible'] must be a contiguous float32 CUDA tensor of n elements")
         # ---- per-view buffers.  Everything the side stream produces for a view (and the moment lines it consumes)
         # exists twice, so that view k+1 can be prepared while view k is still being rasterised.
         self.sets = [self._make_view_set(f32, i32) for _ in range(2)]
@@ -240,6 +245,8 @@ class FusedTrainStep:
                 self.launches += 1
             self._zero(self.vtex4 if self.C == 3 else self.grads["v_texture"])
         self._zero(self.loss)
+        if self.visible is not None:
+            self._zero(self.visible)
         self._first_view = True
 
     def _prepare(self, v, viewmat: torch.Tensor, c2w: torch.Tensor, first: bool) -> None:
@@ -254,7 +261,8 @@ class FusedTrainStep:
                                                  P(p["sh_coeffs"]), P(v.colors), P(v.mask), s), "sh_colors_forward")
         self._ck(lib.gstex_project_aabb_count(n, P(p["means"]), P(p["scales"]), self.glob_scale, P(p["quats"]), P(viewmat),
                                               fx, fy, cx, cy, H, W, bw, P(v.centers), P(v.extents), P(v.depths),
-                                              P(v.nth), s), "project_aabb_count")
+                                              P(v.nth), 0 if self.visible is None else P(self.visible), s),
+                 "project_aabb_count")
         # fused tile binning: bucket by tile + per-tile shared-memory sort; the intersection count stays on the device
         self._ck(lib.gstex_bin_tiles(n, P(v.centers), P(v.extents), P(v.depths), self.tiles_x, self.tiles_y, bw,
                                      self.cap, P(v.ids_sorted), 0, P(v.tile_bins), P(v.num_isect),

@@ -37,12 +37,16 @@ class GStexTrainStep:
                  intrins: Tuple[float, float, float, float], sh_degree: int = 3, lr: float = 0.01,
                  betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8, grad_scale: float = 1.0,
                  train_mapping: bool = False, rank: int = 0, world_size: int = 1, group=None, check_every: int = 100,
-                 **fused_kwargs):
+                 visible_only: bool = False, **fused_kwargs):
         """``raw``: the leaf parameters (copied into this object's arena; ``self.raw`` are views of it).
         ``train_mapping``: example.py:118 freezes the uv mapping (its gradient is computed, the update skipped).
         ``check_every``: every that many steps (and in ``loss_value()``) the running maximum of the intersection count
         is read back and compared with the preallocated capacity - an overflow would otherwise drop intersections
-        silently, also under CUDA-graph replay (0 disables the periodic check)."""
+        silently, also under CUDA-graph replay (0 disables the periodic check).
+        ``visible_only``: the optimiser touches only Gaussians that hit at least one tile in at least one view of the
+        step (on any rank) - parameters and both Adam moments of the others stay as they are ("sparse /
+        visible-only update").  The per-step visibility counts ride in the gradient arena, so the one all-reduce sums
+        them too."""
         self.lib = _lib.load()
         dev = raw["means"].device
         if dev.type != "cuda":
@@ -60,7 +64,7 @@ class GStexTrainStep:
         # all-reduce of the gradient arena sums the loss in the same collective
         self.fields: List[Tuple[str, Tuple[int, ...]]] = [
             ("means", (n, 3)), ("scales", (n, 3)), ("quats", (n, 4)), ("opacities", (n, 1)), col, ("texture", (X, 3)),
-            ("mapping", (n, 1, 4)), ("loss", (1,))]
+            ("mapping", (n, 1, 4)), ("loss", (1,)), ("visible", (n,))]
         pad = lambda sz: -(-sz // 64) * 64  # noqa: E731  (fields start on 256-byte boundaries: vector accesses)
         total = sum(pad(math.prod(shp)) for _, shp in self.fields)
         f32 = dict(dtype=torch.float32, device=dev)
@@ -72,13 +76,30 @@ class GStexTrainStep:
         for name, shp in self.fields:
             sz = math.prod(shp)
             self.raw_grads[name] = self.grad_arena[off:off + sz].view(*shp)
-            if name != "loss":
+            if name not in ("loss", "visible"):
                 if tuple(raw[name].shape) != shp:
                     raise RuntimeError(f"raw[{name!r}] must have shape {shp}, got {tuple(raw[name].shape)}")
                 self.raw[name] = self.param_arena[off:off + sz].view(*shp)
                 self.raw[name].copy_(raw[name])
             off += pad(sz)
-        self.n_train = total - pad(1) - (0 if train_mapping else pad(n * 4))
+        self.n_train = total - pad(n) - pad(1) - (0 if train_mapping else pad(n * 4))
+        self.visible_only, self.train_mapping = bool(visible_only), bool(train_mapping)
+        # texel -> Gaussian for the visible-only update: a uniform layout (every Gaussian owns th*tw consecutive texels,
+        # example.py:139-143) needs no table
+        self._tex_unit, self._tex_owner = 3, None
+        if self.visible_only:
+            d = texture_dims.to(torch.int64)
+            per = d[:, 0] * d[:, 1]
+            if n > 0 and bool((per == per[0]).all()) and bool((d[:, 2] == torch.arange(n, device=d.device) * per[0]).all()) \
+                    and int(per[0]) * n == X:
+                self._tex_unit = 3 * int(per[0])
+            else:
+                owner = torch.full((X,), 0, dtype=torch.int32, device=dev)
+                idx = torch.repeat_interleave(torch.arange(n, device=dev), per)
+                pos = torch.repeat_interleave(d[:, 2], per) + (torch.arange(int(per.sum()), device=dev)
+                                                                - torch.repeat_interleave(torch.cumsum(per, 0) - per, per))
+                owner[pos] = idx.to(torch.int32)
+                self._tex_owner = owner
         self.check_every = int(check_every)
         self.n, self.X = n, X
         self.lr, self.betas, self.eps, self.grad_scale = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(grad_scale)
@@ -94,6 +115,8 @@ class GStexTrainStep:
                         umap=torch.empty((n, 1, 3), **f32), vmap=torch.empty((n, 1, 3), **f32))
         params = dict(self.act, means=self.raw["means"], texture=self.raw["texture"])
         grad_views = dict(v_means=self.raw_grads["means"], v_texture=self.raw_grads["texture"], loss=self.raw_grads["loss"])
+        if self.visible_only:
+            grad_views["visible"] = self.raw_grads["visible"]
         if self.use_sh:
             params["sh_coeffs"] = self.raw["sh_coeffs"]
             grad_views["v_sh_coeffs"] = self.raw_grads["sh_coeffs"]
@@ -150,10 +173,29 @@ class GStexTrainStep:
         corrections live on the device, so the call is the same every iteration (and CUDA-graph replayable)."""
         self.step_count += 1
         P = lambda t: t.data_ptr()  # noqa: E731
-        _lib.check(self.lib.gstex_adam_step_device(self.n_train, P(self.param_arena), P(self.grad_arena), P(self.exp_avg),
-                                                   P(self.exp_avg_sq), self.lr, self.betas[0], self.betas[1], self.eps,
-                                                   P(self.adam_state), self.grad_scale, self._s()), "adam_step")
-        self.launches += 2
+        if not self.visible_only:
+            _lib.check(self.lib.gstex_adam_step_device(self.n_train, P(self.param_arena), P(self.grad_arena), P(self.exp_avg),
+                                                       P(self.exp_avg_sq), self.lr, self.betas[0], self.betas[1], self.eps,
+                                                       P(self.adam_state), self.grad_scale, self._s()), "adam_step")
+            self.launches += 2
+            return
+        # visible-only: one counter advance, then one row-gated launch per field of the arena
+        _lib.check(self.lib.gstex_adam_prepare_device(P(self.adam_state), self.lr, self.betas[0], self.betas[1], self.eps,
+                                                      self.grad_scale, self._s()), "adam_prepare")
+        vis = self.raw_grads["visible"]
+        base = self.param_arena.data_ptr()
+        for name, shp in self.fields:
+            if name in ("loss", "visible") or (name == "mapping" and not self.train_mapping):
+                continue
+            t = self.raw[name]
+            off = t.data_ptr() - base
+            unit, owner = (self._tex_unit, self._tex_owner) if name == "texture" else (t.numel() // self.n, None)
+            _lib.check(self.lib.gstex_adam_apply_rows_device(
+                t.numel(), t.data_ptr(), self.grad_arena.data_ptr() + off, self.exp_avg.data_ptr() + off,
+                self.exp_avg_sq.data_ptr() + off, P(self.adam_state), P(vis), unit, 0 if owner is None else P(owner),
+                self._s()), f"adam_apply_rows[{name}]")
+            self.launches += 1
+        self.launches += 1
 
     def step(self, cameras, targets) -> torch.Tensor:
         loss = self.forward_backward(cameras, targets)

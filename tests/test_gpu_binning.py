@@ -155,7 +155,7 @@ def test_fused_project_aabb_count_matches_separate_calls():
     depths = torch.empty((n,), device=DEV); nth = torch.empty((n,), dtype=torch.int32, device=DEV)
     rc = _lib.load().gstex_project_aabb_count(n, s["means"].data_ptr(), s["scales"].data_ptr(), 1.0, s["quats"].data_ptr(),
                                               s["viewmat"].data_ptr(), fx, fy, cx, cy, H, W, bw, centers.data_ptr(),
-                                              extents.data_ptr(), depths.data_ptr(), nth.data_ptr(),
+                                              extents.data_ptr(), depths.data_ptr(), nth.data_ptr(), 0,
                                               torch.cuda.current_stream().cuda_stream)
     assert rc == 0, _lib.last_error()
     c2, e2 = A.get_aabb_2d(s["means"], s["scales"], 1.0, s["quats"], s["viewmat"], s["intrins"])

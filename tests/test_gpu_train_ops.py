@@ -303,3 +303,60 @@ def test_cuda_graph_replay_matches_eager_steps():
     print(f"  BASELINE config 2 optimiser step: eager {t_e:.0f} us, CUDA graph replay {t_g:.0f} us "
           f"({eager.total_launches // max(1, eager.step_count)} launches -> 1)")
     assert t_g < t_e
+
+
+@pytest.mark.parametrize("jagged", [False, True])
+def test_visible_only_adam_leaves_unseen_gaussians_untouched(jagged):
+    """SURVEY 8f rank 3, "sparse / visible-only update": with visible_only=True the optimiser touches only Gaussians that
+    hit a tile in some view of the step.  Step 1 sees every Gaussian; step 2 looks at the right half of the scene only.
+    A dense Adam keeps moving the unseen Gaussians on their momentum in step 2; the visible-only one leaves their
+    parameters and both moments bit-for-bit alone, and updates the seen ones exactly like the dense one."""
+    N, H, W, th, tw = 400, 96, 128, 3, 2
+    raw, dims, intr = example_raw(N, H, W, th, tw, seed=13)
+    if jagged:  # a permuted texel layout: the texel -> Gaussian table path
+        perm = torch.randperm(N, generator=torch.Generator().manual_seed(1)).to(DEV)
+        dims = dims.clone()
+        dims[:, 2] = (perm * th * tw).to(torch.int32)
+    vm1 = torch.eye(4, device=DEV)
+    vm1[2, 3] = 8.0
+    vm2 = vm1.clone()
+    vm2[0, 3] = -14.0  # scene shifted far left in view space: only its right-hand part stays on screen
+    cams1 = [(vm1.contiguous(), torch.linalg.inv(vm1).contiguous())]
+    cams2 = [(vm2.contiguous(), torch.linalg.inv(vm2).contiguous())]
+    targets = [torch.rand(H, W, 3, generator=torch.Generator().manual_seed(5)).to(DEV)]
+    bg = torch.zeros(3, device=DEV)
+    mk = lambda vis: GStexTrainStep(raw, dims, H, W, intrins=intr, lr=0.01, background=bg, visible_only=vis)  # noqa: E731
+    sparse, dense = mk(True), mk(False)
+    for t in (sparse, dense):
+        t.step(cams1, targets)
+    seen1 = sparse.raw_grads["visible"].clone()
+    assert float((seen1 > 0).float().mean()) > 0.9
+    after1 = {k: v.clone() for k, v in sparse.raw.items()}
+    m1, v1 = sparse.exp_avg.clone(), sparse.exp_avg_sq.clone()
+    for t in (sparse, dense):
+        t.step(cams2, targets)
+    torch.cuda.synchronize()
+    seen2 = sparse.raw_grads["visible"] > 0
+    frac = float(seen2.float().mean())
+    print(f"  visible in step 2: {frac:.2f} of the Gaussians")
+    assert 0.05 < frac < 0.8
+    unseen = ~seen2
+    moved_dense = 0.0
+    for k in ("means", "scales", "quats", "opacities", "rgbs"):
+        a, b, d = sparse.raw[k], after1[k], dense.raw[k]
+        assert torch.equal(a[unseen], b[unseen]), f"{k}: an unseen Gaussian was updated"
+        moved_dense = max(moved_dense, float((d[unseen] - b[unseen]).abs().max()))
+        bad = (a[seen2] - d[seen2]).abs() > 2e-4 + 1e-4 * d[seen2].abs()
+        assert float(bad.float().mean()) <= 5e-3, f"{k}: seen Gaussians differ from the dense update"
+    assert moved_dense > 1e-4  # the dense optimiser did move them (momentum): the gate is what kept them still
+    # texels and both moments of unseen Gaussians
+    tex_owner = torch.empty(N * th * tw, dtype=torch.long, device=DEV)
+    for_g = (dims[:, 2].long()[:, None] + torch.arange(th * tw, device=DEV)[None, :])
+    tex_owner[for_g.reshape(-1)] = torch.arange(N, device=DEV).repeat_interleave(th * tw)
+    tex_unseen = unseen[tex_owner]
+    assert torch.equal(sparse.raw["texture"][tex_unseen], after1["texture"][tex_unseen])
+    off = sparse.raw["means"].data_ptr() - sparse.param_arena.data_ptr()
+    sl = slice(off // 4, off // 4 + 3 * N)
+    assert torch.equal(sparse.exp_avg[sl].view(N, 3)[unseen], m1[sl].view(N, 3)[unseen])
+    assert torch.equal(sparse.exp_avg_sq[sl].view(N, 3)[unseen], v1[sl].view(N, 3)[unseen])
+    assert sparse.step_count == dense.step_count == 2
