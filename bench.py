@@ -503,13 +503,15 @@ def run_e2e(args, scene, cams, mine, targets_host, dev, world, views):
     H, W, bw, intr = args.height, args.width, 16, scene["intrins"]
     leaves = {k: scene[k].clone().requires_grad_(True) for k in
               ("means", "scales", "quats", "opacities", "sh_coeffs", "uv0", "umap", "vmap", "texture")}
-    # the leaves' gradients are views of ONE flat buffer (autograd accumulates into them in place), so that the
-    # data-parallel reduction is one collective, as in the fused step
-    flat = torch.zeros(sum(t.numel() for t in leaves.values()), device=dev)
-    off = 0
-    for t in leaves.values():
-        t.grad = flat[off:off + t.numel()].view_as(t)
-        off += t.numel()
+    # with several ranks the leaves' gradients are views of ONE flat buffer (autograd accumulates into them in place), so
+    # that the data-parallel reduction is one collective, as in the fused step; a single rank lets autograd place them
+    flat = None
+    if world > 1:
+        flat = torch.zeros(sum(t.numel() for t in leaves.values()), device=dev)
+        off = 0
+        for t in leaves.values():
+            t.grad = flat[off:off + t.numel()].view_as(t)
+            off += t.numel()
     cap = int(12 * args.points * max(1.0, args.scale_mult ** 2))
     cams_host = [(a.cpu().pin_memory(), b.cpu().pin_memory()) for a, b in cams]
     h2d = sum(targets_host[v].numel() * 4 + 2 * 64 for v in mine)
@@ -569,7 +571,11 @@ def run_e2e(args, scene, cams, mine, targets_host, dev, world, views):
         loss_ready[k].record()
         val = read_pending()
         state["pending"], state["k"] = k, state["k"] + 1
-        flat.zero_()
+        if flat is not None:
+            flat.zero_()
+        else:
+            for t in leaves.values():
+                t.grad = None
         return val
 
     steps = max(3, min(args.steps, 10))

@@ -75,8 +75,10 @@ constexpr int FWD_BATCH = GSTEX_FWD_BATCH;  // records per shared-memory stage (
 constexpr int FWD_STAGES = 3;
 constexpr int FWD_WARPS = RASTER_MAX_THREADS / 32;
 
-constexpr size_t fwd_smem_bytes() { return sizeof(float4) * FWD_STAGES * FWD_BATCH * REC_PITCH + (size_t)FWD_WARPS * FWD_BATCH; }
-static_assert(fwd_smem_bytes() + 1024 <= 227 * 1024 / GSTEX_FWD_MINB, "forward stage buffers exceed the per-CTA shared memory budget");
+// dynamic shared memory: the stage buffers; the per-warp survivor lists are static (their address is a compile-time
+// constant: no shared-window base to re-derive inside the survivor walk)
+constexpr size_t fwd_smem_bytes() { return sizeof(float4) * FWD_STAGES * FWD_BATCH * REC_PITCH; }
+static_assert(fwd_smem_bytes() + (size_t)FWD_WARPS * FWD_BATCH + 1024 <= 227 * 1024 / GSTEX_FWD_MINB, "forward stage buffers exceed the per-CTA shared memory budget");
 static_assert(FWD_BATCH % 4 == 0 && FWD_BATCH <= 256, "stage size");
 
 // Shared prologue of one stage iteration: issue stage b+1, wait for stage b, CTA barrier.  Returns false when every
@@ -99,15 +101,76 @@ __device__ __forceinline__ bool fwd_stage_advance(float4 (*stage)[FWD_BATCH * RE
     return __syncthreads_count(done) < p.nthreads;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Stage pipeline of the forward kernel (GSTEX_FWD_PIPE = 1): bulk asynchronous copies + mbarriers instead of cp.async +
+// one CTA barrier per stage.  A record is 128 contiguous bytes gathered through gaussian_ids_sorted, so a stage is
+// FWD_BATCH independent `cp.async.bulk.shared.global` copies (one per record, issued by the lanes of warp 0) that
+// complete on the stage's FULL mbarrier (expect-tx byte counting); a warp that finished a stage arrives on its EMPTY
+// mbarrier, and warp 0 refills a slot - one stage ahead, as before - once every warp has released the stage that held
+// it TWO iterations ago.  Warps therefore wait only for data, never for each other's progress through the current stage
+// (the per-stage CTA barrier was 10.7 % of the kernel's stall samples).
+// ------------------------------------------------------------------------------------------------------------------
+#ifndef GSTEX_FWD_PIPE
+#define GSTEX_FWD_PIPE 1
+#endif
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Whole-warp wait for the phase, abandoned when `*flag` reaches `target` (every warp of the CTA finished: nothing more
+// will arrive).  The verdict is made warp-uniform: if any lane gave up, all do.
+__device__ __forceinline__ bool mbar_wait_unless(uint64_t *bar, uint32_t parity, const volatile int *flag, int target) {
+    bool ok = true;
+    while (!mbar_try_wait(bar, parity))
+        if (*flag >= target) {
+            ok = false;
+            break;
+        }
+    return __all_sync(0xffffffffu, ok);
+}
+__device__ __forceinline__ bool flag_reached(const volatile int *flag, int target) {  // warp-uniform read
+    return __shfl_sync(0xffffffffu, *flag, 0) >= target;
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// Issued by ONE warp (warp 0 stages for the whole CTA, so that "is there a next stage" is one warp's decision and no
+// thread that left early can leave a phase incomplete): its lanes copy the stage's records, lane 0 posts the byte count.
+__device__ __forceinline__ void issue_stage_bulk(float4 *__restrict__ dst, const float4 *__restrict__ recs,
+                                                 const int32_t *__restrict__ ids, int first, int cnt, int lane,
+                                                 uint64_t *full) {
+    for (int r = lane; r < cnt; r += 32)
+        bulk_copy_g2s(dst + quad_slot(r, 0), recs + (size_t)ids[first + r] * 8, sizeof(float) * REC_FLOATS, full);
+    if (lane == 0) mbar_arrive_expect_tx(full, (uint32_t)cnt * (uint32_t)(sizeof(float) * REC_FLOATS));
+}
+
 template <bool BLUR>
 __global__ void __launch_bounds__(RASTER_MAX_THREADS, GSTEX_FWD_MINB) raster_masks_kernel(const RasterCommon p,
                                                                                           const float *__restrict__ final_Ts,
                                                                                           const int32_t *__restrict__ final_idx) {
     extern __shared__ __align__(16) unsigned char fwd_smem[];
     float4 (*stage)[FWD_BATCH * REC_PITCH] = reinterpret_cast<float4 (*)[FWD_BATCH * REC_PITCH]>(fwd_smem);
-    uint8_t *const surv_base = fwd_smem + sizeof(float4) * FWD_STAGES * FWD_BATCH * REC_PITCH;
+    __shared__ uint8_t survivors[FWD_WARPS][FWD_BATCH];
     const int tr = threadIdx.x, lane = tr & 31, warp = tr >> 5;
-    uint8_t *__restrict__ my_list = surv_base + warp * FWD_BATCH;
+    uint8_t *__restrict__ my_list = survivors[warp];
     const int tile = blockIdx.y * p.tiles_x + blockIdx.x;
     int lx, ly;
     tile_pixel(p.bw, tr, lx, ly);
@@ -153,10 +216,10 @@ template <bool C3, bool BLUR, bool VIS>
 __global__ void __launch_bounds__(RASTER_MAX_THREADS, GSTEX_FWD_MINB) raster_forward_kernel(const RasterCommon p, const ForwardOut o) {
     extern __shared__ __align__(16) unsigned char fwd_smem[];
     float4 (*stage)[FWD_BATCH * REC_PITCH] = reinterpret_cast<float4 (*)[FWD_BATCH * REC_PITCH]>(fwd_smem);
-    uint8_t *const surv_base = fwd_smem + sizeof(float4) * FWD_STAGES * FWD_BATCH * REC_PITCH;
+    __shared__ uint8_t survivors[FWD_WARPS][FWD_BATCH];
 
     const int tr = threadIdx.x, lane = tr & 31, warp = tr >> 5;
-    uint8_t *__restrict__ my_list = surv_base + warp * FWD_BATCH;
+    uint8_t *__restrict__ my_list = survivors[warp];
     const int tile = blockIdx.y * p.tiles_x + blockIdx.x;
     int lx, ly;
     tile_pixel(p.bw, tr, lx, ly);
@@ -189,12 +252,59 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, GSTEX_FWD_MINB) raster_for
     int last = 0, dlast = -1;
     bool done = !inside;
 
+#if GSTEX_FWD_PIPE
+    __shared__ __align__(8) uint64_t full_bar[FWD_STAGES], empty_bar[FWD_STAGES];
+    __shared__ int warps_done;  // warps whose 32 pixels are all finished
+    const int nwarps = p.nthreads >> 5;
+    if (tr == 0) {
+        for (int k = 0; k < FWD_STAGES; ++k) {
+            mbar_init(&full_bar[k], 1);
+            mbar_init(&empty_bar[k], nwarps);
+        }
+        warps_done = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    bool warp_done = false;
+    int last_issued = -1;  // warp 0: the last stage it issued
+    if (warp == 0 && nbatch > 0) {
+        issue_stage_bulk(stage[0], p.recs, p.ids, range.x, min(FWD_BATCH, total), lane, &full_bar[0]);
+        last_issued = 0;
+    }
+#else
     if (nbatch > 0) stage_records(stage[0], p.recs, p.ids, range.x, min(FWD_BATCH, total), tr, p.nthreads);
+#endif
 
     for (int b = 0; b < nbatch; ++b) {
         const int first = range.x + b * FWD_BATCH;
         const int cnt = min(FWD_BATCH, range.y - first);
+#if GSTEX_FWD_PIPE
+        // warp 0: stage b+1 goes into the slot that held stage b-2, once every warp has released that stage
+        if (warp == 0 && b + 1 < nbatch) {
+            const int slot = (b + 1) % FWD_STAGES;
+            if (b >= 2 && !mbar_wait_unless(&empty_bar[slot], (uint32_t)(((b - 2) / FWD_STAGES) & 1), &warps_done, nwarps)) break;
+            if (flag_reached(&warps_done, nwarps)) break;
+            issue_stage_bulk(stage[slot], p.recs, p.ids, first + FWD_BATCH, min(FWD_BATCH, range.y - first - FWD_BATCH), lane,
+                             &full_bar[slot]);
+            last_issued = b + 1;
+            // the ids of stage b+2 start travelling now: the next issue begins with a dependent load of them
+            if (lane < (FWD_BATCH + 31) / 32 && first + 2 * FWD_BATCH + 32 * lane < range.y)
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(p.ids + first + 2 * FWD_BATCH + 32 * lane));
+        }
+        if (warp_done) {
+            // nothing left to composite for this warp: it only keeps releasing the stages - never ahead of the phase
+            // its arrival belongs to (an arrival for stage b may only land once the slot's phase of stage b-3 is over)
+            if (b >= FWD_STAGES && !mbar_wait_unless(&empty_bar[b % FWD_STAGES], (uint32_t)(((b - FWD_STAGES) / FWD_STAGES) & 1),
+                                                     &warps_done, nwarps))
+                break;
+            if (flag_reached(&warps_done, nwarps)) break;
+            if (lane == 0) mbar_arrive(&empty_bar[b % FWD_STAGES]);
+            continue;
+        }
+        if (!mbar_wait_unless(&full_bar[b % FWD_STAGES], (uint32_t)((b / FWD_STAGES) & 1), &warps_done, nwarps)) break;
+#else
         if (!fwd_stage_advance(stage, p, range, b, nbatch, tr, done)) break;
+#endif
         const float4 *__restrict__ S = stage[b % FWD_STAGES];
         if (C3 && tr < cnt) {  // one thread per staged record: start fetching its texture block
             const float4 q3 = S[quad_slot(tr, 3)], q6 = S[quad_slot(tr, 6)];
@@ -280,8 +390,25 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, GSTEX_FWD_MINB) raster_for
                 last = first + i;
             }
         }
+#if GSTEX_FWD_PIPE
+        // release the stage; a warp whose pixels are all finished says so once (the CTA stops staging when all have)
+        warp_done = __all_sync(0xffffffffu, done);
+        __syncwarp();
+        if (lane == 0) {
+            if (warp_done) atomicAdd(&warps_done, 1);
+            mbar_arrive(&empty_bar[b % FWD_STAGES]);
+        }
+#endif
     }
+#if GSTEX_FWD_PIPE
+    // no bulk copy may still be in flight towards this CTA's shared memory when it is retired: an early exit (every
+    // pixel finished) can leave the last one or two issued stages unread.  Warp 0 issued them; it stays until they landed.
+    for (int j = max(0, last_issued - 1); j <= last_issued; ++j)
+        while (!mbar_try_wait(&full_bar[j % FWD_STAGES], (uint32_t)((j / FWD_STAGES) & 1))) {
+        }
+#else
     __pipeline_wait_prior(0);
+#endif
 
     if (inside) {
         const int pix = row * p.img_w + col;
