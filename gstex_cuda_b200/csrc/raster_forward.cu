@@ -103,16 +103,19 @@ __device__ __forceinline__ bool fwd_stage_advance(float4 (*stage)[FWD_BATCH * RE
 
 
 // ------------------------------------------------------------------------------------------------------------------
-// Stage pipeline of the forward kernel (GSTEX_FWD_PIPE = 1): bulk asynchronous copies + mbarriers instead of cp.async +
-// one CTA barrier per stage.  A record is 128 contiguous bytes gathered through gaussian_ids_sorted, so a stage is
-// FWD_BATCH independent `cp.async.bulk.shared.global` copies (one per record, issued by the lanes of warp 0) that
-// complete on the stage's FULL mbarrier (expect-tx byte counting); a warp that finished a stage arrives on its EMPTY
-// mbarrier, and warp 0 refills a slot - one stage ahead, as before - once every warp has released the stage that held
-// it TWO iterations ago.  Warps therefore wait only for data, never for each other's progress through the current stage
-// (the per-stage CTA barrier was 10.7 % of the kernel's stall samples).
-// ------------------------------------------------------------------------------------------------------------------
+// Alternative stage pipeline of the forward kernel (GSTEX_FWD_PIPE = 1, NOT the default): bulk asynchronous copies +
+// mbarriers instead of cp.async + one CTA barrier per stage.  A record is 128 contiguous bytes gathered through
+// gaussian_ids_sorted, so a stage is FWD_BATCH independent `cp.async.bulk.shared.global` copies (one per record, issued
+// by the lanes of warp 0) that complete on the stage's FULL mbarrier (expect-tx byte counting); a warp that finished a
+// stage arrives on its EMPTY mbarrier, and warp 0 refills a slot - one stage ahead, as before - once every warp has
+// released the stage that held it TWO iterations ago.  Warps then wait only for data, never for each other's progress
+// through the current stage (the per-stage CTA barrier is 10.7 % of the default build's stall samples).
+// Measured on C4 (B200, same box, parity tests green on both): 1.44 ms against 1.31 ms for the default.  The barrier
+// stall disappears, but the waiting does not - within a tile the slow warp is the same one stage after stage, so one or
+// two stages of slack buy nothing - and waiting on an mbarrier costs instructions (try_wait loop: +80 M warp
+// instructions, 1.20 G against 1.12 G) where waiting at a hardware barrier costs none.  Kept selectable for that record.
 #ifndef GSTEX_FWD_PIPE
-#define GSTEX_FWD_PIPE 1
+#define GSTEX_FWD_PIPE 0
 #endif
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
