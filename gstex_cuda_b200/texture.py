@@ -41,8 +41,11 @@ def texture_gaussians(texture_info: Tuple[int, int, int], texture_dims: Tensor, 
     if colors.ndimension() != 2:
         raise ValueError("colors must have dimensions (N, D)")
     if use_torch_impl:
-        raise NotImplementedError("the pure-PyTorch rasteriser of the reference (gstex_cuda/_torch_impl.py) is its "
-                                  "CPU twin, not part of this build; use the CUDA path")
+        # the slow pure-PyTorch checker (reference texture.py:411-514 over _torch_impl.texture_forward): same binning,
+        # torch autograd instead of the backward kernel
+        return _texture_gaussians_torch(texture_info, texture_dims, centers, extents, depths, num_tiles_hit, colors, opacity,
+                                        means, scales, glob_scale, quats, uv0, umap, vmap, texture, viewmat, c2w, fx, fy, cx,
+                                        cy, img_height, img_width, block_width, settings, background)
     return _TextureGaussians.apply(
         texture_info, texture_dims.contiguous(), centers.contiguous(), extents.contiguous(), depths.contiguous(),
         num_tiles_hit.contiguous(), colors.contiguous(), opacity.contiguous(), means.contiguous(), scales.contiguous(),
@@ -64,6 +67,32 @@ def last_intersect_count(device=None) -> int:
 
 def _p(t) -> int:
     return 0 if t is None else t.data_ptr()
+
+
+def _texture_gaussians_torch(texture_info, texture_dims, centers, extents, depths, num_tiles_hit, colors, opacity, means,
+                             scales, glob_scale, quats, uv0, umap, vmap, texture, viewmat, c2w, fx, fy, cx, cy, img_height,
+                             img_width, block_width, settings, background):
+    """``use_torch_impl=True`` (reference texture.py:411-514): binning through the library (not differentiable, as
+    upstream), rasterisation in plain torch ops (``_torch_impl.texture_forward``), gradients by torch autograd."""
+    from . import _torch_impl as _T
+
+    H, W, bw = int(img_height), int(img_width), int(block_width)
+    tile_bounds = ((W + bw - 1) // bw, (H + bw - 1) // bw, 1)
+    with torch.no_grad():
+        num_intersects, cum = compute_cumulative_intersects(num_tiles_hit.contiguous())
+    if num_intersects < 1:
+        img = torch.ones(H, W, colors.shape[-1], device=centers.device) * background
+        z = torch.zeros(H, W, device=centers.device)
+        return (img, z, z.clone(), z.clone(), torch.zeros(H, W, int(texture_info[2]), device=centers.device),
+                torch.zeros(H, W, 3, device=centers.device))
+    with torch.no_grad():
+        _, _, _, ids_sorted, tile_bins = bin_and_sort_gaussians(means.shape[0], num_intersects, centers.contiguous(),
+                                                                extents.contiguous(), depths.contiguous(), cum,
+                                                                tile_bounds, bw)
+    out_img, out_depth, out_reg, out_texture, out_normal, final_Ts, _ = _T.texture_forward(
+        tile_bounds, (bw, bw, 1), (W, H, 1), texture_info, texture_dims, ids_sorted, tile_bins, colors, opacity, means,
+        scales, glob_scale, quats, uv0, umap, vmap, texture, viewmat, c2w, fx, fy, cx, cy, int(settings), background)
+    return out_img, out_depth, out_reg, 1 - final_Ts, out_texture, out_normal
 
 
 class _TextureGaussians(Function):

@@ -80,6 +80,16 @@ def run(name, iterations):
     torch.cuda.synchronize()
     t_ref = time.perf_counter() - t0
     losses_r = [float(l.split("Loss:")[1]) for l in buf.getvalue().splitlines() if "Loss:" in l]
+    # control: the reference trainer AGAIN from the same seed - its backward sums with atomics in arbitrary order, so two
+    # of its own runs drift apart as well; that drift is the yardstick for "the curves agree"
+    example.seed_everything(1)
+    tr2 = example.SimpleTrainer(gt_image=gt_image(cfg["height"], cfg["width"]), num_points=cfg["num_points"],
+                                num_texels=cfg["num_texels"])
+    buf2 = io.StringIO()
+    with contextlib.redirect_stdout(buf2):
+        tr2.train(iterations=iterations, lr=1e-2, save_imgs=False, torch_compare=False)
+    losses_r2 = [float(l.split("Loss:")[1]) for l in buf2.getvalue().splitlines() if "Loss:" in l]
+    rel_rr = [abs(a - b) / max(abs(b), 1e-12) for a, b in zip(losses_r2, losses_r)]
     lo = losses_o.cpu().tolist()
     rel = [abs(a - b) / max(abs(b), 1e-12) for a, b in zip(lo, losses_r)]
     marks = [i for i in (0, 9, 99, 499, iterations - 1) if i < iterations]
@@ -89,7 +99,11 @@ def run(name, iterations):
            "loss": {"ours": {str(i + 1): lo[i] for i in marks}, "reference": {str(i + 1): losses_r[i] for i in marks},
                     "relative_difference": {str(i + 1): rel[i] for i in marks},
                     "max_relative_difference_first_100": max(rel[:100]), "max_relative_difference": max(rel),
-                    "final_ratio_ours_over_reference": lo[-1] / losses_r[-1]},
+                    "final_ratio_ours_over_reference": lo[-1] / losses_r[-1],
+                    "reference_vs_reference_rerun": {"relative_difference": {str(i + 1): rel_rr[i] for i in marks},
+                                                     "max_relative_difference_first_100": max(rel_rr[:100]),
+                                                     "max_relative_difference": max(rel_rr),
+                                                     "final_ratio": losses_r2[-1] / losses_r[-1]}},
            "max_intersections_seen": int(ours.fused.max_count_seen.item()),
            "note": "same initial parameters, same Adam hyper-parameters; the two runs diverge slowly through fp32 "
                    "summation order (atomics) amplified by 1000 Adam steps"}
