@@ -5,7 +5,8 @@ arena must equal the single-process step over the whole batch.
 """
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-os.environ.pop("NCCL_DEBUG", None)
+if os.environ.get("NCCL_DEBUG"):
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout for the one JSON line
 import torch
 import torch.distributed as dist
 from gstex_cuda_b200.pipeline import FusedTrainStep, DataParallelTrainStep
@@ -18,11 +19,13 @@ dist.init_process_group("nccl", device_id=dev)
 N, W, H, V = 200_000, 960, 544, 8
 s = synthetic_scene(N, W, H, seed=11, device=dev)
 params = {k: s[k] for k in ("means", "scales", "quats", "opacities", "sh_coeffs", "uv0", "umap", "vmap", "texture")}
+# the benchmark's layout: texels at a 16-byte pitch, read and differentiated in place
+params["texture"] = torch.cat([s["texture"], torch.zeros_like(s["texture"][:, :1])], 1).contiguous()
 cams = [(a.to(dev), b.to(dev)) for a, b in arc_cameras(V)]
 g = torch.Generator().manual_seed(3)
 targets = [torch.rand(H, W, 3, generator=g).to(dev) for _ in range(V)]
 mk = lambda: FusedTrainStep(params, s["texture_dims"], H, W, intrins=s["intrins"], sh_degree=3, background=s["background"],
-                            max_intersects=16 * N)
+                            max_intersects=16 * N, texture_rgba=True)
 dp = DataParallelTrainStep(mk(), rank, world)
 loss_dp = dp.step(cams, targets)
 torch.cuda.synchronize()
