@@ -503,6 +503,8 @@ def run_e2e(args, scene, cams, mine, targets_host, dev, world, views):
     H, W, bw, intr = args.height, args.width, 16, scene["intrins"]
     leaves = {k: scene[k].clone().requires_grad_(True) for k in
               ("means", "scales", "quats", "opacities", "sh_coeffs", "uv0", "umap", "vmap", "texture")}
+    if args.texture_layout == "rgba":  # the same layout as the device-resident run: texels at a 16-byte pitch
+        leaves["texture"] = torch.cat([scene["texture"], torch.zeros_like(scene["texture"][:, :1])], 1).contiguous().requires_grad_(True)
     # with several ranks the leaves' gradients are views of ONE flat buffer (autograd accumulates into them in place), so
     # that the data-parallel reduction is one collective, as in the fused step; a single rank lets autograd place them
     flat = None

@@ -115,7 +115,10 @@ class _TextureGaussians(Function):
         n, X = means.shape[0], texture.shape[0]
         _C._check_raster_inputs(texture_dims, None, None, colors, opacity, means, scales, quats, uv0, umap, vmap, texture,
                                 viewmat, c2w, background)
-        if texture.dim() != 2 or texture.shape[1] != C:
+        # (X,4) texels with texture_info[2] == 3: the three channels stored at a 16-byte pitch - read, and differentiated,
+        # in place (no padded copy, no un-padding of the gradient); an opt-in layout beyond the reference's (X,C)
+        rgba = C == 3 and texture.dim() == 2 and texture.shape[1] == 4
+        if texture.dim() != 2 or (texture.shape[1] != C and not rgba):
             raise RuntimeError(f"texture must have dimensions (X, {C})")
         f32, i32 = dict(dtype=torch.float32, device=dev), dict(dtype=torch.int32, device=dev)
         stream = torch.cuda.current_stream(dev)
@@ -136,12 +139,12 @@ class _TextureGaussians(Function):
             final_Ts, final_idx, depth_idx = torch.empty((H, W), **f32), torch.empty((H, W), **i32), torch.empty((H, W), **i32)
             out_reg_s = torch.empty((H, W, 3), **f32)
             recs, mean2d = torch.empty((max(n, 1), 32), **f32), torch.empty((max(n, 1), 2), **f32)
-            tex4 = torch.empty((max(X, 1), 4), **f32) if C == 3 else None
+            tex4 = texture if rgba else (torch.empty((max(X, 1), 4), **f32) if C == 3 else None)
             if n > 0:
                 _lib.check(lib.gstex_pack_records(n, _p(texture_dims), _p(colors), _p(opacity), _p(means), _p(scales),
                                                   float(glob_scale), _p(quats), _p(uv0), _p(umap), _p(vmap), _p(viewmat),
                                                   _p(c2w), fx, fy, cx, cy, _p(recs), _p(mean2d), 0, s), "pack_records")
-            if C == 3 and X > 0:
+            if C == 3 and X > 0 and not rgba:
                 _lib.check(lib.gstex_pad_texture(X, _p(texture), _p(tex4), s), "pad_texture")
             # 3. the count (the reference's one sync per call)
             num_intersects = 0
@@ -209,8 +212,9 @@ class _TextureGaussians(Function):
                             ("v_output_alpha", v_alp), ("v_output_texture", v_tex), ("v_output_normal", v_nrm)):
                 _C._chk(name, t, torch.float32)
             acc = torch.zeros((n, 32), **f32)                       # moment lines (csrc/common.cuh: AccSlot)
-            v_texture = torch.zeros((X, C), **f32) if C != 3 else torch.empty((X, C), **f32)
-            vtex4 = torch.zeros((X, 4), **f32) if C == 3 else None  # padded texel gradients
+            rgba = C == 3 and texture.shape[1] == 4
+            vtex4 = torch.zeros((X, 4), **f32) if C == 3 else None  # texel gradients at a 16-byte pitch
+            v_texture = vtex4 if rgba else (torch.zeros((X, C), **f32) if C != 3 else torch.empty((X, C), **f32))
             v_colors, v_opacity = torch.empty((n, 3), **f32), torch.empty((n, 1), **f32)
             v_means, v_scales, v_quats = torch.empty((n, 3), **f32), torch.empty((n, 3), **f32), torch.empty((n, 4), **f32)
             # shaped like the inputs ((n, num_probs, k) upstream, zero-filled: texture.cu:1004-1006); the kernels address
@@ -234,7 +238,7 @@ class _TextureGaussians(Function):
                                                _p(v_means), _p(v_scales), _p(v_quats), _p(v_uv0), _p(v_umap), _p(v_vmap),
                                                0, s)
                 _lib.check(rc, "raster_epilogue")
-                if C == 3:
+                if C == 3 and not rgba:
                     _lib.check(lib.gstex_unpad_texture_grad(X, _p(vtex4), _p(v_texture), 0, s), "unpad_texture_grad")
             grads = (v_colors, v_opacity, v_means, v_scales, v_quats, v_uv0, v_umap, v_vmap, v_texture)
         v_colors, v_opacity, v_means, v_scales, v_quats, v_uv0, v_umap, v_vmap, v_texture = grads

@@ -209,3 +209,81 @@ def test_fused_image_loss_and_sh_colors_match_torch_glue():
         # a channel within rounding of the clamp can be gated on one side only
         bad = ((g_got - g_ref).abs() > 1e-5 + 1e-4 * g_ref.abs()).float().mean()
         assert float(bad) < 1e-3
+
+
+def _run_api(s, leaves, **kw):
+    H, W, bw, intr = s["H"], s["W"], 16, s["intrins"]
+    _, depths = project_points(leaves["means"], s["viewmat"], intr)
+    centers, extents = get_aabb_2d(leaves["means"], leaves["scales"], 1, leaves["quats"], s["viewmat"], intr)
+    nth = get_num_tiles_hit_2d(centers, extents, H, W, bw)
+    return texture_gaussians(s["texture_info"], s["texture_dims"], centers, extents, depths, nth, leaves["colors"],
+                             leaves["opacities"], leaves["means"], leaves["scales"], 1, leaves["quats"], leaves["uv0"],
+                             leaves["umap"], leaves["vmap"], leaves["texture"], s["viewmat"], s["c2w"], *intr, H, W, bw,
+                             1 << 8, s["background"], **kw)
+
+
+_LEAVES = ("colors", "opacities", "means", "scales", "quats", "uv0", "umap", "vmap", "texture")
+
+
+def test_capacity_mode_equals_the_synchronising_call():
+    """texture_gaussians(..., max_intersects=cap): no host read-back of the intersection count; same images, same
+    gradients as the reference-shaped call, and last_intersect_count() reports what a too-small capacity dropped."""
+    from gstex_cuda_b200 import texture as TX
+    s = random_small_scene(300, 128, 96, seed=17, device=DEV)
+    res = []
+    for kw in ({}, {"max_intersects": 50000}):
+        leaves = {k: s[k].clone().requires_grad_(True) for k in _LEAVES}
+        outs = _run_api(s, leaves, **kw)
+        _loss(outs, s["target"]).backward()
+        res.append((outs, leaves))
+    count = TX.last_intersect_count(DEV)
+    assert 0 < count <= 50000
+    for a, b in zip(res[0][0], res[1][0]):
+        assert torch.equal(a, b)
+    for k in _LEAVES:
+        ga, gb = res[0][1][k].grad, res[1][1][k].grad
+        assert float((ga - gb).abs().max()) <= 1e-5 * float(ga.abs().max()) + 1e-12, k  # atomic order only
+    leaves = {k: s[k].clone() for k in _LEAVES}
+    _run_api(s, leaves, max_intersects=count // 2)  # deliberately too small: detectable, no crash
+    assert TX.last_intersect_count(DEV) == count > count // 2
+
+
+def test_use_torch_impl_agrees_with_the_kernels_like_example_torch_compare():
+    """use_torch_impl=True runs the package's pure-PyTorch rasteriser over the same binning (reference texture.py:117,
+    :411-514).  On a case without alpha-cap or stop-rule activity (where the torch twin's semantics coincide with the
+    kernels', as in example.py --torch_compare) outputs and autograd gradients match the CUDA path."""
+    s = random_small_scene(40, 48, 32, seed=23, device=DEV, jagged=True)
+    s["opacities"] = (0.6 * s["opacities"]).contiguous()
+    res = []
+    for flag in (False, True):
+        leaves = {k: s[k].clone().requires_grad_(True) for k in _LEAVES}
+        outs = _run_api(s, leaves, use_torch_impl=flag)
+        _loss(outs, s["target"]).backward()
+        res.append((outs, leaves))
+    for k, a, b in zip(("out_img", "out_depth", "out_reg", "out_alpha", "out_texture", "out_normal"), res[0][0], res[1][0]):
+        assert_close_frac(k, to_np(a), to_np(b), 1e-4, 2e-5, 5e-3)
+    for k in _LEAVES:
+        ref, got = to_np(res[1][1][k].grad), to_np(res[0][1][k].grad)
+        assert_close_frac("grad " + k, got, ref, 2e-3, 1e-9 + 2e-4 * float(np.abs(ref).max()), 5e-3, 12, 0.1)
+
+
+def test_rgba_texture_layout_through_the_autograd_api():
+    """texture (X,4) with texture_info[2] == 3: the same images and gradients as the (X,3) texture, without the padding
+    passes; the gradient comes back (X,4) with a zero fourth column."""
+    s = random_small_scene(200, 96, 64, seed=29, device=DEV)
+    res = []
+    for rgba in (False, True):
+        leaves = {k: s[k].clone().requires_grad_(True) for k in _LEAVES}
+        if rgba:
+            leaves["texture"] = torch.cat([s["texture"], torch.zeros_like(s["texture"][:, :1])], 1).contiguous().requires_grad_(True)
+        outs = _run_api(s, leaves)
+        _loss(outs, s["target"]).backward()
+        res.append((outs, leaves))
+    for a, b in zip(res[0][0], res[1][0]):
+        assert torch.equal(a, b)
+    g3, g4 = res[0][1]["texture"].grad, res[1][1]["texture"].grad
+    assert g4.shape == (s["texture"].shape[0], 4) and float(g4[:, 3].abs().max()) == 0.0
+    assert float((g4[:, :3] - g3).abs().max()) <= 1e-5 * float(g3.abs().max()) + 1e-12
+    for k in _LEAVES[:-1]:
+        ga, gb = res[0][1][k].grad, res[1][1][k].grad
+        assert float((ga - gb).abs().max()) <= 1e-5 * float(ga.abs().max()) + 1e-12, k
