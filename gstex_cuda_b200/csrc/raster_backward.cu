@@ -156,11 +156,7 @@ __device__ __forceinline__ void pair_rows(const RasterCommon &p, const BackwardI
             const float vv0 = vis * px.vt0, vv1 = vis * px.vt1, vv2 = vis * px.vt2;
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-#ifdef GSTEX_EXP_NO_TEXRED
-                if (tf.w[k] == 12345.f)
-#else
                 if (tf.w[k] != 0.f)
-#endif
                     atomicAdd(o.vtex4 + tf.idx[k], make_float4(tf.w[k] * vv0, tf.w[k] * vv1, tf.w[k] * vv2, 0.f));
         } else {
             const float *__restrict__ vtp = in.v_tex + (size_t)fl.C * px.pix;
@@ -431,11 +427,7 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, GSTEX_BWD_MINB) raster_bac
                             pair_rows<C3, BLUR>(p, in, o, fl, q0, q3, q4, q5, q6, pe, pc, me, alpha * T, v_alpha, gu, gv,
                                                 idx == me.dfinal && me.dfinal != -1, r);
                         }
-#ifdef GSTEX_EXP_NO_BUTTERFLY  // timing experiment only (wrong gradients): what the moment reduction costs
-                        const float tot = r[0].x + r[1].y + r[2].z + r[3].w + r[4].x + r[5].y + r[6].z;
-#else
                         const float tot = warp_reduce_slots(r, lane);
-#endif
                         if (lane < (BLUR ? 30 : 28))  // one 4-byte reduction per lane, 112 contiguous bytes of the moment line
                             atomicAdd(reinterpret_cast<float *>(o.acc) + (size_t)__float_as_int(q2.w) * 32 + lane, tot);
                     } else {
