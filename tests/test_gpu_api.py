@@ -251,9 +251,16 @@ def test_capacity_mode_equals_the_synchronising_call():
 def test_use_torch_impl_agrees_with_the_kernels_like_example_torch_compare():
     """use_torch_impl=True runs the package's pure-PyTorch rasteriser over the same binning (reference texture.py:117,
     :411-514).  On a case without alpha-cap or stop-rule activity (where the torch twin's semantics coincide with the
-    kernels', as in example.py --torch_compare) outputs and autograd gradients match the CUDA path."""
+    kernels', as in example.py --torch_compare) outputs and autograd gradients match the CUDA path.
+    The uv maps are shrunk so that every blended pixel samples strictly inside the unit square: the reference's two
+    rasterisers themselves disagree where u or v is clamped - its CUDA backward keeps the uv gradient there
+    (texture.cu:608-609 clamps, texture_helpers.cuh:252-300 differentiates regardless), torch.clamp in its twin
+    (_torch_impl.py:337-338) zeroes it - and the kernels follow the CUDA one (tests/test_oracle_golden.py pins the
+    oracle on both sides of that line: test_uv_clamp_gradient_follows_the_reference_cuda)."""
     s = random_small_scene(40, 48, 32, seed=23, device=DEV, jagged=True)
     s["opacities"] = (0.6 * s["opacities"]).contiguous()
+    s["umap"], s["vmap"] = (0.12 * s["umap"]).contiguous(), (0.12 * s["vmap"]).contiguous()
+    s["uv0"] = torch.full_like(s["uv0"], 0.5)
     res = []
     for flag in (False, True):
         leaves = {k: s[k].clone().requires_grad_(True) for k in _LEAVES}

@@ -88,12 +88,61 @@ def _c1_iterations_asserted_equal(mod, capsys):
     return sum(1 for l in out.splitlines() if l.startswith("Iteration ")), err
 
 
+PARAMS = ("means", "scales", "quats", "rgbs", "opacities", "mapping", "texture")
+OUTS = ("out_img", "out_depth", "out_reg", "out_alpha", "out_texture", "out_normal")
+
+
+def three_way_c1(iters=10):
+    """On IDENTICAL parameters, every iteration of upstream's C1 trainer: the reference's pure-PyTorch rasteriser (twin), the
+    unmodified reference CUDA extension and this repo's kernels, all driven by the reference's own Python layer.  Returns per
+    iteration the pairwise max |d| of the six outputs and max |d| / max |g| of the seven parameter gradients.  Adam steps on
+    OUR gradients (upstream's optimiser settings)."""
+    import gstex_cuda_b200.cuda as backend
+
+    ex_ours = _load_example(backend)
+    ext = _reference_extension()
+    assert ext is not None, "oracle/_ref/gstex_ref_C.so missing"
+    ex_ref = _load_example(ext)
+    ex_ours.seed_everything(1)
+    tr = ex_ours.SimpleTrainer(gt_image=_gt(32, 32), num_points=10, num_texels=1000000)
+    tr_ref = ex_ref.SimpleTrainer(gt_image=_gt(32, 32), num_points=10, num_texels=1000000)
+    for k in PARAMS + ("viewmat", "c2w", "background"):
+        setattr(tr_ref, k, getattr(tr, k))  # the same tensors
+    opt = torch.optim.Adam([getattr(tr, k) for k in PARAMS], 1e-2)
+    timer = ex_ours.Timer(disabled=True)
+
+    def one(trainer, torch_impl):
+        opt.zero_grad()
+        outs = trainer.forward(timer, use_torch_impl=torch_impl)
+        trainer.compute_loss(outs, trainer.gt_image).backward()
+        grads = [getattr(tr, k).grad.detach().clone() if getattr(tr, k).grad is not None
+                 else torch.zeros_like(getattr(tr, k)) for k in PARAMS]
+        return [o.detach().clone() for o in outs], grads
+
+    rows = []
+    for it in range(iters):
+        twin, ref, mine = one(tr, True), one(tr_ref, False), one(tr, False)  # ours last: Adam steps on its gradients
+        row = {"iteration": it + 1}
+        for name, (a, b) in (("ours_vs_twin", (mine, twin)), ("ref_vs_twin", (ref, twin)), ("ours_vs_ref", (mine, ref))):
+            d = {k: float((x - y).abs().max()) for k, x, y in zip(OUTS, a[0], b[0])}
+            d.update({"grad_" + k: float((x - y).abs().max() / (y.abs().max() + 1e-30))
+                      for k, x, y in zip(PARAMS, a[1], b[1])})
+            row[name] = d
+        rows.append(row)
+        opt.step()
+    return rows
+
+
 def test_c1_torch_compare_through_the_reference_python(staged, capsys):
     """Upstream warns that its CUDA and torch rasterisers drift apart after a few Adam steps ("for < 10 iterations these
-    generally don't affect the renders and gradients", example.py main docstring) - the torch twin caps alpha at 0.999,
-    the kernels at 0.99 - and asserts with torch.testing's default fp32 tolerances (rtol 1.3e-6, atol 1e-5).  The bar here:
-    outputs AND all gradients pass upstream's own assert for at least the first 5 iterations, and for at least as many
-    iterations as the reference's own CUDA extension manages under the same trainer on this GPU."""
+    generally don't affect the renders and gradients", example.py main docstring) and asserts with torch.testing's default
+    fp32 tolerances (rtol 1.3e-6, atol 1e-5).  Measured on identical parameters (tools/c1_compare_diag.py), the reference's
+    OWN extension sits 3e-6 ... 8e-6 from its twin on the outputs - so whether an iteration clears atol 1e-5 depends on the
+    atomic order of the backward that produced the parameters.  The bars here:
+      (1) upstream's trainer, unmodified, over our backend: outputs AND all gradients pass its own assert for at least the
+          first 5 iterations (the count the reference extension reaches is printed beside ours);
+      (2) on identical parameters, all 10 iterations: our kernels are no further from the twin than the reference extension
+          is, up to a factor 2 (outputs, absolute) / 3 (gradients, relative to max |g|) and a floor of fp32 rounding."""
     import gstex_cuda_b200.cuda as backend
 
     n_ours, err_ours = _c1_iterations_asserted_equal(_load_example(backend), capsys)
@@ -106,8 +155,19 @@ def test_c1_torch_compare_through_the_reference_python(staged, capsys):
         if err_ref:
             print("  reference, first failing assert:", " ".join(err_ref.split())[:260])
     assert n_ours >= 5
-    if n_ref is not None:
-        assert n_ours >= min(n_ref, 10) - 1
+    if ext is None:
+        return
+    rows = three_way_c1(10)
+    worst = lambda name, pick: max(v for r in rows for k, v in r[name].items() if pick(k))  # noqa: E731
+    is_out, is_grad = (lambda k: not k.startswith("grad_")), (lambda k: k.startswith("grad_"))
+    o_ours, o_ref = worst("ours_vs_twin", is_out), worst("ref_vs_twin", is_out)
+    g_ours, g_ref = worst("ours_vs_twin", is_grad), worst("ref_vs_twin", is_grad)
+    with capsys.disabled():
+        print(f"  identical parameters, 10 iterations, worst case: outputs |ours - twin| {o_ours:.2e}  |reference - twin| "
+              f"{o_ref:.2e}  |ours - reference| {worst('ours_vs_ref', is_out):.2e};  gradients / max|g|: {g_ours:.2e}  "
+              f"{g_ref:.2e}  {worst('ours_vs_ref', is_grad):.2e}")
+    assert o_ours <= max(2.0 * o_ref, 2e-5)
+    assert g_ours <= max(3.0 * g_ref, 5e-4)
 
 
 def test_c2_default_overfit_through_the_reference_python(example, capsys):
