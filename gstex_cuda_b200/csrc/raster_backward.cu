@@ -55,6 +55,14 @@ constexpr int BWD_BATCH = GSTEX_BWD_BATCH;  // list entries whose mask words a w
 #define GSTEX_BWD_FULL 14
 #endif
 constexpr int BWD_FULL = GSTEX_BWD_FULL;  // entries covering at least this many of the 32 pixels run lane = pixel
+#ifndef GSTEX_BWD_CTA_WARPS
+#define GSTEX_BWD_CTA_WARPS 1
+#endif
+// Warps per CTA (1, 2, 4 or 8; 8 = one CTA per 16x16 tile).  One-warp CTAs: measured 2.51 -> 2.37 ms on C4 (2 warps: 2.46,
+// 4 warps: 2.47) - the warps of a tile finish at very different times, and a CTA's slots are only refilled when its
+// slowest warp retires.
+constexpr int BWD_CTA_WARPS = GSTEX_BWD_CTA_WARPS;
+static_assert(BWD_WARPS % BWD_CTA_WARPS == 0, "a tile's 8 warps are split evenly over its CTAs");
 
 template <bool BLUR>
 struct BwdWarpSmem {
@@ -66,7 +74,9 @@ struct BwdWarpSmem {
     float e_gu[BWD_QCAP], e_gv[BWD_QCAP];  // d(texture term)/du, /dv per unit vis (D1)
     int row_gid[32];                   // Gaussian id of each row
     uint32_t sv_mask[BWD_BATCH];       // blend mask of each non-empty entry of the batch
+#ifndef GSTEX_BWD_NO_SVGID
     int32_t sv_gid[BWD_BATCH];         // its Gaussian id
+#endif
     uint16_t q_ent[BWD_QCAP];          // pair -> (chunk-local entry | pixel lane << 8)
     uint16_t ch_off[BWD_ECAP];         // first queue slot of each chunk entry
     uint8_t sv_r[BWD_BATCH];           // its position inside the batch
@@ -223,27 +233,37 @@ __device__ __forceinline__ float warp_reduce_slots(const float4 (&r)[8], int lan
 }
 
 template <bool C3, bool BLUR>
-__global__ void __launch_bounds__(RASTER_MAX_THREADS, GSTEX_BWD_MINB) raster_backward_kernel(const RasterCommon p, const BackwardIn in,
+#ifndef GSTEX_BWD_MIN_CTAS
+#define GSTEX_BWD_MIN_CTAS (GSTEX_BWD_MINB * (BWD_WARPS / BWD_CTA_WARPS))
+#endif
+__global__ void __launch_bounds__(BWD_CTA_WARPS * 32, GSTEX_BWD_MIN_CTAS) raster_backward_kernel(const RasterCommon p, const BackwardIn in,
                                                                                const BackwardOut o) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using WS = BwdWarpSmem<BLUR>;
     constexpr int PITCH = WS::PITCH;
     const unsigned full = 0xffffffffu;
-    const int tr = threadIdx.x, warp = tr >> 5;
+    // A tile's warps never synchronise with each other, so a tile may be spread over several CTAs of BWD_CTA_WARPS warps:
+    // a finished warp's slot is then refilled without waiting for the slowest warp of its tile.
+    const int groups = ((p.nthreads >> 5) + BWD_CTA_WARPS - 1) / BWD_CTA_WARPS;  // CTAs per tile
+    const int tile_x = BWD_CTA_WARPS == BWD_WARPS ? (int)blockIdx.x : (int)blockIdx.x / groups;
+    const int tr = BWD_CTA_WARPS == BWD_WARPS ? (int)threadIdx.x
+                                              : ((int)blockIdx.x - tile_x * groups) * (BWD_CTA_WARPS * 32) + (int)threadIdx.x;
+    if (tr >= p.nthreads) return;
+    const int warp = tr >> 5;  // warp of the TILE: pixel patch and mask word
     // Under the 80-register cap ptxas re-derives `lane` and this warp's shared-memory base from S2R SR_TID.X (a
     // ~20-cycle special-register read at the head of dependent address chains) inside every hot loop.  Passing both
     // through an empty asm makes them opaque, so they are held in registers instead: 2.60 -> 2.51 ms on C4.
     int lane = tr & 31;
     asm volatile("" : "+r"(lane));
     const unsigned lt = (1u << lane) - 1u;
-    unsigned wbase = (unsigned)warp * (unsigned)sizeof(WS);
+    unsigned wbase = (threadIdx.x >> 5) * (unsigned)sizeof(WS);
     asm volatile("" : "+r"(wbase));
     WS &W = *reinterpret_cast<WS *>(smem_raw + wbase);
 
-    const int tile = blockIdx.y * p.tiles_x + blockIdx.x;
+    const int tile = blockIdx.y * p.tiles_x + tile_x;
     int lx, ly;
     tile_pixel(p.bw, tr, lx, ly);
-    const int col = blockIdx.x * p.bw + lx, row = blockIdx.y * p.bw + ly;
+    const int col = tile_x * p.bw + lx, row = blockIdx.y * p.bw + ly;
     const bool inside = (tr < p.bw * p.bw) && col < p.img_w && row < p.img_h;
     const PixelConsts pc = make_pixel(col, row, p.c2w, p.viewmat, p.fx, p.fy, p.cx, p.cy);
     PairFlags fl;
@@ -320,7 +340,9 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, GSTEX_BWD_MINB) raster_bac
                 const int pos = nsurv + __popc(m & lt);
                 W.sv_r[pos] = (uint8_t)r;
                 W.sv_mask[pos] = mw;
+#ifndef GSTEX_BWD_NO_SVGID
                 W.sv_gid[pos] = g;
+#endif
             }
             nsurv += __popc(m);
         }
@@ -354,7 +376,12 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, GSTEX_BWD_MINB) raster_bac
                 // the pair queue is being written
                 for (int t = lane; t < ne * 8; t += 32) {
                     const int j = t >> 3, q = t & 7;
-                    __pipeline_memcpy_async(W.rec + quad_slot(j, q), p.recs + (size_t)W.sv_gid[si0 - j] * 8 + q, 16);
+#ifndef GSTEX_BWD_NO_SVGID
+                    const int32_t gid = W.sv_gid[si0 - j];
+#else
+                    const int32_t gid = __ldg(p.ids + first + (int)W.sv_r[si0 - j]);
+#endif
+                    __pipeline_memcpy_async(W.rec + quad_slot(j, q), p.recs + (size_t)gid * 8 + q, 16);
                 }
                 __pipeline_commit();
                 unsigned mm = (lane < ne && sparse) ? m : 0u;
@@ -502,11 +529,13 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, GSTEX_BWD_MINB) raster_bac
 template <bool C3, bool BLUR>
 static int launch_bwd_variant(const dim3 grid, const RasterCommon &p, const BackwardIn &in, const BackwardOut &o,
                               cudaStream_t s) {
-    const size_t smem = sizeof(BwdWarpSmem<BLUR>) * BWD_WARPS;
+    const size_t smem = sizeof(BwdWarpSmem<BLUR>) * BWD_CTA_WARPS;
     static SmemOnceFlags once;  // one per template instantiation
     const int rc = configure_dynamic_smem((const void *)raster_backward_kernel<C3, BLUR>, smem, true, once);
     if (rc != GSTEX_OK) return rc;
-    raster_backward_kernel<C3, BLUR><<<grid, p.nthreads, smem, s>>>(p, in, o);
+    const int cta_threads = min(p.nthreads, BWD_CTA_WARPS * 32);
+    const dim3 g(grid.x * ceil_div(p.nthreads, BWD_CTA_WARPS * 32), grid.y);
+    raster_backward_kernel<C3, BLUR><<<g, cta_threads, smem, s>>>(p, in, o);
     return GSTEX_OK;
 }
 
