@@ -550,7 +550,12 @@ def run_e2e(args, scene, cams, mine, targets_host, dev, world, views):
         for idx, v in enumerate(order):
             vm, c2w, gt = loader.get()
             loader.submit(host_inputs(order[(idx + 1) % len(order)]))
-            colors = SH.spherical_harmonics_colors(3, leaves["means"], c2w, leaves["sh_coeffs"])
+            # with several views per step the two large gradients (texels, SH coefficients) are added straight into the
+            # flat buffer by the backward kernels (the package's opt-in texture_grad= / coeffs_grad=), not returned to
+            # autograd for a zero-fill + "grad += new" pass per view
+            fused = dict(texture_grad=leaves["texture"].grad) if flat is not None else {}
+            colors = SH.spherical_harmonics_colors(3, leaves["means"], c2w, leaves["sh_coeffs"],
+                                                   coeffs_grad=leaves["sh_coeffs"].grad if flat is not None else None)
             _, depths = project_points(leaves["means"].detach(), vm, intr)
             centers, extents = get_aabb_2d(leaves["means"].detach(), leaves["scales"].detach(), 1.0,
                                            leaves["quats"].detach(), vm, intr)
@@ -558,7 +563,7 @@ def run_e2e(args, scene, cams, mine, targets_host, dev, world, views):
             outs = texture_gaussians(scene["texture_info"], scene["texture_dims"], centers, extents, depths, nth, colors,
                                      leaves["opacities"], leaves["means"], leaves["scales"], 1.0, leaves["quats"],
                                      leaves["uv0"], leaves["umap"], leaves["vmap"], leaves["texture"], vm, c2w, *intr, H,
-                                     W, bw, 1 << 8, scene["background"], max_intersects=cap)
+                                     W, bw, 1 << 8, scene["background"], max_intersects=cap, **fused)
             loss = image_loss(outs[4], outs[2], outs[5], gt)  # example.py:189-209, one kernel (csrc/loss.cu)
             loss.backward()
             loader.release()
@@ -608,7 +613,9 @@ def run_e2e(args, scene, cams, mine, targets_host, dev, world, views):
     return {"value": views * H * W / (ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
             "d2h_bytes_per_step": 4, "ms_per_step": ms, "steps": steps,
             "api": "spherical_harmonics_colors + project_points + get_aabb_2d + get_num_tiles_hit_2d + texture_gaussians "
-                   "(max_intersects capacity: no host sync per call) + "
+                   "(max_intersects capacity: no host sync per call"
+                   + ("; texture_grad= / coeffs_grad=: texel and SH gradients added in place into the flat all-reduce buffer" if world > 1 else "")
+                   + ") + "
                    "image_loss (the example.py loss), all autograd ops of the package; inputs staged by gstex_cuda_b200.prefetch.ViewPrefetcher "
                    "(pinned host -> device on a copy stream, one view ahead); the loss of every step is read back through "
                    "an asynchronous copy into pinned memory, consumed one step later",

@@ -43,18 +43,27 @@ class _SphericalHarmonics(Function):
                                                    v_colors.contiguous()))
 
 
-def spherical_harmonics_colors(degrees_to_use: int, means: Tensor, c2w: Tensor, coeffs: Tensor) -> Tensor:
+def spherical_harmonics_colors(degrees_to_use: int, means: Tensor, c2w: Tensor, coeffs: Tensor,
+                               coeffs_grad: Tensor = None) -> Tensor:
     """View-dependent colours as a trainer forms them around the SH op, in one kernel each way:
     ``clamp(spherical_harmonics(deg, means - c2w[:3, 3], coeffs) + 0.5, 0, 1)``.  Differentiable w.r.t. ``coeffs``
-    only (like the reference op, sh.py:60-96, whose ``viewdirs`` carry no gradient); the clamp gates the gradient."""
+    only (like the reference op, sh.py:60-96, whose ``viewdirs`` carry no gradient); the clamp gates the gradient.
+
+    ``coeffs_grad`` (opt-in): a float32 tensor shaped like ``coeffs`` that the backward pass ADDS the coefficient
+    gradients into instead of returning them to autograd (see ``texture_gaussians(..., texture_grad=)``)."""
     assert coeffs.shape[-2] >= num_sh_bases(degrees_to_use)
+    if coeffs_grad is not None and not (coeffs_grad.is_cuda and coeffs_grad.dtype == torch.float32
+                                        and coeffs_grad.is_contiguous() and coeffs_grad.shape == coeffs.shape
+                                        and coeffs_grad.device == coeffs.device):
+        raise ValueError("coeffs_grad must be a contiguous float32 CUDA tensor shaped like coeffs")
     return _SphericalHarmonicsColors.apply(degrees_to_use, means.detach().contiguous(), c2w.contiguous(),
-                                           coeffs.contiguous())
+                                           coeffs.contiguous(), coeffs_grad)
 
 
 class _SphericalHarmonicsColors(Function):
     @staticmethod
-    def forward(ctx, degrees_to_use: int, means: Tensor, c2w: Tensor, coeffs: Tensor):
+    def forward(ctx, degrees_to_use: int, means: Tensor, c2w: Tensor, coeffs: Tensor, coeffs_grad=None):
+        ctx.coeffs_grad = coeffs_grad
         for name, t in (("means", means), ("c2w", c2w), ("coeffs", coeffs)):
             if not (t.is_cuda and t.dtype == torch.float32):
                 raise RuntimeError(f"spherical_harmonics_colors: {name} must be a float32 CUDA tensor")
@@ -76,10 +85,13 @@ class _SphericalHarmonicsColors(Function):
         means, c2w, mask = ctx.saved_tensors
         n, dev = means.shape[0], means.device
         v_colors = v_colors.contiguous()
-        v_coeffs = torch.zeros(ctx.coeff_shape, dtype=torch.float32, device=dev)  # rows past degrees_to_use stay zero
+        fused = ctx.coeffs_grad
+        # rows past degrees_to_use stay zero (or, when adding into the caller's buffer, untouched)
+        v_coeffs = fused if fused is not None else torch.zeros(ctx.coeff_shape, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             rc = _lib.load().gstex_sh_colors_backward(n, ctx.degree, ctx.degrees_to_use, means.data_ptr(), c2w.data_ptr(),
-                                                      v_colors.data_ptr(), mask.data_ptr(), v_coeffs.data_ptr(), 0,
+                                                      v_colors.data_ptr(), mask.data_ptr(), v_coeffs.data_ptr(),
+                                                      1 if fused is not None else 0,
                                                       torch.cuda.current_stream(dev).cuda_stream)
         _lib.check(rc, "sh_colors_backward")
-        return None, None, None, v_coeffs
+        return None, None, None, (None if fused is not None else v_coeffs), None

@@ -22,14 +22,19 @@ def texture_gaussians(texture_info: Tuple[int, int, int], texture_dims: Tensor, 
                       texture: Tensor, viewmat: Tensor, c2w: Tensor, fx: float, fy: float, cx: float, cy: float,
                       img_height: int, img_width: int, block_width: int, settings: int,
                       background: Optional[Tensor] = None, use_torch_impl: bool = False,
-                      max_intersects: Optional[int] = None):
+                      max_intersects: Optional[int] = None, texture_grad: Optional[Tensor] = None):
     """Rasterise textured 2D Gaussians; differentiable w.r.t. colors, opacity, means, scales, quats, uv0,
     umap, vmap and texture.  Arguments, defaults and outputs as in the reference (texture.py:14-150).
 
     ``max_intersects`` (extension, opt-in): a capacity for the sorted intersection list.  The reference synchronises
     the host once per call to read the intersection count (``cum_tiles_hit[-1].item()``, utils.py:58) because its
     buffers are sized by it; with a capacity the count stays on the device and the call never waits for the GPU.
-    Intersections beyond the capacity are dropped: ``last_intersect_count()`` returns the count of the last call."""
+    Intersections beyond the capacity are dropped: ``last_intersect_count()`` returns the count of the last call.
+
+    ``texture_grad`` (extension, opt-in): a float32 tensor shaped like ``texture`` that the backward pass ADDS the texel
+    gradients into, instead of returning them to autograd (``texture.grad`` is then left untouched: pass the buffer the
+    optimiser or the data-parallel reduction reads).  A multi-view step otherwise pays, per view, for a zero-filled
+    gradient the size of the texture plus autograd's ``grad += new`` pass over it."""
     assert block_width > 1 and block_width <= 16, "block_width must be between 2 and 16"
     if colors.dtype == torch.uint8:
         colors = colors.float() / 255
@@ -40,6 +45,12 @@ def texture_gaussians(texture_info: Tuple[int, int, int], texture_dims: Tensor, 
         background = torch.ones(colors.shape[-1], dtype=torch.float32, device=colors.device)
     if colors.ndimension() != 2:
         raise ValueError("colors must have dimensions (N, D)")
+    if texture_grad is not None:
+        if use_torch_impl:
+            raise ValueError("texture_grad is an option of the CUDA path")
+        if not (texture_grad.is_cuda and texture_grad.dtype == torch.float32 and texture_grad.is_contiguous()
+                and texture_grad.shape == texture.shape and texture_grad.device == texture.device):
+            raise ValueError("texture_grad must be a contiguous float32 CUDA tensor shaped like texture")
     if use_torch_impl:
         # the slow pure-PyTorch checker (reference texture.py:411-514 over _torch_impl.texture_forward): same binning,
         # torch autograd instead of the backward kernel
@@ -51,7 +62,7 @@ def texture_gaussians(texture_info: Tuple[int, int, int], texture_dims: Tensor, 
         num_tiles_hit.contiguous(), colors.contiguous(), opacity.contiguous(), means.contiguous(), scales.contiguous(),
         glob_scale, quats.contiguous(), uv0.contiguous(), umap.contiguous(), vmap.contiguous(), texture.contiguous(),
         viewmat.contiguous(), c2w.contiguous(), fx, fy, cx, cy, img_height, img_width, block_width, settings,
-        background.contiguous(), None if max_intersects is None else int(max_intersects))
+        background.contiguous(), None if max_intersects is None else int(max_intersects), texture_grad)
 
 
 _LAST_COUNT = {}
@@ -106,7 +117,7 @@ class _TextureGaussians(Function):
     @staticmethod
     def forward(ctx, texture_info, texture_dims, centers, extents, depths, num_tiles_hit, colors, opacity, means,
                 scales, glob_scale, quats, uv0, umap, vmap, texture, viewmat, c2w, fx, fy, cx, cy, img_height,
-                img_width, block_width, settings, background, max_intersects=None):
+                img_width, block_width, settings, background, max_intersects=None, texture_grad=None):
         lib = _lib.load()
         H, W, bw = int(img_height), int(img_width), int(block_width)
         tile_bounds = ((W + bw - 1) // bw, (H + bw - 1) // bw, 1)
@@ -154,6 +165,7 @@ class _TextureGaussians(Function):
         if max_intersects is not None:
             num_intersects = max(int(max_intersects), 1)  # a capacity: the true count stays on the device
         ctx.num_intersects = num_intersects
+        ctx.texture_grad = texture_grad
         if num_intersects < 1:
             # upstream leaves several outputs undefined in this branch (texture.py:197-205, :254-289);
             # we return the background-only image and zeros
@@ -188,10 +200,12 @@ class _TextureGaussians(Function):
 
     @staticmethod
     def backward(ctx, v_out_img, v_out_depth, v_out_reg, v_out_alpha, v_out_texture, v_out_normal):
-        none18 = [None] * 28
+        none18 = [None] * 29
+        fused_tex = ctx.texture_grad  # texel gradients are added into this buffer instead of being returned
         if ctx.num_intersects < 1:
             colors, opacity, means, scales, quats, uv0, umap, vmap, texture = ctx.saved_tensors
-            grads = [torch.zeros_like(t) for t in (colors, opacity, means, scales, quats, uv0, umap, vmap, texture)]
+            grads = [torch.zeros_like(t) for t in (colors, opacity, means, scales, quats, uv0, umap, vmap)]
+            grads.append(None if fused_tex is not None else torch.zeros_like(texture))
         else:
             (gaussian_ids_sorted, tile_bins, means, scales, quats, umap, vmap, texture, viewmat, c2w, background,
              final_Ts, final_idx, depth_idx, out_reg_s, recs, mean2d, tex4, masks, uv0) = ctx.saved_tensors
@@ -213,8 +227,13 @@ class _TextureGaussians(Function):
                 _C._chk(name, t, torch.float32)
             acc = torch.zeros((n, 32), **f32)                       # moment lines (csrc/common.cuh: AccSlot)
             rgba = C == 3 and texture.shape[1] == 4
-            vtex4 = torch.zeros((X, 4), **f32) if C == 3 else None  # texel gradients at a 16-byte pitch
-            v_texture = vtex4 if rgba else (torch.zeros((X, C), **f32) if C != 3 else torch.empty((X, C), **f32))
+            if fused_tex is not None and (rgba or C != 3):
+                vtex4 = v_texture = fused_tex  # the rasteriser's reductions land in the caller's buffer
+            else:
+                vtex4 = torch.zeros((X, 4), **f32) if C == 3 else None  # texel gradients at a 16-byte pitch
+                v_texture = vtex4 if rgba else (torch.zeros((X, C), **f32) if C != 3 else torch.empty((X, C), **f32))
+                if fused_tex is not None:
+                    v_texture = fused_tex  # (X,3): the un-padding pass adds into it
             v_colors, v_opacity = torch.empty((n, 3), **f32), torch.empty((n, 1), **f32)
             v_means, v_scales, v_quats = torch.empty((n, 3), **f32), torch.empty((n, 3), **f32), torch.empty((n, 4), **f32)
             # shaped like the inputs ((n, num_probs, k) upstream, zero-filled: texture.cu:1004-1006); the kernels address
@@ -239,8 +258,10 @@ class _TextureGaussians(Function):
                                                0, s)
                 _lib.check(rc, "raster_epilogue")
                 if C == 3 and not rgba:
-                    _lib.check(lib.gstex_unpad_texture_grad(X, _p(vtex4), _p(v_texture), 0, s), "unpad_texture_grad")
-            grads = (v_colors, v_opacity, v_means, v_scales, v_quats, v_uv0, v_umap, v_vmap, v_texture)
+                    _lib.check(lib.gstex_unpad_texture_grad(X, _p(vtex4), _p(v_texture), 1 if fused_tex is not None else 0, s),
+                               "unpad_texture_grad")
+            grads = (v_colors, v_opacity, v_means, v_scales, v_quats, v_uv0, v_umap, v_vmap,
+                     None if fused_tex is not None else v_texture)
         v_colors, v_opacity, v_means, v_scales, v_quats, v_uv0, v_umap, v_vmap, v_texture = grads
         none18[6], none18[7], none18[8], none18[9] = v_colors, v_opacity, v_means, v_scales
         none18[11], none18[12], none18[13], none18[14], none18[15] = v_quats, v_uv0, v_umap, v_vmap, v_texture

@@ -296,3 +296,41 @@ def test_rgba_texture_layout_through_the_autograd_api():
     for k in _LEAVES[:-1]:
         ga, gb = res[0][1][k].grad, res[1][1][k].grad
         assert float((ga - gb).abs().max()) <= 1e-5 * float(ga.abs().max()) + 1e-12, k
+
+
+@pytest.mark.parametrize("rgba", [False, True])
+def test_in_place_gradient_accumulation_equals_autograd(rgba):
+    """texture_gaussians(..., texture_grad=buf) and spherical_harmonics_colors(..., coeffs_grad=buf): two views accumulated
+    straight into caller-owned buffers equal autograd's own accumulation over the same two views, and the leaves' .grad of
+    the fused inputs stays untouched."""
+    from gstex_cuda_b200 import sh as SH
+    s = random_small_scene(150, 96, 64, seed=31, device=DEV)
+    g = torch.Generator().manual_seed(5)
+    coeffs0 = (torch.randn(150, 16, 3, generator=g) * 0.5).to(DEV)
+    tex0 = torch.cat([s["texture"], torch.zeros_like(s["texture"][:, :1])], 1).contiguous() if rgba else s["texture"]
+    views = [s["c2w"], s["c2w"].clone()]
+    views[1][0, 3] += 0.4  # SH colours see a second camera position
+    res = []
+    for fused in (False, True):
+        leaves = {k: s[k].clone().requires_grad_(True) for k in _LEAVES if k not in ("colors", "texture")}
+        leaves["texture"] = tex0.clone().requires_grad_(True)
+        coeffs = coeffs0.clone().requires_grad_(True)
+        tg, cg = (torch.zeros_like(tex0), torch.zeros_like(coeffs0)) if fused else (None, None)
+        for c2w in views:
+            leaves["colors"] = SH.spherical_harmonics_colors(3, leaves["means"], c2w, coeffs, coeffs_grad=cg)
+            kw = dict(texture_grad=tg) if fused else {}
+            outs = _run_api(s, leaves, **kw)
+            (_loss(outs, s["target"]) + (outs[0] - s["target"]).square().mean()).backward()  # colours (SH) take part
+        if fused:
+            assert leaves["texture"].grad is None and coeffs.grad is None
+            res.append((tg, cg, leaves))
+        else:
+            res.append((leaves["texture"].grad, coeffs.grad, leaves))
+    for a, b in zip(res[0][:2], res[1][:2]):
+        assert float(a.abs().max()) > 0
+        assert float((a - b).abs().max()) <= 1e-5 * float(a.abs().max()) + 1e-12  # atomic order only
+    for k in ("means", "scales", "quats", "opacities", "uv0", "umap", "vmap"):
+        ga, gb = res[0][2][k].grad, res[1][2][k].grad
+        assert float((ga - gb).abs().max()) <= 1e-5 * float(ga.abs().max()) + 1e-12, k
+    with pytest.raises(ValueError):
+        _run_api(s, res[0][2], texture_grad=torch.zeros(3, device=DEV))
