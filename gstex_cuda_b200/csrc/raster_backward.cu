@@ -287,14 +287,21 @@ __global__ void __launch_bounds__(BWD_CTA_WARPS * 32, GSTEX_BWD_MIN_CTAS) raster
     float T = in.final_Ts[me.pix];
     me.Sf0 = in.final_s[3 * me.pix]; me.Sf1 = in.final_s[3 * me.pix + 1]; me.Sf2 = in.final_s[3 * me.pix + 2];
     me.dfinal = in.depth_idx[me.pix];
-    me.vi0 = in.v_img[3 * me.pix]; me.vi1 = in.v_img[3 * me.pix + 1]; me.vi2 = in.v_img[3 * me.pix + 2];
-    me.vn0 = in.v_normal[3 * me.pix]; me.vn1 = in.v_normal[3 * me.pix + 1]; me.vn2 = in.v_normal[3 * me.pix + 2];
-    me.v_dep = in.v_depth[me.pix]; me.v_reg = in.v_reg[me.pix];
-    me.vt0 = me.vt1 = me.vt2 = 0.f;
-    if (C3) {
+    // an upstream gradient the loss does not produce may be passed as NULL (= zeros), except the generic-channel v_tex
+    me.vi0 = me.vi1 = me.vi2 = me.vn0 = me.vn1 = me.vn2 = me.vt0 = me.vt1 = me.vt2 = 0.f;
+    if (in.v_img) {
+        me.vi0 = in.v_img[3 * me.pix]; me.vi1 = in.v_img[3 * me.pix + 1]; me.vi2 = in.v_img[3 * me.pix + 2];
+    }
+    if (in.v_normal) {
+        me.vn0 = in.v_normal[3 * me.pix]; me.vn1 = in.v_normal[3 * me.pix + 1]; me.vn2 = in.v_normal[3 * me.pix + 2];
+    }
+    me.v_dep = in.v_depth ? in.v_depth[me.pix] : 0.f;
+    me.v_reg = in.v_reg ? in.v_reg[me.pix] : 0.f;
+    if (C3 && in.v_tex) {
         me.vt0 = in.v_tex[3 * me.pix]; me.vt1 = in.v_tex[3 * me.pix + 1]; me.vt2 = in.v_tex[3 * me.pix + 2];
     }
-    float v_T_run = p.background[0] * me.vi0 + p.background[1] * me.vi1 + p.background[2] * me.vi2 - in.v_alpha[me.pix];
+    float v_T_run = p.background[0] * me.vi0 + p.background[1] * me.vi1 + p.background[2] * me.vi2 -
+                    (in.v_alpha ? in.v_alpha[me.pix] : 0.f);
 
     // values of pixel lane `pl`, fetched by a pair lane (all 32 lanes must call this together)
     auto fetch_pixel = [&](int pl, PixelConsts &qc, PixelShare &px) {

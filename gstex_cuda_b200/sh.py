@@ -86,8 +86,9 @@ class _SphericalHarmonicsColors(Function):
         n, dev = means.shape[0], means.device
         v_colors = v_colors.contiguous()
         fused = ctx.coeffs_grad
-        # rows past degrees_to_use stay zero (or, when adding into the caller's buffer, untouched)
-        v_coeffs = fused if fused is not None else torch.zeros(ctx.coeff_shape, dtype=torch.float32, device=dev)
+        # rows past degrees_to_use come back zero (or, when adding into the caller's buffer, stay untouched)
+        # (the kernel writes every row, zeros past degrees_to_use: no zero-fill needed)
+        v_coeffs = fused if fused is not None else torch.empty(ctx.coeff_shape, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             rc = _lib.load().gstex_sh_colors_backward(n, ctx.degree, ctx.degrees_to_use, means.data_ptr(), c2w.data_ptr(),
                                                       v_colors.data_ptr(), mask.data_ptr(), v_coeffs.data_ptr(),

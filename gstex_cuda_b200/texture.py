@@ -214,17 +214,22 @@ class _TextureGaussians(Function):
             dev = means.device
             f32 = dict(dtype=torch.float32, device=dev)
 
-            def dense(v, shape):
-                return torch.zeros(shape, **f32) if v is None else v.contiguous()
+            def dense(v, shape, needed=False):
+                # an output the loss does not use has no upstream gradient: the kernel takes NULL for zeros
+                if v is None:
+                    return torch.zeros(shape, **f32) if needed else None
+                return v.contiguous()
 
             C = int(ctx.texture_info[2])
             n, X = means.shape[0], texture.shape[0]
             fx, fy, cx, cy = ctx.intr
             v_img, v_dep, v_reg = dense(v_out_img, (H, W, 3)), dense(v_out_depth, (H, W)), dense(v_out_reg, (H, W))
-            v_alp, v_tex, v_nrm = dense(v_out_alpha, (H, W)), dense(v_out_texture, (H, W, C)), dense(v_out_normal, (H, W, 3))
+            v_alp, v_nrm = dense(v_out_alpha, (H, W)), dense(v_out_normal, (H, W, 3))
+            v_tex = dense(v_out_texture, (H, W, C), needed=C != 3)  # the generic-channel path reads it unconditionally
             for name, t in (("v_output", v_img), ("v_output_depth", v_dep), ("v_output_reg", v_reg),
                             ("v_output_alpha", v_alp), ("v_output_texture", v_tex), ("v_output_normal", v_nrm)):
-                _C._chk(name, t, torch.float32)
+                if t is not None:
+                    _C._chk(name, t, torch.float32)
             acc = torch.zeros((n, 32), **f32)                       # moment lines (csrc/common.cuh: AccSlot)
             rgba = C == 3 and texture.shape[1] == 4
             if fused_tex is not None and (rgba or C != 3):

@@ -274,6 +274,8 @@ int gstex_raster_masks(int img_height, int img_width, int block_width, int setti
                        const float *mean2d, const float *viewmat, const float *c2w, float fx, float fy, float cx,
                        float cy, const float *final_Ts, const int32_t *final_idx, uint32_t *masks,
                        int64_t mask_entries, const int32_t *d_num_intersects, gstex_stream_t stream);
+/* The upstream gradients v_out_img / v_out_depth / v_out_reg / v_out_alpha / v_out_normal, and v_out_texture when
+ * channels == 3, may be NULL: an output the caller's loss does not use (zeros, without the buffer). */
 int gstex_raster_backward(int img_height, int img_width, int block_width, int channels, int settings,
                           const int32_t *gaussian_ids_sorted, const int32_t *tile_bins, const float *recs,
                           const float *mean2d, const float *tex, const float *viewmat, const float *c2w, float fx,
