@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(256) image_loss_kernel(int npix, const float *
             const float d = out_texture[3 * i + c] - gt[3 * i + c];
             mse += d * d;
             v_tex[3 * i + c] = 2.f * d * inv_3p;
-            v_img[3 * i + c] = 0.f;
+            if (v_img) v_img[3 * i + c] = 0.f;
         }
         const float nx = out_normal[3 * i], ny = out_normal[3 * i + 1], nz = out_normal[3 * i + 2];
         part += mse * inv_3p + out_reg[i] * inv_p + (nx * nx + ny * ny + (1.f - nz) * (1.f - nz)) * inv_p;
@@ -31,8 +31,8 @@ __global__ void __launch_bounds__(256) image_loss_kernel(int npix, const float *
         v_normal[3 * i + 1] = 2.f * ny * inv_p;
         v_normal[3 * i + 2] = -2.f * (1.f - nz) * inv_p;
         v_reg[i] = inv_p;
-        v_depth[i] = 0.f;
-        v_alpha[i] = 0.f;
+        if (v_depth) v_depth[i] = 0.f;  // the three outputs this loss does not use: NULL = not wanted (the backward
+        if (v_alpha) v_alpha[i] = 0.f;  // rasteriser takes NULL for a zero gradient)
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);

@@ -1,6 +1,8 @@
 // sh.cu -- spherical-harmonics colour evaluation, degrees 0-4, 3 channels (SURVEY 8a row a-11;
 // reference sh.cuh:46-253, bindings.cu:18-75).  HBM bound: 12 + 12K bytes in, 12 out per Gaussian.
 // One thread per Gaussian; the basis is evaluated once and shared by the three channels.
+#include <cuda_pipeline.h>
+
 #include "common.cuh"
 
 namespace gstex {
@@ -56,6 +58,10 @@ __device__ __forceinline__ void sh_basis(int deg, Vec3 dir, float *Y) {
 constexpr int SH_ROWS = 128;
 
 __host__ __device__ inline int sh_pitch(int L) { return L | 1; }
+// Row pitch (floats) of the forward tile when rows are whole float4s (L % 4 == 0): a multiple of 4 floats, so that rows
+// can be filled with 16-byte cp.async copies, and an ODD number of quads, so that the 8 lanes of a quarter warp reading
+// quad q of 8 consecutive rows (LDS.128) touch 8 different 16-byte bank groups.
+__host__ __device__ inline int sh_pitch4(int L) { return ((L >> 2) | 1) << 2; }
 
 __device__ __forceinline__ void sh_tile_load(float *__restrict__ tile, int pitch, const float *__restrict__ g,
                                              int rows, int L, bool vec4) {
@@ -109,11 +115,22 @@ __global__ void __launch_bounds__(SH_ROWS) sh_forward_tiled(int n, int K, const 
                                                             const float *__restrict__ coeffs,
                                                             float *__restrict__ colors, uint8_t *__restrict__ mask,
                                                             int vec4) {
-    extern __shared__ float sh_tile[];
+    extern __shared__ __align__(16) float sh_tile[];
     constexpr int KU = (DEG + 1) * (DEG + 1);
-    const int L = 3 * K, pitch = sh_pitch(L);
+    const int L = 3 * K, pitch = vec4 ? sh_pitch4(L) : sh_pitch(L);
     const int row0 = blockIdx.x * SH_ROWS, rows = min(SH_ROWS, n - row0);
-    sh_tile_load(sh_tile, pitch, coeffs + (size_t)row0 * L, rows, L, vec4 != 0);
+    if (vec4) {  // the block's rows * L floats go to shared memory as 16-byte asynchronous copies (no register staging)
+        const float4 *__restrict__ g4 = reinterpret_cast<const float4 *>(coeffs + (size_t)row0 * L);
+        const int qpr = L >> 2;
+        for (int q = threadIdx.x; q < rows * qpr; q += blockDim.x) {
+            const int r = q / qpr, c = q - r * qpr;
+            __pipeline_memcpy_async(sh_tile + r * pitch + 4 * c, g4 + q, 16);
+        }
+        __pipeline_commit();
+        __pipeline_wait_prior(0);
+    } else {
+        sh_tile_load(sh_tile, pitch, coeffs + (size_t)row0 * L, rows, L, false);
+    }
     __syncthreads();
     const int t = threadIdx.x, i = row0 + t;
     if (t >= rows) return;
@@ -124,11 +141,25 @@ __global__ void __launch_bounds__(SH_ROWS) sh_forward_tiled(int n, int K, const 
     const float *__restrict__ c = sh_tile + t * pitch;
     float v[3];
     v[0] = v[1] = v[2] = FUSED ? 0.5f : 0.f;
+    if (vec4) {  // the same sums in the same order, the row read as float4s
+        const float4 *__restrict__ c4 = reinterpret_cast<const float4 *>(c);
 #pragma unroll
-    for (int k = 0; k < KU; ++k) {
-        v[0] = fmaf(Y[k], c[3 * k], v[0]);
-        v[1] = fmaf(Y[k], c[3 * k + 1], v[1]);
-        v[2] = fmaf(Y[k], c[3 * k + 2], v[2]);
+        for (int q = 0; q < (3 * KU + 3) / 4; ++q) {
+            const float4 w4 = c4[q];
+            const float w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int j = 4 * q + e;
+                if (j < 3 * KU) v[j % 3] = fmaf(Y[j / 3], w[e], v[j % 3]);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < KU; ++k) {
+            v[0] = fmaf(Y[k], c[3 * k], v[0]);
+            v[1] = fmaf(Y[k], c[3 * k + 1], v[1]);
+            v[2] = fmaf(Y[k], c[3 * k + 2], v[2]);
+        }
     }
     if (FUSED) {
         unsigned m = 0;
@@ -152,7 +183,7 @@ __global__ void __launch_bounds__(SH_ROWS) sh_backward_tiled(int n, int K, const
                                                              const float *__restrict__ v_colors,
                                                              const uint8_t *__restrict__ mask,
                                                              float *__restrict__ v_coeffs, int accumulate, int vec4) {
-    extern __shared__ float sh_tile[];
+    extern __shared__ __align__(16) float sh_tile[];
     constexpr int KU = (DEG + 1) * (DEG + 1);
     const int L = 3 * K, pitch = sh_pitch(L);
     const int row0 = blockIdx.x * SH_ROWS, rows = min(SH_ROWS, n - row0);
@@ -186,8 +217,8 @@ template <bool FUSED>
 static int launch_sh_forward(int n, int degree, int degrees_to_use, const float *dirs_or_means, const float *c2w,
                              const float *coeffs, float *colors, uint8_t *mask, cudaStream_t s) {
     const int K = sh_num_bases(degree), L = 3 * K, grid = ceil_div(n, SH_ROWS);
-    const size_t smem = sizeof(float) * SH_ROWS * sh_pitch(L);
     const int vec4 = (L % 4 == 0) && ((uintptr_t)coeffs % 16 == 0);
+    const size_t smem = sizeof(float) * SH_ROWS * (vec4 ? sh_pitch4(L) : sh_pitch(L));
     switch (degrees_to_use) {
         case 0: sh_forward_tiled<0, FUSED><<<grid, SH_ROWS, smem, s>>>(n, K, dirs_or_means, c2w, coeffs, colors, mask, vec4); break;
         case 1: sh_forward_tiled<1, FUSED><<<grid, SH_ROWS, smem, s>>>(n, K, dirs_or_means, c2w, coeffs, colors, mask, vec4); break;

@@ -34,12 +34,10 @@ class _ImageLoss(Function):
         loss = torch.zeros((), dtype=torch.float32, device=dev)
         v_tex, v_nrm = torch.empty_like(out_texture), torch.empty_like(out_normal)
         v_reg = torch.empty_like(out_reg)
-        # the kernel also fills the three gradients this loss does not use (image, depth, alpha): one scratch buffer
-        scratch = torch.empty((5, H, W), dtype=torch.float32, device=dev)
+        # the three gradients this loss does not use (image, depth, alpha) are not wanted: NULL
         with torch.cuda.device(dev):
             rc = _lib.load().gstex_image_loss(H, W, out_texture.data_ptr(), out_reg.data_ptr(), out_normal.data_ptr(),
-                                              gt.data_ptr(), loss.data_ptr(), scratch[:3].data_ptr(),
-                                              scratch[3].data_ptr(), v_reg.data_ptr(), scratch[4].data_ptr(),
+                                              gt.data_ptr(), loss.data_ptr(), 0, 0, v_reg.data_ptr(), 0,
                                               v_tex.data_ptr(), v_nrm.data_ptr(),
                                               torch.cuda.current_stream(dev).cuda_stream)
         _lib.check(rc, "image_loss")

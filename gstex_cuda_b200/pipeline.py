@@ -146,6 +146,9 @@ class FusedTrainStep:
         self.vout = dict(v_out_img=torch.empty((H, W, 3), **f32), v_out_depth=torch.empty((H, W), **f32),
                          v_out_reg=torch.empty((H, W), **f32), v_out_alpha=torch.empty((H, W), **f32),
                          v_out_texture=torch.empty((H, W, C), **f32), v_out_normal=torch.empty((H, W, 3), **f32))
+        # what view_loss() leaves for the backward: the gradients of the outputs its loss does not use are None (zeros)
+        self.vout_loss = dict(self.vout, v_out_img=None, v_out_depth=None, v_out_alpha=None)
+        self._cur_vout = self.vout
         self.max_count_seen = torch.zeros(1, **i32)
         # bookkeeping for bench.py: number of libgstex_b200 kernels launched, optional per-kernel CUDA events
         self.launches = 0
@@ -290,12 +293,13 @@ class FusedTrainStep:
                                               self.cap, P(v.num_isect), s), "raster_forward")
         self.launches += 2  # mask zero-fill + raster
         self.cur = v
+        self._cur_vout = self.vout  # a caller that fills self.vout itself fills all six; view_loss() narrows it
         return o
 
     def _raster_backward(self, v, viewmat: torch.Tensor, c2w: torch.Tensor, vout: Dict[str, torch.Tensor]) -> None:
         lib, s = self.lib, self._s()
         fx, fy, cx, cy = self.intr
-        P = lambda t: t.data_ptr()  # noqa: E731
+        P = lambda t: 0 if t is None else t.data_ptr()  # noqa: E731  (None: an upstream gradient that is all zeros)
         o = self.out
         tex = self.tex4 if self.C == 3 else self.p["texture"]
         vtex = self.vtex4 if self.C == 3 else self.grads["v_texture"]
@@ -346,17 +350,18 @@ class FusedTrainStep:
         """example.py:189-209 loss, accumulated into self.loss; fills the upstream-gradient buffers."""
         o, v = self.out, self.vout
         P = lambda t: t.data_ptr()  # noqa: E731
+        # the loss does not use out_img / out_depth / out_alpha: their zero gradients are neither written nor read (NULL)
         self._ck(self.lib.gstex_image_loss(self.H, self.W, P(o["out_texture"]), P(o["out_reg"]), P(o["out_normal"]),
-                                           P(target), P(self.loss), P(v["v_out_img"]), P(v["v_out_depth"]),
-                                           P(v["v_out_reg"]), P(v["v_out_alpha"]), P(v["v_out_texture"]),
+                                           P(target), P(self.loss), 0, 0, P(v["v_out_reg"]), 0, P(v["v_out_texture"]),
                                            P(v["v_out_normal"]), self._s()), "image_loss")
+        self._cur_vout = self.vout_loss
         self.launches += 1
 
     def view_backward(self, viewmat: torch.Tensor, c2w: torch.Tensor, vout: Optional[Dict[str, torch.Tensor]] = None) -> None:
         """Rasterise backward + epilogue + SH backward of the view last rendered; accumulates into the arena."""
         viewmat, c2w = self._cam(viewmat, "viewmat"), self._cam(c2w, "c2w")
         v = self.cur
-        self._raster_backward(v, viewmat, c2w, vout if vout is not None else self.vout)
+        self._raster_backward(v, viewmat, c2w, vout if vout is not None else self._cur_vout)
         self._tail(v, viewmat, c2w, self._first_view)
         self._first_view = False
 
@@ -394,7 +399,7 @@ class FusedTrainStep:
             main.wait_event(v.prep_done)
             self._render(v, viewmat, c2w)
             self.view_loss(targets[k])
-            self._raster_backward(v, viewmat, c2w, self.vout)
+            self._raster_backward(v, viewmat, c2w, self._cur_vout)
             with torch.cuda.stream(side):  # tail of this view, underneath the next view's rasterisers
                 side.wait_event(v.bwd_done)
                 self._tail(v, viewmat, c2w, k == 0)

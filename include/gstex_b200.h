@@ -237,7 +237,8 @@ int gstex_texture_sample_backward(int num_queries, int channels, const int32_t *
 
 /* Fused image loss of example.py:189-209 and its gradient w.r.t. the rasteriser outputs:
  *   loss = mean((out_texture - gt)^2) + mean(out_reg) + mean(nx^2 + ny^2 + (1-nz)^2)
- * loss_accum[0] += loss (atomic, one add per block); v_* are fully written. */
+ * loss_accum[0] += loss (atomic, one add per block); v_* are fully written.  v_out_img / v_out_depth / v_out_alpha (all
+ * zero for this loss) may be NULL: not written. */
 int gstex_image_loss(int img_height, int img_width, const float *out_texture, const float *out_reg,
                      const float *out_normal, const float *gt, float *loss_accum, float *v_out_img,
                      float *v_out_depth, float *v_out_reg, float *v_out_alpha, float *v_out_texture,
