@@ -314,10 +314,11 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, GSTEX_FWD_MINB) raster_for
             prefetch_texture_block(p.tex4, __float_as_int(q6.w), __float_as_int(q3.z), __float_as_int(q3.w));
         }
         const int nsurv = __all_sync(0xffffffffu, done) ? 0 : build_survivors<BLUR, !VIS>(S, 0, cnt, wr, p.mean2d, my_list, lane);
+        // this warp's mask word of the stage's first entry (only lane 0 stores; a NULL array keeps the pointer NULL)
+        uint32_t *__restrict__ mrow = (!VIS && p.masks && lane == 0) ? p.masks + (size_t)first * MASK_WARPS + warp : nullptr;
         // The survivor walk is warp-uniform: finished pixels stay in the loop (predicated off) so that the blend
         // decision of all 32 pixels is one ballot - the mask word the backward pass reads.
         for (int si = 0; si < nsurv; ++si) {
-            if (__all_sync(0xffffffffu, done)) break;
             const int i = my_list[si];
             const float4 *__restrict__ R = S + i * REC_PITCH;
             const float4 q0 = R[0], q1 = R[1], q2 = R[2], q3 = R[3];
@@ -332,8 +333,11 @@ __global__ void __launch_bounds__(RASTER_MAX_THREADS, GSTEX_FWD_MINB) raster_for
             done = done || next_T <= T_STOP;
             const bool blend = !done && !pair_skipped(pe);
             const unsigned bm = __ballot_sync(0xffffffffu, blend);
-            if (bm == 0u) continue;
-            if (!VIS && p.masks && lane == 0) p.masks[(size_t)(first + i) * MASK_WARPS + warp] = bm;
+            if (bm == 0u) {  // nobody blends: the only place where "every pixel of the warp is finished" can become true
+                if (__all_sync(0xffffffffu, done)) break;
+                continue;
+            }
+            if (mrow) mrow[(unsigned)i * MASK_WARPS] = bm;
             if (blend) {
                 const float4 q4 = R[4], q5 = R[5], q6 = R[6], q7 = R[7];
                 const float vis = pe.alpha * T;
