@@ -146,6 +146,15 @@ __device__ __forceinline__ void pair_terms(const RasterCommon &p, const Backward
     y = v_vis + (tv * tv * px.Sf0 - 2.f * tv * px.Sf1 + px.Sf2) * px.v_reg;
 }
 
+// red.global.add.v4.f32 of (x, y, z, 0) unless `w` is exactly zero - a predicated instruction, not a branch: the four
+// corner reductions of a pair otherwise compile to four divergent regions of 13 instructions each.
+__device__ __forceinline__ void red_add_v4_if_nonzero(float4 *addr, float x, float y, float z, float w) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.neu.f32 p, %4, 0f00000000;\n\t@p red.global.add.v4.f32 [%0], {%1, %2, %3, %5};\n\t}" ::"l"(addr),
+        "f"(x), "f"(y), "f"(z), "f"(w), "f"(0.f)
+        : "memory");
+}
+
 // Second half: given vis = alpha T_k and v_alpha, the texel-gradient reductions and the moment row (AccSlot order,
 // quad by quad; r[7] only with BLUR).
 template <bool C3, bool BLUR>
@@ -165,9 +174,8 @@ __device__ __forceinline__ void pair_rows(const RasterCommon &p, const BackwardI
         if (C3) {
             const float vv0 = vis * px.vt0, vv1 = vis * px.vt1, vv2 = vis * px.vt2;
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (tf.w[k] != 0.f)
-                    atomicAdd(o.vtex4 + tf.idx[k], make_float4(tf.w[k] * vv0, tf.w[k] * vv1, tf.w[k] * vv2, 0.f));
+            for (int k = 0; k < 4; ++k)  // texel indices are non-negative: unsigned scaling is one IMAD.WIDE
+                red_add_v4_if_nonzero(o.vtex4 + (unsigned)tf.idx[k], tf.w[k] * vv0, tf.w[k] * vv1, tf.w[k] * vv2, tf.w[k]);
         } else {
             const float *__restrict__ vtp = in.v_tex + (size_t)fl.C * px.pix;
             for (int c = 0; c < fl.C; ++c) {
