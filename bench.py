@@ -585,9 +585,11 @@ def run_e2e(args, scene, cams, mine, targets_host, dev, world, views):
                 t.grad = None
         return val
 
-    steps = max(3, min(args.steps, 10))
+    # enough steps that one slow one (allocator growth, a host hiccup) does not decide the figure: up to 40 single-view
+    # steps (0.2 s), up to 10 of the multi-view ones
+    steps = max(3, min(args.steps, 40 if len(order) <= 2 else 10))
     loader_steps = [0]
-    for _ in range(2):
+    for _ in range(3):
         one_step()
     loader.bytes_copied = 0
     read_pending()  # the warm-up's last loss: nothing of the warm-up is left to read inside the timed region
