@@ -162,6 +162,9 @@ class FusedTrainStep:
         # default priority: measured on C5 (8 views/step, 1 GPU) a high-priority side stream only moves time from its own
         # kernels into the rasterisers they displace (32.7 ms vs 32.4 ms per step)
         self.side = torch.cuda.Stream(device=dev)
+        # the exposed head of a step's first view (_prepare): SH colours + record packing / the binning chain
+        self.side2 = torch.cuda.Stream(device=dev)
+        self.side_hi = torch.cuda.Stream(device=dev, priority=-1)
 
     def _make_view_set(self, f32, i32):
         n, dev = self.n, self.dev
@@ -253,28 +256,53 @@ class FusedTrainStep:
         self._first_view = True
 
     def _prepare(self, v, viewmat: torch.Tensor, c2w: torch.Tensor, first: bool) -> None:
-        """Bandwidth-bound head of a view on the CURRENT stream: zero-fills, SH colours, project / AABB / count, fused tile
-        binning, record packing.  Records ``v.prep_done``."""
-        lib, s, p = self.lib, self._s(), self.p
+        """Head of a view, ordered after the CURRENT stream's work: SH colours, record packing (which also clears the
+        view's moment lines), project / AABB / count, fused tile binning.  Records ``v.prep_done`` on the current stream.
+
+        ``first`` (the step's first view: nothing else is running) splits the head into two independent chains on helper
+        streams - [SH colours -> packing] moves 0.8 GB at HBM speed, [project -> binning] is bound by L2 atomics, a one-CTA
+        scan and the per-tile sorts.  The binning chain gets the higher priority so that its small kernels do not queue
+        behind the thousands of CTAs of the two bandwidth kernels (C4: head 0.356 -> 0.329 ms).  The heads of later views
+        already run underneath the previous view's rasterisers; they stay one in-order chain (two more streams competing
+        with the rasterisers measured 0.8 % slower on 64 views)."""
+        lib, p = self.lib, self.p
         n, H, W, bw = self.n, self.H, self.W, self.bw
         fx, fy, cx, cy = self.intr
         P = lambda t: t.data_ptr()  # noqa: E731
-        if self.use_sh:
-            self._ck(lib.gstex_sh_colors_forward(n, self.sh_degree, self.sh_degree, P(p["means"]), P(c2w),
-                                                 P(p["sh_coeffs"]), P(v.colors), P(v.mask), s), "sh_colors_forward")
-        self._ck(lib.gstex_project_aabb_count(n, P(p["means"]), P(p["scales"]), self.glob_scale, P(p["quats"]), P(viewmat),
-                                              fx, fy, cx, cy, H, W, bw, P(v.centers), P(v.extents), P(v.depths),
-                                              P(v.nth), 0 if self.visible is None else P(self.visible), s),
-                 "project_aabb_count")
-        # fused tile binning: bucket by tile + per-tile shared-memory sort; the intersection count stays on the device
-        self._ck(lib.gstex_bin_tiles(n, P(v.centers), P(v.extents), P(v.depths), self.tiles_x, self.tiles_y, bw,
-                                     self.cap, P(v.ids_sorted), 0, P(v.tile_bins), P(v.num_isect),
-                                     P(self.max_count_seen), P(v.bin_temp), v.bin_temp.numel(), s), "bin_tiles")
-        self._ck(lib.gstex_pack_records(n, P(self.texture_dims), P(v.colors), P(p["opacities"]), P(p["means"]),
-                                        P(p["scales"]), self.glob_scale, P(p["quats"]), P(p["uv0"]), P(p["umap"]),
-                                        P(p["vmap"]), P(viewmat), P(c2w), fx, fy, cx, cy, P(v.recs), P(v.mean2d),
-                                        P(v.acc), s), "pack_records")  # also clears the view's moment lines
-        v.prep_done.record(torch.cuda.current_stream(self.dev))
+        cur = torch.cuda.current_stream(self.dev)
+
+        def colours_and_records(s):
+            if self.use_sh:
+                self._ck(lib.gstex_sh_colors_forward(n, self.sh_degree, self.sh_degree, P(p["means"]), P(c2w),
+                                                     P(p["sh_coeffs"]), P(v.colors), P(v.mask), s), "sh_colors_forward")
+            self._ck(lib.gstex_pack_records(n, P(self.texture_dims), P(v.colors), P(p["opacities"]), P(p["means"]),
+                                            P(p["scales"]), self.glob_scale, P(p["quats"]), P(p["uv0"]), P(p["umap"]),
+                                            P(p["vmap"]), P(viewmat), P(c2w), fx, fy, cx, cy, P(v.recs), P(v.mean2d),
+                                            P(v.acc), s), "pack_records")  # also clears the view's moment lines
+
+        def project_and_bin(s):
+            self._ck(lib.gstex_project_aabb_count(n, P(p["means"]), P(p["scales"]), self.glob_scale, P(p["quats"]),
+                                                  P(viewmat), fx, fy, cx, cy, H, W, bw, P(v.centers), P(v.extents),
+                                                  P(v.depths), P(v.nth), 0 if self.visible is None else P(self.visible), s),
+                     "project_aabb_count")
+            # fused tile binning: bucket by tile + per-tile sort; the intersection count stays on the device
+            self._ck(lib.gstex_bin_tiles(n, P(v.centers), P(v.extents), P(v.depths), self.tiles_x, self.tiles_y, bw,
+                                         self.cap, P(v.ids_sorted), 0, P(v.tile_bins), P(v.num_isect),
+                                         P(self.max_count_seen), P(v.bin_temp), v.bin_temp.numel(), s), "bin_tiles")
+
+        if first:
+            self.side2.wait_stream(cur)
+            self.side_hi.wait_stream(cur)
+            with torch.cuda.stream(self.side2):
+                colours_and_records(self._s())
+            with torch.cuda.stream(self.side_hi):
+                project_and_bin(self._s())
+            cur.wait_stream(self.side2)
+            cur.wait_stream(self.side_hi)
+        else:
+            colours_and_records(self._s())
+            project_and_bin(self._s())
+        v.prep_done.record(cur)
         self.launches += int(self.use_sh) + 1 + self._bin_launches + 1  # sh, project, binning, pack
 
     def _render(self, v, viewmat: torch.Tensor, c2w: torch.Tensor) -> Dict[str, torch.Tensor]:
