@@ -69,9 +69,8 @@ struct BwdWarpSmem {
     static constexpr int PITCH = BLUR ? 32 : 28;  // floats per moment row (28 used; 30 with BLUR)
     float4 rec[BWD_ECAP * REC_PITCH];          // packed records of the chunk's entries (quad_slot layout)
     float rows[32 * PITCH];            // moment rows of one dense iteration (D2)
-    float e_a[BWD_QCAP];               // alpha (D1) -> vis = alpha * T_k (scan)
-    float e_y[BWD_QCAP];               // y (D1) -> v_alpha (scan)
-    float e_gu[BWD_QCAP], e_gv[BWD_QCAP];  // d(texture term)/du, /dv per unit vis (D1)
+    float2 e_ay[BWD_QCAP];             // (alpha, y) (D1) -> (vis = alpha * T_k, v_alpha) (scan): one 8-byte access each way
+    float2 e_g[BWD_QCAP];              // d(texture term)/du, /dv per unit vis (D1)
     int row_gid[32];                   // Gaussian id of each row
     uint32_t sv_mask[BWD_BATCH];       // blend mask of each non-empty entry of the batch
 #ifndef GSTEX_BWD_NO_SVGID
@@ -431,10 +430,8 @@ __global__ void __launch_bounds__(BWD_CTA_WARPS * 32, GSTEX_BWD_MIN_CTAS) raster
                     eval_pair<BLUR>(q0, q1, q2, q3, qc, p.mean2d, pe);
                     float y, gu, gv;
                     pair_terms<C3>(p, in, fl, q3, q4, q5, q6, q7, pe, qc, px, y, gu, gv);
-                    W.e_a[e] = pe.alpha;
-                    W.e_y[e] = y;
-                    W.e_gu[e] = gu;
-                    W.e_gv[e] = gv;
+                    W.e_ay[e] = make_float2(pe.alpha, y);
+                    W.e_g[e] = make_float2(gu, gv);
                 }
             }
             __syncwarp();
@@ -475,10 +472,10 @@ __global__ void __launch_bounds__(BWD_CTA_WARPS * 32, GSTEX_BWD_MIN_CTAS) raster
                     } else {
                         if (mine) {
                             const int e = (int)W.ch_off[jj] + __popc(m & lt);
-                            const float alpha = W.e_a[e], d = W.e_y[e] - v_T_run;
+                            const float2 ay = W.e_ay[e];
+                            const float alpha = ay.x, d = ay.y - v_T_run;
                             T *= fast_rcp(1.f - alpha);  // transmittance in front of the entry (texture.cu:579-580)
-                            W.e_a[e] = alpha * T;
-                            W.e_y[e] = T * d;                        // v_alpha (texture.cu:650, :667)
+                            W.e_ay[e] = make_float2(alpha * T, T * d);  // (vis, v_alpha) (texture.cu:650, :667)
                             v_T_run = fmaf(alpha, d, v_T_run);       // alpha y + (1 - alpha) R  (texture.cu:651, :668-670)
                         }
                     }
@@ -503,8 +500,9 @@ __global__ void __launch_bounds__(BWD_CTA_WARPS * 32, GSTEX_BWD_MIN_CTAS) raster
                     eval_pair<BLUR>(q0, q1, q2, q3, qc, p.mean2d, pe);
                     const int idx = first + (int)W.sv_r[si0 - jloc];
                     float4 r[8];
-                    pair_rows<C3, BLUR>(p, in, o, fl, q0, q3, q4, q5, q6, pe, qc, px, W.e_a[e], W.e_y[e], W.e_gu[e],
-                                        W.e_gv[e], idx == px.dfinal && px.dfinal != -1, r);
+                    const float2 va = W.e_ay[e], g2 = W.e_g[e];
+                    pair_rows<C3, BLUR>(p, in, o, fl, q0, q3, q4, q5, q6, pe, qc, px, va.x, va.y, g2.x, g2.y,
+                                        idx == px.dfinal && px.dfinal != -1, r);
                     float4 *__restrict__ rowp = reinterpret_cast<float4 *>(W.rows + lane * PITCH);
 #pragma unroll
                     for (int k = 0; k < (BLUR ? 8 : 7); ++k) rowp[k] = r[k];
